@@ -1,0 +1,127 @@
+"""Seeded synthetic 2-D world, LiDAR scans and trajectories.
+
+Used by tests/ and bench.py to make the same inputs for the CUDA path and the CPU
+oracle. Pure numpy; no reference code involved (the reference ships no datasets,
+yag_slam/helpers.py:607-610).
+"""
+import numpy as np
+
+WORLD_SEED = 1234
+ROOM_W, ROOM_H = 40.0, 30.0
+
+
+class World:
+    def __init__(self, segments):
+        self.segments = np.ascontiguousarray(segments, dtype=np.float64)  # (S, 4): x1 y1 x2 y2
+
+
+def loop_path(n, step=0.25, half_w=12.0, half_h=7.0, radius=3.0, start_s=0.0):
+    """n poses (x, y, heading) on a closed rounded rectangle, arc-length step `step`."""
+    sx, sy = half_w - radius, half_h - radius
+    segs = [("L", (-sx, -half_h), 0.0, 2 * sx), ("A", (sx, -sy), -np.pi / 2, radius * np.pi / 2),
+            ("L", (half_w, -sy), np.pi / 2, 2 * sy), ("A", (sx, sy), 0.0, radius * np.pi / 2),
+            ("L", (sx, half_h), np.pi, 2 * sx), ("A", (-sx, sy), np.pi / 2, radius * np.pi / 2),
+            ("L", (-half_w, sy), -np.pi / 2, 2 * sy), ("A", (-sx, -sy), np.pi, radius * np.pi / 2)]
+    per = sum(s[3] for s in segs)
+    out = np.zeros((n, 3))
+    for i in range(n):
+        s = (start_s + i * step) % per
+        for kind, p0, ang, length in segs:
+            if s <= length:
+                if kind == "L":
+                    out[i] = (p0[0] + s * np.cos(ang), p0[1] + s * np.sin(ang), ang)
+                else:
+                    a = ang + s / radius
+                    out[i] = (p0[0] + radius * np.cos(a), p0[1] + radius * np.sin(a), a + np.pi / 2)
+                break
+            s -= length
+    out[:, 2] = (out[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    return out
+
+
+def make_world(seed=WORLD_SEED, n_pillars=24, keep_clear=None, clear_dist=1.2):
+    """Outer 40x30 m rectangle + axis-aligned rectangular pillars (side U[0.5,3])."""
+    rng = np.random.default_rng(seed)
+    hw, hh = ROOM_W / 2, ROOM_H / 2
+    segs = [(-hw, -hh, hw, -hh), (hw, -hh, hw, hh), (hw, hh, -hw, hh), (-hw, hh, -hw, -hh)]
+    if keep_clear is None:
+        keep_clear = loop_path(600, step=0.125)[:, :2]
+    placed = 0
+    while placed < n_pillars:
+        cx, cy = rng.uniform(-hw + 2, hw - 2), rng.uniform(-hh + 2, hh - 2)
+        w, h = rng.uniform(0.5, 3.0), rng.uniform(0.5, 3.0)
+        d = np.abs(keep_clear - np.array([cx, cy]))
+        if np.any((d[:, 0] < w / 2 + clear_dist) & (d[:, 1] < h / 2 + clear_dist)):
+            continue
+        x0, x1, y0, y1 = cx - w / 2, cx + w / 2, cy - h / 2, cy + h / 2
+        segs += [(x0, y0, x1, y0), (x1, y0, x1, y1), (x1, y1, x0, y1), (x0, y1, x0, y0)]
+        placed += 1
+    return World(np.array(segs))
+
+
+def cast_scan(world, pose, n_beams, noise_rng=None, noise=0.01, max_range=30.0, min_angle=-np.pi,
+              angle_increment=None):
+    """Analytic ray-segment ranges in float64 (+ optional N(0, noise)); all finite."""
+    if angle_increment is None:
+        angle_increment = 2 * np.pi / n_beams
+    x, y, h = pose
+    ang = h + min_angle + np.arange(n_beams) * angle_increment
+    dx, dy = np.cos(ang)[:, None], np.sin(ang)[:, None]
+    s = world.segments
+    ex, ey = (s[:, 2] - s[:, 0])[None, :], (s[:, 3] - s[:, 1])[None, :]
+    wx, wy = (s[:, 0] - x)[None, :], (s[:, 1] - y)[None, :]
+    den = dx * ey - dy * ex
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (wx * ey - wy * ex) / den
+        u = (wx * dy - wy * dx) / den
+    ok = (np.abs(den) > 1e-12) & (t > 1e-9) & (u >= 0.0) & (u <= 1.0)
+    t = np.where(ok, t, np.inf)
+    r = t.min(axis=1)
+    r = np.where(np.isfinite(r), r, max_range)
+    if noise_rng is not None and noise > 0:
+        r = r + noise_rng.normal(0.0, noise, size=n_beams)
+    return np.clip(r, 0.06, max_range)
+
+
+def laser_params(n_beams, range_threshold=20.0):
+    """(min_angle, max_angle, angle_increment, min_range, max_range, range_threshold)."""
+    inc = 2 * np.pi / n_beams
+    return (-np.pi, -np.pi + inc * (n_beams - 1), inc, 0.05, 30.0, range_threshold)
+
+
+def noisy_odometry(poses, rng, sigma_xy=0.02, sigma_t=0.01):
+    """odom = truth + cumulative N(0, sigma) drift (SURVEY 8d cfg 2)."""
+    n = len(poses)
+    drift = np.cumsum(np.column_stack([rng.normal(0, sigma_xy, n), rng.normal(0, sigma_xy, n),
+                                       rng.normal(0, sigma_t, n)]), axis=0)
+    drift[0] = 0
+    out = poses + drift
+    out[:, 2] = (out[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    return out
+
+
+def occupancy_image(world, resolution=0.05, pad=1.0, unknown_outside=True):
+    """Rasterise the world into the reference's map convention (0 occupied, 200 unknown,
+    255 free; ros1/slam_node_ros1:199-202). Returns (img uint8 HxW, origin_xy)."""
+    hw, hh = ROOM_W / 2 + pad, ROOM_H / 2 + pad
+    w, h = int(round(2 * hw / resolution)), int(round(2 * hh / resolution))
+    img = np.full((h, w), 200 if unknown_outside else 255, dtype=np.uint8)
+    x0, y0 = -hw, -hh
+    ix0, ix1 = int(round((-ROOM_W / 2 - x0) / resolution)), int(round((ROOM_W / 2 - x0) / resolution))
+    iy0, iy1 = int(round((-ROOM_H / 2 - y0) / resolution)), int(round((ROOM_H / 2 - y0) / resolution))
+    img[iy0:iy1 + 1, ix0:ix1 + 1] = 255
+    for (ax, ay, bx, by) in world.segments:
+        n = int(np.hypot(bx - ax, by - ay) / (resolution * 0.5)) + 2
+        xs, ys = np.linspace(ax, bx, n), np.linspace(ay, by, n)
+        img[np.clip(np.round((ys - y0) / resolution).astype(int), 0, h - 1),
+            np.clip(np.round((xs - x0) / resolution).astype(int), 0, w - 1)] = 0
+    # pillar interiors are unknown (never observed)
+    segs = world.segments[4:].reshape(-1, 4, 4)
+    for p in segs:
+        xa, xb = p[:, [0, 2]].min(), p[:, [0, 2]].max()
+        ya, yb = p[:, [1, 3]].min(), p[:, [1, 3]].max()
+        i0, i1 = int(round((xa - x0) / resolution)) + 1, int(round((xb - x0) / resolution))
+        j0, j1 = int(round((ya - y0) / resolution)) + 1, int(round((yb - y0) / resolution))
+        if i1 > i0 and j1 > j0:
+            img[j0:j1, i0:i1] = 200
+    return img, (x0, y0)
