@@ -1,0 +1,144 @@
+/*
+ * ysm.h -- C ABI of the B200-native correlative scan matcher (libysm_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of safijari/yag-slam: Karto's
+ * ScanMatcher::MatchScan behind
+ *     yag_slam/scan_matching.py:40-42   Scan2DMatcherCpp.match_scan
+ *       -> karto_scanmatcher.Wrapper.match_scan(query._scan, [b._scan...], penalty, do_fine)
+ * plus the numba ray-walk yag_slam/raytracing.py:63-92.
+ *
+ * The reference's boundary is a pybind11 module (external wheel
+ * karto_scanmatcher==1.0.0, reference setup.py:46); it has no C ABI today. These entry
+ * points are what a maintainer would bind instead (ctypes stub: INTEGRATION.md).
+ * Plain pointers and sizes only; no exceptions cross the ABI; every function
+ * returns 0 on success or a negative YSM_E* code (text via ysm_last_error).
+ * There is NO CPU fallback: ysm_create fails if no CUDA device is usable.
+ */
+#ifndef YSM_H_
+#define YSM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YSM_OK 0
+#define YSM_EINVAL (-1)   /* bad argument / parameter out of bounds (e.g. smear deviation) */
+#define YSM_ECUDA (-2)    /* CUDA runtime error */
+#define YSM_ENOMEM (-3)   /* workspace does not fit */
+#define YSM_EMATCH (-4)   /* "Unable to find best position" (Karto runtime_error) */
+#define YSM_EUNSUP (-5)   /* parameter regime not supported yet */
+
+/* Replaces karto_scanmatcher.ScanMatcherConfig (attribute names: reference
+ * yag_slam/helpers.py:339-351; consumed by ScanMatcher::Create).
+ * minimum_distance_penalty is Karto's fixed default 0.5 (not in yag's config). */
+typedef struct ysm_params {
+  double search_size;
+  double resolution;
+  double smear_deviation;
+  double range_threshold;
+  double coarse_search_angle_offset;
+  double coarse_angle_resolution;
+  double fine_search_angle_resolution;
+  double distance_variance_penalty;
+  double angle_variance_penalty;
+  double minimum_angle_penalty;
+  double minimum_distance_penalty;
+  int32_t use_response_expansion;
+  int32_t max_slots;       /* correlation grids kept resident in HBM at once; 0 = auto */
+  int64_t max_grid_bytes;  /* HBM budget for those grids; 0 = 16 GiB */
+} ysm_params;
+
+/* Derived sizes (ScanMatcher::Create / CorrelationGrid::CreateGrid). */
+typedef struct ysm_dims {
+  int32_t side, margin, roi, half_kernel, kernel_size, border;
+  int32_t width, height, stride, slots;
+  int64_t grid_bytes;
+} ysm_dims;
+
+/* One batch of independent MatchScan calls over a pool of scans.
+ * A scan is its filtered world-frame point readings (what Karto's
+ * LocalizedRangeScan::GetPointReadings() caches) -- compute them with
+ * ysm_point_readings. Match i matches pool scan query_scan[i], whose sensor pose is
+ * query_pose[i], against pool scans base_idx[base_ptr[i] .. base_ptr[i+1]). */
+typedef struct ysm_batch {
+  int32_t n_matches;
+  int32_t n_scans;
+  int64_t n_points;            /* total points in the pool */
+  const double *pool_xy;       /* [n_points][2]; host, or device if pool_on_device */
+  const int32_t *scan_start;   /* [n_scans]  host */
+  const int32_t *scan_count;   /* [n_scans]  host */
+  const int32_t *query_scan;   /* [n_matches] host */
+  const double *query_pose;    /* [n_matches][3] x, y, heading; host */
+  const int32_t *base_ptr;     /* [n_matches+1] host */
+  const int32_t *base_idx;     /* [base_ptr[n_matches]] host */
+  int32_t do_penalize;         /* Wrapper.match_scan arg 3 */
+  int32_t do_refine;           /* Wrapper.match_scan arg 4 */
+  int32_t pool_on_device;      /* 1: pool_xy is a device pointer already resident in HBM */
+  int32_t _pad;
+} ysm_batch;
+
+/* 128-byte result record (what Wrapper.match_scan returns: response, best_pose, covariance). */
+typedef struct ysm_result {
+  double response;
+  double x, y, heading;
+  double cov[9];          /* row-major 3x3 */
+  int32_t n_passes;       /* CorrelateScan calls made (coarse + expansions + fine) */
+  int32_t n_ties;         /* poses averaged in the last pass */
+  int32_t status;         /* YSM_OK or YSM_EMATCH */
+  int32_t _pad;
+  double _reserved;       /* pads the record to 128 bytes */
+} ysm_result;
+
+typedef struct ysm_handle ysm_handle;
+
+/* Replaces Wrapper(config) -> ScanMatcher::Create: allocates the correlation-grid slots,
+ * kernel and workspaces once; reused by every call (reference ownership rule). */
+int ysm_create(const ysm_params *params, int device, ysm_handle **out);
+void ysm_destroy(ysm_handle *h);
+const char *ysm_last_error(const ysm_handle *h); /* h may be NULL: last create error */
+int ysm_get_dims(const ysm_handle *h, ysm_dims *out);
+
+/* Replaces Wrapper.match_scan (ScanMatcher::MatchScan), batched. `out` is host memory,
+ * [n_matches]. `stream` is a cudaStream_t (0 = default). Synchronous w.r.t. the host:
+ * results are valid on return. Not re-entrant per handle (as the reference matcher). */
+int ysm_match_batch(ysm_handle *h, const ysm_batch *batch, ysm_result *out, void *stream);
+
+/* Replaces LocalizedRangeScan::Update (point readings; python twin
+ * yag_slam/helpers.py:58-68): host libm, bit-identical to the CPU reference.
+ * out_xy has room for n pairs; *n_out receives the number kept. */
+int ysm_point_readings(const double *ranges, int32_t n, double min_angle,
+                       double angular_resolution, double min_range, double range_threshold,
+                       double x, double y, double heading, double *out_xy, int32_t *n_out);
+
+/* Replaces yag_slam/raytracing.py:90-92 run_raytracing_sweep for n_starts start cells.
+ * img: uint8 [h][w] (host, or device if img_on_device); angles in degrees (float64);
+ * starts_xy [n_starts][2]; out (host) [n_starts][n_angles][5] float32 rows
+ * start.x, start.y, end.x, end.y, length. */
+int ysm_raytrace(const uint8_t *img, int32_t h, int32_t w, int32_t img_on_device,
+                 const double *angles_deg, int32_t n_angles, const double *starts_xy,
+                 int32_t n_starts, float *out, int device, void *stream);
+
+/* ---- introspection for parity tests (not part of the reference surface) ---- */
+#define YSM_DEBUG_KEEP_GRIDS 1 /* do not clear the slot grids after a batch */
+int ysm_set_debug(ysm_handle *h, int32_t flags);
+/* copies the correlation grid built for match `i` of the last batch (stride*height bytes) */
+int ysm_debug_copy_grid(ysm_handle *h, int32_t match, uint8_t *out_host);
+/* copies the smear kernel (kernel_size^2 bytes) */
+int ysm_debug_copy_kernel(ysm_handle *h, uint8_t *out_host);
+/* copies the COARSE lookup-offset table of match `i` of the last batch: [n_angles][n_points] */
+int ysm_debug_copy_offsets(ysm_handle *h, int32_t match, int32_t *out_host, int32_t *n_angles,
+                           int32_t *n_points);
+/* number of kernels launched by this handle since creation */
+int64_t ysm_launch_count(const ysm_handle *h);
+/* device milliseconds spent in the sweep kernel (coarse lattice) during the last batch,
+ * from CUDA events on the call's stream (only when YSM_DEBUG_TIME_KERNELS is set) */
+#define YSM_DEBUG_TIME_KERNELS 2
+int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, double *reduce_ms,
+                       double *total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YSM_H_ */

@@ -1,0 +1,110 @@
+"""ctypes binding of the C ABI in include/ysm.h (libysm_b200.so). No CPU fallback: loading
+fails loudly if the CUDA library has not been built."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import SO_PATH
+
+PARAM_FIELDS = [
+    "search_size", "resolution", "smear_deviation", "range_threshold",
+    "coarse_search_angle_offset", "coarse_angle_resolution", "fine_search_angle_resolution",
+    "distance_variance_penalty", "angle_variance_penalty", "minimum_angle_penalty",
+    "minimum_distance_penalty",
+]
+
+YSM_OK, YSM_EINVAL, YSM_ECUDA, YSM_ENOMEM, YSM_EMATCH, YSM_EUNSUP = 0, -1, -2, -3, -4, -5
+DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS = 1, 2
+
+
+class YsmParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in PARAM_FIELDS] + [
+        ("use_response_expansion", C.c_int32), ("max_slots", C.c_int32), ("max_grid_bytes", C.c_int64)]
+
+
+class YsmDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("side", "margin", "roi", "half_kernel", "kernel_size", "border",
+                                         "width", "height", "stride", "slots")] + [("grid_bytes", C.c_int64)]
+
+
+class YsmBatch(C.Structure):
+    _fields_ = [
+        ("n_matches", C.c_int32), ("n_scans", C.c_int32), ("n_points", C.c_int64),
+        ("pool_xy", C.c_void_p), ("scan_start", C.c_void_p), ("scan_count", C.c_void_p),
+        ("query_scan", C.c_void_p), ("query_pose", C.c_void_p), ("base_ptr", C.c_void_p),
+        ("base_idx", C.c_void_p), ("do_penalize", C.c_int32), ("do_refine", C.c_int32),
+        ("pool_on_device", C.c_int32), ("_pad", C.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([("response", "<f8"), ("x", "<f8"), ("y", "<f8"), ("heading", "<f8"),
+                         ("cov", "<f8", (9,)), ("n_passes", "<i4"), ("n_ties", "<i4"),
+                         ("status", "<i4"), ("_pad", "<i4"), ("_reserved", "<f8")])
+assert RESULT_DTYPE.itemsize == 128
+
+EXPORTS = [
+    "ysm_create", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
+    "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
+    "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libysm_b200.so (raises if it is missing -- there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            "libysm_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
+    L.ysm_create.restype = C.c_int
+    L.ysm_create.argtypes = [C.POINTER(YsmParams), C.c_int, C.POINTER(vp)]
+    L.ysm_destroy.restype = None
+    L.ysm_destroy.argtypes = [vp]
+    L.ysm_last_error.restype = C.c_char_p
+    L.ysm_last_error.argtypes = [vp]
+    L.ysm_get_dims.restype = C.c_int
+    L.ysm_get_dims.argtypes = [vp, C.POINTER(YsmDims)]
+    L.ysm_match_batch.restype = C.c_int
+    L.ysm_match_batch.argtypes = [vp, C.POINTER(YsmBatch), vp, vp]
+    L.ysm_point_readings.restype = C.c_int
+    L.ysm_point_readings.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, f64, vp, C.POINTER(i32)]
+    L.ysm_raytrace.restype = C.c_int
+    L.ysm_raytrace.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, C.c_int, vp]
+    L.ysm_set_debug.restype = C.c_int
+    L.ysm_set_debug.argtypes = [vp, i32]
+    L.ysm_debug_copy_grid.restype = C.c_int
+    L.ysm_debug_copy_grid.argtypes = [vp, i32, vp]
+    L.ysm_debug_copy_kernel.restype = C.c_int
+    L.ysm_debug_copy_kernel.argtypes = [vp, vp]
+    L.ysm_debug_copy_offsets.restype = C.c_int
+    L.ysm_debug_copy_offsets.argtypes = [vp, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.ysm_launch_count.restype = C.c_int64
+    L.ysm_launch_count.argtypes = [vp]
+    L.ysm_last_kernel_ms.restype = C.c_int
+    L.ysm_last_kernel_ms.argtypes = [vp] + [C.POINTER(f64)] * 4
+    _lib = L
+    return L
+
+
+def last_error(handle=None):
+    s = lib().ysm_last_error(handle)
+    return s.decode("utf-8", "replace") if s else ""
+
+
+def point_readings(ranges, min_angle, angular_resolution, min_range, range_threshold, x, y, heading):
+    """LocalizedRangeScan::Update (host libm inside the library): (k, 2) float64 world points."""
+    r = np.ascontiguousarray(ranges, dtype=np.float64)
+    out = np.empty((max(1, len(r)), 2), dtype=np.float64)
+    n = C.c_int32(0)
+    rc = lib().ysm_point_readings(r.ctypes.data, len(r), float(min_angle), float(angular_resolution),
+                                  float(min_range), float(range_threshold), float(x), float(y),
+                                  float(heading), out.ctypes.data, C.byref(n))
+    if rc != YSM_OK:
+        raise RuntimeError("ysm_point_readings failed (%d)" % rc)
+    return out[:n.value].copy()

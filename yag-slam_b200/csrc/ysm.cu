@@ -1,0 +1,1016 @@
+// ysm.cu -- host runtime + C ABI (include/ysm.h) of the B200-native correlative scan matcher.
+//
+// Host side of ScanMatcher::MatchScan: it owns the correlation-grid slots and
+// workspaces, schedules CorrelateScan passes (coarse -> response expansion -> fine) over a
+// wave of independent matches, evaluates every transcendental (cos/sin/atan2/exp/hypot) with
+// libm so results are bit-identical to the CPU reference, and launches the sm_100a kernels in
+// ysm_kernels.cuh for all of the gather/reduce work. There is no CPU compute fallback.
+#include "../../include/ysm.h"
+#include "ysm_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace ysm;
+
+static_assert(sizeof(ysm_result) == 128, "ysm_result must be a 128-byte record");
+
+#define KT_PI 3.14159265358979323846
+#define KT_2PI 6.28318530717958647692
+#define KT_PI_180 0.01745329251994329577
+#define KT_TOLERANCE 1e-06
+#define MAX_VARIANCE 500.0
+
+static std::string g_create_error;
+
+namespace {
+
+inline double h_round(double v) { return v >= 0.0 ? floor(v + 0.5) : ceil(v - 0.5); }
+inline bool h_double_equal(double a, double b) { return fabs(a - b) <= KT_TOLERANCE; }
+inline double h_square(double v) { return v * v; }
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+double h_normalize_angle(double angle) {
+  while (angle < -KT_PI) {
+    if (angle < -KT_2PI) angle += (uint32_t)(angle / -KT_2PI) * KT_2PI;
+    else angle += KT_2PI;
+  }
+  while (angle > KT_PI) {
+    if (angle > KT_2PI) angle -= (uint32_t)(angle / KT_2PI) * KT_2PI;
+    else angle -= KT_2PI;
+  }
+  return angle;
+}
+
+double h_normalize_angle_difference(double minuend, double subtrahend) {
+  while (minuend - subtrahend < -KT_PI) minuend += KT_2PI;
+  while (minuend - subtrahend > KT_PI) minuend -= KT_2PI;
+  return minuend;
+}
+
+// growable device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// growable pinned host buffer
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct TableKey {
+  int q;
+  uint64_t b[6];  // pose x,y,h; angle centre, offset, res (bit patterns)
+  bool operator==(const TableKey& o) const { return q == o.q && memcmp(b, o.b, sizeof(b)) == 0; }
+};
+struct TableKeyHash {
+  size_t operator()(const TableKey& k) const {
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)k.q;
+    for (int i = 0; i < 6; i++) {
+      h ^= k.b[i];
+      h *= 1099511628211ull;
+    }
+    return (size_t)h;
+  }
+};
+inline uint64_t dbits(double d) {
+  uint64_t u;
+  memcpy(&u, &d, 8);
+  return u;
+}
+
+// host state of one match while its passes are scheduled
+struct MatchState {
+  int idx;        // index in the batch
+  int slot;       // grid slot == index in the wave
+  int q;          // pool scan id of the query
+  int P;          // query point readings
+  double pose[3];
+  double gox, goy;
+  int stage;      // 0 coarse, 1..3 expansion k, 4 fine, 5 done
+  double angle_offset_cur;
+  double mean[3];
+  double cov[9];
+  double best;
+  int n_passes, n_ties;
+  int status;
+  // current pass
+  int pass_id;
+};
+
+struct PassHost {
+  int match;  // index into wave states
+  bool fine;
+  double cx, cy, ch, offx, offy, resx, resy, angle_offset, angle_res;
+  int nA, nX, nY;
+  int ang_off;
+};
+
+}  // namespace
+
+struct ysm_handle {
+  ysm_params prm;
+  int device = 0;
+  GridC g;
+  PenaltyC pen;
+  int side = 0, margin = 0;
+  double res_eff = 0.0;
+  int slots = 0;
+  uint8_t* d_grids = nullptr;
+  uint8_t* d_kernel = nullptr;
+  std::vector<uint8_t> h_kernel;
+  std::string err;
+  int debug = 0;
+  int64_t launches = 0;
+  int num_sms = 148;
+  // device workspaces
+  DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
+  DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
+  PinBuf h_blob, h_outs, h_angsums;
+  // last-batch debug info
+  std::vector<int> last_slot_of_match;    // match -> slot (only for the last wave)
+  std::vector<int> last_coarse_table_off; // match -> offsets element offset of its first coarse table
+  std::vector<int> last_coarse_nA, last_coarse_P, last_coarse_Ppad;
+  int last_wave_begin = 0, last_wave_end = 0;
+  bool grids_dirty = false;
+  std::vector<MatchDev> dirty_matches;  // for deferred clear in KEEP_GRIDS mode
+  // timing
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
+};
+
+#define CK(call)                                                                     \
+  do {                                                                               \
+    cudaError_t _e = (call);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+      return YSM_ECUDA;                                                              \
+    }                                                                                \
+  } while (0)
+
+static int fail(ysm_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+extern "C" const char* ysm_last_error(const ysm_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+// CorrelationGrid::CalculateKernel (python twin yag_slam/helpers.py:86-97)
+static int calculate_kernel(double res_eff, double smear, std::vector<uint8_t>& out, int& half, int& K) {
+  if (!(smear >= 0.5 * res_eff && smear <= 10 * res_eff)) return -1;
+  half = (int)h_round(2.0 * smear / res_eff);
+  K = 2 * half + 1;
+  out.assign((size_t)K * K, 0);
+  const int hk = K / 2;
+  for (int i = -hk; i <= hk; i++) {
+    for (int j = -hk; j <= hk; j++) {
+      double d = hypot(i * res_eff, j * res_eff);
+      double z = exp(-0.5 * pow(d / smear, 2));
+      uint32_t kv = (uint32_t)h_round(z * 100);
+      out[(size_t)(i + hk) + (size_t)K * (j + hk)] = (uint8_t)kv;
+    }
+  }
+  return 0;
+}
+
+extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
+  if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
+  *out = nullptr;
+  if (!(p->resolution > 0) || !(p->search_size > 0) || p->smear_deviation < 0 || !(p->range_threshold > 0))
+    return fail(nullptr, YSM_EINVAL, "invalid matcher parameters");
+  if (!(p->coarse_angle_resolution > 0) || !(p->fine_search_angle_resolution > 0) ||
+      !(p->coarse_search_angle_offset > 0))
+    return fail(nullptr, YSM_EINVAL, "angle offsets/resolutions must be positive");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, YSM_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, YSM_EINVAL, "bad device index");
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return fail(nullptr, YSM_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+
+  ysm_handle* h = new ysm_handle();
+  h->prm = *p;
+  h->device = device;
+  // ScanMatcher::Create sizing
+  h->side = (int)(uint32_t)(h_round(p->search_size / p->resolution) + 1);
+  h->margin = (int)(uint32_t)ceil(p->range_threshold / p->resolution);
+  GridC& g = h->g;
+  g.roi = h->side + 2 * h->margin;
+  g.border = (int)h_round(2.0 * p->smear_deviation / p->resolution) + 1;
+  g.width = g.roi + 2 * g.border;
+  g.height = g.width;
+  g.stride = align_up(g.width, 8);
+  g.stride4 = g.stride / 4;
+  g.scale = 1.0 / p->resolution;
+  h->res_eff = 1.0 / g.scale;
+  const long long dsz = (long long)g.stride * g.height;
+  if (dsz > 0x7fffffffLL || g.width > 65535) {
+    delete h;
+    return fail(nullptr, YSM_EUNSUP, "correlation grid too large (>= 2 GiB or > 65535 cells wide)");
+  }
+  g.data_size = (int)dsz;
+  g.grid_bytes = (dsz + 255) / 256 * 256;
+  if (calculate_kernel(h->res_eff, p->smear_deviation, h->h_kernel, g.half_kernel, g.K) != 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "Mapper Error:  Smear deviation too small:  Must be between %g and %g",
+             0.5 * h->res_eff, 10 * h->res_eff);
+    delete h;
+    return fail(nullptr, YSM_EINVAL, buf);
+  }
+  if (g.half_kernel + 1 > g.border) {
+    delete h;
+    return fail(nullptr, YSM_EUNSUP, "kernel larger than the grid border");
+  }
+  // The parallel smear relies on the kernel being 100 only at its centre; when
+  // smear_deviation >= ~9.99 * resolution Karto's "cell already occupied -> skip" test makes
+  // the result depend on point order, which the scatter kernel does not reproduce yet.
+  {
+    int hot = 0;
+    for (uint8_t v : h->h_kernel) hot += (v == 100);
+    if (hot != 1) {
+      delete h;
+      return fail(nullptr, YSM_EUNSUP,
+                  "smear_deviation >= ~9.99*resolution (kernel has several 100-valued taps) is not supported yet");
+    }
+  }
+  g.Wk = (g.K + 6) / 4;
+  h->pen.distance_variance_penalty = p->distance_variance_penalty;
+  h->pen.angle_variance_penalty = p->angle_variance_penalty;
+  h->pen.minimum_distance_penalty = p->minimum_distance_penalty;
+  h->pen.minimum_angle_penalty = p->minimum_angle_penalty;
+
+  long long budget = p->max_grid_bytes > 0 ? p->max_grid_bytes : (16LL << 30);
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if ((long long)free_b / 2 < budget) budget = (long long)free_b / 2;
+  long long slots = budget / g.grid_bytes;
+  if (p->max_slots > 0 && slots > p->max_slots) slots = p->max_slots;
+  if (slots > 8192) slots = 8192;
+  if (slots < 1) {
+    delete h;
+    return fail(nullptr, YSM_ENOMEM, "not enough device memory for one correlation grid");
+  }
+  h->slots = (int)slots;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  e = cudaMalloc((void**)&h->d_grids, (size_t)slots * g.grid_bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->d_grids, 0, (size_t)slots * g.grid_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_kernel, h->h_kernel.size());
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_kernel, h->h_kernel.data(), h->h_kernel.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    h->ev_ok = true;
+    for (int i = 0; i < 8; i++)
+      if (cudaEventCreate(&h->ev[i]) != cudaSuccess) h->ev_ok = false;
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
+    if (h->d_grids) cudaFree(h->d_grids);
+    if (h->d_kernel) cudaFree(h->d_kernel);
+    delete h;
+    return fail(nullptr, YSM_ECUDA, msg);
+  }
+  *out = h;
+  return YSM_OK;
+}
+
+extern "C" void ysm_destroy(ysm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->d_grids) cudaFree(h->d_grids);
+  if (h->d_kernel) cudaFree(h->d_kernel);
+  DevBuf* bufs[] = {&h->d_pool, &h->d_scan_start, &h->d_scan_count, &h->d_base_idx, &h->d_matches,
+                    &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_tables, &h->d_passes,
+                    &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
+                    &h->d_angsums, &h->d_blob};
+  for (DevBuf* b : bufs) b->release();
+  h->h_blob.release();
+  h->h_outs.release();
+  h->h_angsums.release();
+  if (h->ev_ok)
+    for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+  delete h;
+}
+
+extern "C" int ysm_get_dims(const ysm_handle* h, ysm_dims* out) {
+  if (!h || !out) return YSM_EINVAL;
+  out->side = h->side; out->margin = h->margin; out->roi = h->g.roi;
+  out->half_kernel = h->g.half_kernel; out->kernel_size = h->g.K; out->border = h->g.border;
+  out->width = h->g.width; out->height = h->g.height; out->stride = h->g.stride;
+  out->slots = h->slots; out->grid_bytes = h->g.data_size;
+  return YSM_OK;
+}
+
+extern "C" int ysm_set_debug(ysm_handle* h, int32_t flags) {
+  if (!h) return YSM_EINVAL;
+  h->debug = flags;
+  return YSM_OK;
+}
+
+extern "C" int64_t ysm_launch_count(const ysm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int ysm_last_kernel_ms(const ysm_handle* h, double* sweep_ms, double* build_ms,
+                                  double* reduce_ms, double* total_ms) {
+  if (!h) return YSM_EINVAL;
+  if (sweep_ms) *sweep_ms = h->t_sweep;
+  if (build_ms) *build_ms = h->t_build;
+  if (reduce_ms) *reduce_ms = h->t_reduce;
+  if (total_ms) *total_ms = h->t_total;
+  return YSM_OK;
+}
+
+// LocalizedRangeScan::Update
+extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_angle,
+                                  double angular_resolution, double min_range,
+                                  double range_threshold, double x, double y, double heading,
+                                  double* out_xy, int32_t* n_out) {
+  if (!ranges || !out_xy || !n_out || n < 0) return YSM_EINVAL;
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    const double r = ranges[i];
+    if (!(r >= min_range && r <= range_threshold)) continue;
+    const double angle = heading + min_angle + (double)(uint32_t)i * angular_resolution;
+    out_xy[2 * k] = x + (r * cos(angle));
+    out_xy[2 * k + 1] = y + (r * sin(angle));
+    k++;
+  }
+  *n_out = k;
+  return YSM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// clear the footprint of a set of matches (wave) -- the grids return to all-zero
+static int clear_wave(ysm_handle* h, const MatchDev* d_matches, int n, cudaStream_t st) {
+  if (n <= 0) return YSM_OK;
+  const GridC& g = h->g;
+  const size_t smem = (size_t)4 * g.K * g.Wk * 4;
+  int chunks = std::max(1, std::min(64, (h->num_sms * 8 + n - 1) / n));
+  dim3 grid(chunks, n);
+  k_stamp<<<grid, 256, smem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p, (const int*)h->d_cellcount.p,
+                                    h->d_kernel, h->d_grids, 1);
+  h->launches++;
+  return YSM_OK;
+}
+
+static void finalize_positional(const ysm_handle* h, const PassHost& ph, const PassOut& po, double* cov) {
+  // ComputePositionalCovariance tail
+  memset(cov, 0, 9 * sizeof(double));
+  cov[0] = cov[4] = cov[8] = 1.0;
+  const double best = po.best;
+  if (best < KT_TOLERANCE) {
+    cov[0] = MAX_VARIANCE;
+    cov[4] = MAX_VARIANCE;
+    cov[8] = 4 * h_square(ph.angle_res);
+    return;
+  }
+  if (po.norm > KT_TOLERANCE) {
+    double vxx = po.axx / po.norm, vxy = po.axy / po.norm, vyy = po.ayy / po.norm;
+    const double vthth = 4 * h_square(ph.angle_res);
+    const double min_vxx = 0.1 * h_square(ph.resx);
+    const double min_vyy = 0.1 * h_square(ph.resy);
+    vxx = vxx > min_vxx ? vxx : min_vxx;
+    vyy = vyy > min_vyy ? vyy : min_vyy;
+    const double mult = 1.0 / best;
+    cov[0] = vxx * mult;
+    cov[1] = vxy * mult;
+    cov[3] = vxy * mult;
+    cov[4] = vyy * mult;
+    cov[8] = vthth;
+  }
+  if (h_double_equal(cov[0], 0.0)) cov[0] = MAX_VARIANCE;
+  if (h_double_equal(cov[4], 0.0)) cov[4] = MAX_VARIANCE;
+}
+
+static void finalize_angular(const PassHost& ph, const PassOut& po, double heading, const int* angsums,
+                             int P, double* cov) {
+  // ComputeAngularCovariance; the per-angle GetResponse sums come from the GPU
+  const double best_angle = h_normalize_angle_difference(heading, ph.ch);
+  const double start_angle = ph.ch - ph.angle_offset;
+  double norm = 0.0, acc = 0.0;
+  const double denom = (double)((uint32_t)P * 100u);
+  for (int a = 0; a < ph.nA; a++) {
+    const double angle = start_angle + (double)(uint32_t)a * ph.angle_res;
+    double response = (double)angsums[a];
+    response /= denom;
+    if (response >= (po.best - 0.1)) {
+      norm += response;
+      acc += (h_square(angle - best_angle) * response);
+    }
+  }
+  if (norm > KT_TOLERANCE) {
+    if (acc < KT_TOLERANCE) acc = h_square(ph.angle_res);
+    acc /= norm;
+  } else {
+    acc = 1000 * h_square(ph.angle_res);
+  }
+  cov[8] = acc;
+}
+
+static inline int n_steps(double off, double res) { return (int)(uint32_t)(h_round(off * 2.0 / res) + 1); }
+
+// --------------------------------------------------------------------------------------------
+extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
+  if (!h || !b || !out) return YSM_EINVAL;
+  if (b->n_matches < 0 || b->n_scans < 0) return fail(h, YSM_EINVAL, "negative sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const GridC& g = h->g;
+  const bool timing = (h->debug & YSM_DEBUG_TIME_KERNELS) && h->ev_ok;
+  h->t_sweep = h->t_build = h->t_reduce = h->t_total = 0.0;
+  if (b->n_matches == 0) return YSM_OK;
+
+  // deferred clear from a previous KEEP_GRIDS batch
+  if (h->grids_dirty) {
+    clear_wave(h, (const MatchDev*)h->d_matches.p, (int)h->dirty_matches.size(), st);
+    h->grids_dirty = false;
+    h->dirty_matches.clear();
+  }
+
+  // validate + sizes
+  int pmax = 1;
+  for (int s = 0; s < b->n_scans; s++) {
+    if (b->scan_count[s] < 0 || b->scan_start[s] < 0 ||
+        (int64_t)b->scan_start[s] + b->scan_count[s] > b->n_points)
+      return fail(h, YSM_EINVAL, "scan range outside the point pool");
+    pmax = std::max(pmax, b->scan_count[s]);
+  }
+  if (pmax > 16384) return fail(h, YSM_EUNSUP, "more than 16384 point readings in one scan");
+  for (int i = 0; i < b->n_matches; i++) {
+    if (b->query_scan[i] < 0 || b->query_scan[i] >= b->n_scans) return fail(h, YSM_EINVAL, "bad query scan index");
+    if (b->base_ptr[i + 1] < b->base_ptr[i]) return fail(h, YSM_EINVAL, "base_ptr not monotone");
+    for (int k = b->base_ptr[i]; k < b->base_ptr[i + 1]; k++)
+      if (b->base_idx[k] < 0 || b->base_idx[k] >= b->n_scans) return fail(h, YSM_EINVAL, "bad base scan index");
+  }
+
+  // pool -> device
+  const double* d_pool = nullptr;
+  if (b->pool_on_device) {
+    d_pool = b->pool_xy;
+  } else {
+    CK(h->d_pool.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
+    if (b->n_points > 0)
+      CK(cudaMemcpyAsync(h->d_pool.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
+    d_pool = (const double*)h->d_pool.p;
+  }
+  CK(h->d_scan_start.ensure((size_t)std::max(1, b->n_scans) * 4));
+  CK(h->d_scan_count.ensure((size_t)std::max(1, b->n_scans) * 4));
+  if (b->n_scans > 0) {
+    CK(cudaMemcpyAsync(h->d_scan_start.p, b->scan_start, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_scan_count.p, b->scan_count, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
+  }
+
+  if (timing) CK(cudaEventRecord(h->ev[6], st));
+
+  const double csx = 0.5 * (h->side - 1) * h->res_eff;
+  const double crx = 2 * h->res_eff;
+  const int S = h->slots;
+
+  std::vector<MatchState> states;
+  std::vector<MatchDev> hm;
+  std::vector<int> hbase;
+  std::vector<TableDev> htab;
+  std::vector<PassDev> hpass;
+  std::vector<PassHost> hph;
+  std::vector<PassAngle> hpa;
+  std::vector<int> hfine;
+  std::vector<double> htrig;
+  std::unordered_map<TableKey, int, TableKeyHash> tab_index;
+
+  h->last_slot_of_match.assign(b->n_matches, -1);
+  h->last_coarse_table_off.assign(b->n_matches, -1);
+  h->last_coarse_nA.assign(b->n_matches, 0);
+  h->last_coarse_P.assign(b->n_matches, 0);
+  h->last_coarse_Ppad.assign(b->n_matches, 0);
+
+  for (int w0 = 0; w0 < b->n_matches; w0 += S) {
+    const int w1 = std::min(b->n_matches, w0 + S);
+    const int nw = w1 - w0;
+    h->last_wave_begin = w0;
+    h->last_wave_end = w1;
+    // ---- wave setup: match descriptors, base lists ------------------------------------------
+    states.assign(nw, MatchState());
+    hm.assign(nw, MatchDev());
+    hbase.clear();
+    long long cells_total = 0;
+    int nbase_max = 1;
+    int n_active = 0;
+    for (int i = 0; i < nw; i++) {
+      const int mi = w0 + i;
+      MatchState& s = states[i];
+      s.idx = mi;
+      s.slot = i;
+      s.q = b->query_scan[mi];
+      s.P = b->scan_count[s.q];
+      s.pose[0] = b->query_pose[3 * mi];
+      s.pose[1] = b->query_pose[3 * mi + 1];
+      s.pose[2] = b->query_pose[3 * mi + 2];
+      s.gox = s.pose[0] - (0.5 * (g.roi - 1) * h->res_eff);
+      s.goy = s.pose[1] - (0.5 * (g.roi - 1) * h->res_eff);
+      s.stage = 0;
+      s.angle_offset_cur = h->prm.coarse_search_angle_offset;
+      s.n_passes = 0;
+      s.n_ties = 0;
+      s.status = YSM_OK;
+      s.best = 0.0;
+      memset(s.cov, 0, sizeof(s.cov));
+      s.mean[0] = s.pose[0]; s.mean[1] = s.pose[1]; s.mean[2] = s.pose[2];
+      MatchDev& m = hm[i];
+      m.slot = i;
+      m.base_begin = (int)hbase.size();
+      long long mc = 0;
+      if (s.P > 0) {
+        for (int k = b->base_ptr[mi]; k < b->base_ptr[mi + 1]; k++) {
+          hbase.push_back(b->base_idx[k]);
+          mc += b->scan_count[b->base_idx[k]];
+        }
+      }
+      m.base_end = (int)hbase.size();
+      nbase_max = std::max(nbase_max, m.base_end - m.base_begin);
+      m.cells_off = (int)cells_total;
+      cells_total += mc;
+      m.vpx = s.pose[0]; m.vpy = s.pose[1];
+      m.gox = s.gox; m.goy = s.goy;
+      if (s.P == 0) {
+        // scan has no readings (MatchScan early return)
+        s.stage = 5;
+        s.cov[0] = MAX_VARIANCE;
+        s.cov[4] = MAX_VARIANCE;
+        s.cov[8] = 4 * h_square(h->prm.coarse_angle_resolution);
+        s.best = 0.0;
+      } else {
+        n_active++;
+      }
+      h->last_slot_of_match[mi] = i;
+    }
+    if (cells_total > 0x7fffff00LL) return fail(h, YSM_ENOMEM, "wave has too many base points");
+    CK(h->d_matches.ensure(sizeof(MatchDev) * (size_t)nw));
+    CK(h->d_base_idx.ensure(std::max<size_t>(4, hbase.size() * 4)));
+    CK(h->d_cells.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
+    CK(h->d_ptcell.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
+    CK(h->d_cellcount.ensure((size_t)nw * 4));
+    CK(cudaMemcpyAsync(h->d_matches.p, hm.data(), sizeof(MatchDev) * (size_t)nw, cudaMemcpyHostToDevice, st));
+    if (!hbase.empty())
+      CK(cudaMemcpyAsync(h->d_base_idx.p, hbase.data(), hbase.size() * 4, cudaMemcpyHostToDevice, st));
+
+    // ---- K1: grid build -----------------------------------------------------------------------
+    if (timing) CK(cudaEventRecord(h->ev[0], st));
+    {
+      int nwarps = 8;
+      while (nwarps > 1 && (size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max > 200 * 1024) nwarps >>= 1;
+      const size_t smem = (size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max;
+      if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points for the filter kernel");
+      if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, (const MatchDev*)h->d_matches.p, (const int*)h->d_base_idx.p,
+                                                   (const int*)h->d_scan_start.p, (const int*)h->d_scan_count.p,
+                                                   d_pool, (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
+                                                   (int*)h->d_cellcount.p, pmax);
+      h->launches++;
+      const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
+      int chunks = std::max(1, std::min(64, (h->num_sms * 8 + nw - 1) / nw));
+      dim3 grid(chunks, nw);
+      k_stamp<<<grid, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
+                                        (const int*)h->d_cellcount.p, h->d_kernel, h->d_grids, 0);
+      h->launches++;
+    }
+    if (timing) CK(cudaEventRecord(h->ev[1], st));
+    CK(cudaGetLastError());
+
+    // ---- pass iterations ------------------------------------------------------------------------
+    int iter = 0;
+    while (true) {
+      htab.clear(); hpass.clear(); hph.clear(); hpa.clear(); hfine.clear(); htrig.clear();
+      tab_index.clear();
+      size_t off_elems = 0, sums_elems = 0;
+      int ang_elems = 0;
+      int max_lat_P = 0, max_lat_nx = 0, max_lat_ny = 0, max_lat_tasks = 0, max_fine_poses = 0;
+      for (int i = 0; i < nw; i++) {
+        MatchState& s = states[i];
+        if (s.stage >= 5) continue;
+        PassHost ph;
+        ph.match = i;
+        ph.fine = (s.stage == 4);
+        if (!ph.fine) {
+          ph.cx = s.pose[0]; ph.cy = s.pose[1]; ph.ch = s.pose[2];
+          ph.offx = csx; ph.offy = csx; ph.resx = crx; ph.resy = crx;
+          ph.angle_offset = s.angle_offset_cur;
+          ph.angle_res = h->prm.coarse_angle_resolution;
+        } else {
+          ph.cx = s.mean[0]; ph.cy = s.mean[1]; ph.ch = s.mean[2];
+          ph.offx = crx * 0.5; ph.offy = crx * 0.5; ph.resx = h->res_eff; ph.resy = h->res_eff;
+          ph.angle_offset = 0.5 * h->prm.coarse_angle_resolution;
+          ph.angle_res = h->prm.fine_search_angle_resolution;
+        }
+        ph.nX = n_steps(ph.offx, ph.resx);
+        ph.nY = n_steps(ph.offy, ph.resy);
+        ph.nA = n_steps(ph.angle_offset, ph.angle_res);
+        if (ph.nA <= 0 || ph.nA > 100000) return fail(h, YSM_EINVAL, "bad angle search window");
+        // lookup table (deduplicated: same query scan, pose and angle window share one table)
+        TableKey key;
+        key.q = s.q;
+        key.b[0] = dbits(s.pose[0]); key.b[1] = dbits(s.pose[1]); key.b[2] = dbits(s.pose[2]);
+        key.b[3] = dbits(ph.ch); key.b[4] = dbits(ph.angle_offset); key.b[5] = dbits(ph.angle_res);
+        int tid;
+        auto it = tab_index.find(key);
+        const int Ppad = align_up(s.P, 4);
+        if (it == tab_index.end()) {
+          TableDev t;
+          t.q_start = b->scan_start[s.q];
+          t.P = s.P; t.Ppad = Ppad; t.nA = ph.nA;
+          t.trig_off = (int)(htrig.size() / 2);
+          t.out_off = (int)off_elems;
+          off_elems += (size_t)ph.nA * Ppad;
+          t.px = s.pose[0]; t.py = s.pose[1];
+          // Transform(sensorPose): m_InverseRotation = FromAxisAngle(0,0,1, 0 - heading)
+          if (s.pose[0] == 0.0 && s.pose[1] == 0.0 && s.pose[2] == 0.0) {
+            t.r00 = 1.0; t.r01 = 0.0; t.r10 = 0.0; t.r11 = 1.0;
+          } else {
+            const double radians = 0.0 - s.pose[2];
+            const double c = cos(radians), sn = sin(radians);
+            const double omc = 1.0 - c;
+            t.r00 = 0.0 * omc + c;
+            t.r01 = (0.0 * 0.0 * omc) - (1.0 * sn);
+            t.r10 = (0.0 * 0.0 * omc) + (1.0 * sn);
+            t.r11 = 0.0 * omc + c;
+          }
+          t.gox = s.gox; t.goy = s.goy;
+          const double start_angle = ph.ch - ph.angle_offset;
+          for (int a = 0; a < ph.nA; a++) {
+            const double angle = start_angle + (double)(uint32_t)a * ph.angle_res;
+            htrig.push_back(cos(angle));
+            htrig.push_back(sin(angle));
+          }
+          tid = (int)htab.size();
+          htab.push_back(t);
+          tab_index.emplace(key, tid);
+        } else {
+          tid = it->second;
+        }
+        PassDev pd;
+        pd.slot = s.slot; pd.table = tid; pd.nA = ph.nA; pd.nX = ph.nX; pd.nY = ph.nY;
+        pd.P = s.P; pd.Ppad = Ppad; pd.fine = ph.fine ? 1 : 0; pd.penalize = b->do_penalize ? 1 : 0;
+        pd.sums_off = (int)sums_elems;
+        sums_elems += (size_t)ph.nX * ph.nY * ph.nA;
+        // cos/sin of the normalised headings (tie average). Identical to the table's when
+        // normalisation is a no-op; evaluated separately otherwise.
+        pd.htrig_off = (int)(htrig.size() / 2);
+        {
+          const double start_angle = ph.ch - ph.angle_offset;
+          for (int a = 0; a < ph.nA; a++) {
+            const double angle = start_angle + (double)(uint32_t)a * ph.angle_res;
+            const double hn = h_normalize_angle(angle);
+            htrig.push_back(cos(hn));
+            htrig.push_back(sin(hn));
+          }
+        }
+        pd.ang_off = ang_elems;
+        ph.ang_off = ang_elems;
+        if (ph.fine) ang_elems += ph.nA;
+        pd.cx = ph.cx; pd.cy = ph.cy; pd.ch = ph.ch;
+        pd.offx = ph.offx; pd.offy = ph.offy; pd.resx = ph.resx; pd.resy = ph.resy;
+        pd.angle_offset = ph.angle_offset; pd.angle_res = ph.angle_res;
+        pd.gox = s.gox; pd.goy = s.goy;
+        const int pid = (int)hpass.size();
+        s.pass_id = pid;
+        hpass.push_back(pd);
+        hph.push_back(ph);
+        if (!ph.fine) {
+          for (int a = 0; a < ph.nA; a++) hpa.push_back(PassAngle{pid, a});
+          max_lat_P = std::max(max_lat_P, s.P);
+          max_lat_nx = std::max(max_lat_nx, ph.nX);
+          max_lat_ny = std::max(max_lat_ny, ph.nY);
+          max_lat_tasks = std::max(max_lat_tasks, ph.nY * ((ph.nX + 31) / 32));
+          if (s.stage == 0) {
+            h->last_coarse_table_off[s.idx] = htab[tid].out_off;
+            h->last_coarse_nA[s.idx] = ph.nA;
+            h->last_coarse_P[s.idx] = s.P;
+            h->last_coarse_Ppad[s.idx] = Ppad;
+          }
+        } else {
+          hfine.push_back(pid);
+          max_fine_poses = std::max(max_fine_poses, ph.nX * ph.nY * ph.nA);
+        }
+      }
+      const int npass = (int)hpass.size();
+      if (npass == 0) break;
+      if (off_elems > 0x7fffff00ull || sums_elems > 0x7fffff00ull)
+        return fail(h, YSM_ENOMEM, "wave workspace exceeds 2^31 elements; lower max_slots");
+
+      // one staging blob: tables | passes | pa_list | fine ids | trig
+      size_t o_tab = 0;
+      size_t o_pass = o_tab + sizeof(TableDev) * htab.size();
+      size_t o_pa = o_pass + sizeof(PassDev) * hpass.size();
+      size_t o_fine = o_pa + sizeof(PassAngle) * hpa.size();
+      size_t o_trig = (o_fine + sizeof(int) * hfine.size() + 15) / 16 * 16;
+      size_t blob = o_trig + sizeof(double) * htrig.size();
+      CK(h->h_blob.ensure(blob));
+      CK(h->d_blob.ensure(blob));
+      char* hb = (char*)h->h_blob.p;
+      memcpy(hb + o_tab, htab.data(), sizeof(TableDev) * htab.size());
+      memcpy(hb + o_pass, hpass.data(), sizeof(PassDev) * hpass.size());
+      if (!hpa.empty()) memcpy(hb + o_pa, hpa.data(), sizeof(PassAngle) * hpa.size());
+      if (!hfine.empty()) memcpy(hb + o_fine, hfine.data(), sizeof(int) * hfine.size());
+      memcpy(hb + o_trig, htrig.data(), sizeof(double) * htrig.size());
+      CK(cudaMemcpyAsync(h->d_blob.p, hb, blob, cudaMemcpyHostToDevice, st));
+      const char* db = (const char*)h->d_blob.p;
+      const TableDev* d_tab = (const TableDev*)(db + o_tab);
+      const PassDev* d_pass = (const PassDev*)(db + o_pass);
+      const PassAngle* d_pa = (const PassAngle*)(db + o_pa);
+      const int* d_fine = (const int*)(db + o_fine);
+      const double* d_trig = (const double*)(db + o_trig);
+
+      CK(h->d_offsets.ensure(std::max<size_t>(16, off_elems * 4)));
+      CK(h->d_sums.ensure(std::max<size_t>(16, sums_elems * 4)));
+      CK(h->d_outs.ensure(sizeof(PassOut) * (size_t)npass));
+      CK(h->d_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
+      CK(h->h_outs.ensure(sizeof(PassOut) * (size_t)npass));
+      CK(h->h_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
+
+      // ---- K2 offsets ---------------------------------------------------------------------------
+      {
+        int maxwork = 1;
+        for (const TableDev& t : htab) maxwork = std::max(maxwork, t.nA * (t.Ppad / 4));
+        dim3 grid((maxwork + 255) / 256, (unsigned)htab.size());
+        k_offsets<<<grid, 256, 0, st>>>(g, d_tab, d_trig, d_pool, (int*)h->d_offsets.p);
+        h->launches++;
+      }
+      // ---- K3 sweeps ----------------------------------------------------------------------------
+      if (timing) CK(cudaEventRecord(h->ev[2], st));
+      if (!hpa.empty()) {
+        // enough CTAs to fill the machine: split lattice rows, then the points, when the batch is small
+        const int npa = (int)hpa.size();
+        const int target = h->num_sms * 8;
+        int task_chunks = 1, p_chunks = 1;
+        if (npa < target) {
+          task_chunks = std::min(std::max(1, (max_lat_tasks + 7) / 8), (target + npa - 1) / npa);
+          if (npa * task_chunks < target) p_chunks = std::min(std::max(1, max_lat_P / 64), (target + npa * task_chunks - 1) / (npa * task_chunks));
+        }
+        const int tpc = (max_lat_tasks + task_chunks - 1) / task_chunks;
+        task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+        const int p_chunk = (max_lat_P + p_chunks - 1) / p_chunks;
+        p_chunks = (max_lat_P + p_chunk - 1) / p_chunk;
+        const size_t smem = (size_t)(p_chunk + max_lat_nx + max_lat_ny) * 4;
+        if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
+        dim3 grid(npa, task_chunks, p_chunks);
+        if (p_chunks > 1) {
+          CK(cudaMemsetAsync(h->d_sums.p, 0, sums_elems * 4, st));
+          if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_sweep_lattice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_sweep_lattice<true><<<grid, 256, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                         h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
+        } else {
+          if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_sweep_lattice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_sweep_lattice<false><<<grid, 256, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                          h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
+        }
+        h->launches++;
+      }
+      if (timing) CK(cudaEventRecord(h->ev[3], st));
+      if (!hfine.empty()) {
+        dim3 grid((max_fine_poses + 7) / 8, (unsigned)hfine.size());
+        k_sweep_points<<<grid, 256, 0, st>>>(g, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
+                                             (uint32_t*)h->d_sums.p);
+        h->launches++;
+      }
+      // ---- K3b/K4 reduce ------------------------------------------------------------------------
+      if (timing) CK(cudaEventRecord(h->ev[4], st));
+      k_reduce<<<npass, 256, 0, st>>>(g, h->pen, d_pass, d_tab, (const int*)h->d_offsets.p,
+                                      (const uint32_t*)h->d_sums.p, d_trig, h->d_grids, (PassOut*)h->d_outs.p,
+                                      (int*)h->d_angsums.p);
+      h->launches++;
+      if (timing) CK(cudaEventRecord(h->ev[5], st));
+      CK(cudaMemcpyAsync(h->h_outs.p, h->d_outs.p, sizeof(PassOut) * (size_t)npass, cudaMemcpyDeviceToHost, st));
+      if (ang_elems > 0)
+        CK(cudaMemcpyAsync(h->h_angsums.p, h->d_angsums.p, (size_t)ang_elems * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGetLastError());
+      if (timing) {
+        float ms = 0;
+        if (iter == 0) {
+          cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+          h->t_build += ms;
+        }
+        if (!hpa.empty()) {
+          cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+          h->t_sweep += ms;
+        }
+        cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+        h->t_reduce += ms;
+      }
+
+      // ---- host: finish every pass exactly as CorrelateScan / MatchScan do ----------------------
+      const PassOut* outs = (const PassOut*)h->h_outs.p;
+      const int* angs = (const int*)h->h_angsums.p;
+      for (int pid = 0; pid < npass; pid++) {
+        const PassHost& ph = hph[pid];
+        const PassOut& po = outs[pid];
+        MatchState& s = states[ph.match];
+        s.n_passes++;
+        s.n_ties = po.n_ties;
+        if (po.n_ties <= 0) {
+          s.status = YSM_EMATCH;  // "Mapper FATAL ERROR - Unable to find best position"
+          s.stage = 5;
+          continue;
+        }
+        const double heading = atan2(po.ty, po.tx);
+        if (!ph.fine) {
+          finalize_positional(h, ph, po, s.cov);
+        } else {
+          finalize_angular(ph, po, heading, angs + ph.ang_off, s.P, s.cov);
+        }
+        s.mean[0] = po.avg_x; s.mean[1] = po.avg_y; s.mean[2] = heading;
+        double best = po.best;
+        if (best > 1.0) best = 1.0;
+        s.best = best;
+        // MatchScan schedule
+        if (ph.fine) {
+          s.stage = 5;
+        } else {
+          bool expand = false;
+          if (h->prm.use_response_expansion && h_double_equal(best, 0.0) && s.stage < 3) {
+            // stage 0 -> expansion 1, ..., stage 2 -> expansion 3
+            expand = true;
+          }
+          if (expand) {
+            s.stage += 1;
+            s.angle_offset_cur += 20 * KT_PI_180;
+          } else {
+            s.stage = b->do_refine ? 4 : 5;
+          }
+        }
+      }
+      iter++;
+    }
+
+    // ---- results + clear ------------------------------------------------------------------------
+    for (int i = 0; i < nw; i++) {
+      const MatchState& s = states[i];
+      ysm_result& r = out[s.idx];
+      r.response = s.best;
+      r.x = s.mean[0]; r.y = s.mean[1]; r.heading = s.mean[2];
+      memcpy(r.cov, s.cov, sizeof(s.cov));
+      r.n_passes = s.n_passes;
+      r.n_ties = s.n_ties;
+      r.status = s.status;
+      r._pad = 0;
+      r._reserved = 0.0;
+    }
+    if (h->debug & YSM_DEBUG_KEEP_GRIDS) {
+      h->grids_dirty = true;
+      h->dirty_matches = hm;
+      if (w1 < b->n_matches) {
+        // more waves follow: the slots are needed again
+        clear_wave(h, (const MatchDev*)h->d_matches.p, nw, st);
+        h->grids_dirty = false;
+        h->dirty_matches.clear();
+      }
+    } else {
+      clear_wave(h, (const MatchDev*)h->d_matches.p, nw, st);
+    }
+    CK(cudaGetLastError());
+  }
+  if (timing) {
+    CK(cudaEventRecord(h->ev[7], st));
+    CK(cudaEventSynchronize(h->ev[7]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
+    h->t_total = ms;
+  }
+  // the clear kernel must not race with a caller that frees / reuses `pool_xy` on the device
+  // or with the next call's staging: d_matches/d_cells are reused by the next wave, which is
+  // ordered behind the clear on the same stream.
+  for (int i = 0; i < b->n_matches; i++)
+    if (out[i].status != YSM_OK) return fail(h, YSM_EMATCH, "Mapper FATAL ERROR - Unable to find best position");
+  return YSM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+extern "C" int ysm_debug_copy_grid(ysm_handle* h, int32_t match, uint8_t* out_host) {
+  if (!h || !out_host) return YSM_EINVAL;
+  if (match < h->last_wave_begin || match >= h->last_wave_end || !h->grids_dirty)
+    return fail(h, YSM_EINVAL, "grid of that match is not resident (set YSM_DEBUG_KEEP_GRIDS; last wave only)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const int slot = h->last_slot_of_match[match];
+  CK(cudaMemcpy(out_host, h->d_grids + (size_t)slot * h->g.grid_bytes, (size_t)h->g.data_size, cudaMemcpyDeviceToHost));
+  return YSM_OK;
+}
+
+extern "C" int ysm_debug_copy_kernel(ysm_handle* h, uint8_t* out_host) {
+  if (!h || !out_host) return YSM_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out_host, h->d_kernel, h->h_kernel.size(), cudaMemcpyDeviceToHost));
+  return YSM_OK;
+}
+
+extern "C" int ysm_debug_copy_offsets(ysm_handle* h, int32_t match, int32_t* out_host, int32_t* n_angles,
+                                      int32_t* n_points) {
+  if (!h || !n_angles || !n_points) return YSM_EINVAL;
+  if (match < 0 || match >= (int)h->last_coarse_table_off.size() || h->last_coarse_table_off[match] < 0)
+    return fail(h, YSM_EINVAL, "no coarse table recorded for that match");
+  *n_angles = h->last_coarse_nA[match];
+  *n_points = h->last_coarse_P[match];
+  if (!out_host) return YSM_OK;
+  // valid only if the match needed a single pass iteration after the coarse one did not
+  // overwrite the offsets buffer: callers use do_refine=0 and non-degenerate inputs
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const int Ppad = h->last_coarse_Ppad[match];
+  std::vector<int32_t> tmp((size_t)(*n_angles) * Ppad);
+  CK(cudaMemcpy(tmp.data(), (const int*)h->d_offsets.p + h->last_coarse_table_off[match], tmp.size() * 4,
+                cudaMemcpyDeviceToHost));
+  for (int a = 0; a < *n_angles; a++)
+    memcpy(out_host + (size_t)a * (*n_points), tmp.data() + (size_t)a * Ppad, (size_t)(*n_points) * 4);
+  return YSM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// run_raytracing_sweep (reference yag_slam/raytracing.py:90-92) for many start cells
+extern "C" int ysm_raytrace(const uint8_t* img, int32_t hh, int32_t ww, int32_t img_on_device,
+                            const double* angles_deg, int32_t n_angles, const double* starts_xy,
+                            int32_t n_starts, float* out, int device, void* stream) {
+  if (!img || !angles_deg || !starts_xy || !out || hh < 3 || ww < 3 || n_angles < 0 || n_starts < 0)
+    return fail(nullptr, YSM_EINVAL, "ysm_raytrace: bad argument");
+  if (n_angles == 0 || n_starts == 0) return YSM_OK;
+  const long long n_rays = (long long)n_angles * n_starts;
+  if (n_rays > 0x7fffffffLL / 5) return fail(nullptr, YSM_EUNSUP, "ysm_raytrace: too many rays in one call");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, YSM_ECUDA, cudaGetErrorString(e));
+  std::vector<double> cs((size_t)2 * n_angles);
+  for (int a = 0; a < n_angles; a++) {
+    const double ang = angles_deg[a] * (3.141592653589793 / 180.0);  // np.deg2rad
+    cs[2 * a] = cos(ang);
+    cs[2 * a + 1] = sin(ang);
+  }
+  uint8_t* d_img = nullptr;
+  double *d_cs = nullptr, *d_starts = nullptr;
+  float* d_out = nullptr;
+  int rc = YSM_OK;
+  do {
+    if (!img_on_device) {
+      if ((e = cudaMalloc((void**)&d_img, (size_t)hh * ww)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(d_img, img, (size_t)hh * ww, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    }
+    if ((e = cudaMalloc((void**)&d_cs, cs.size() * 8)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&d_starts, (size_t)n_starts * 16)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&d_out, (size_t)n_rays * 5 * 4)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d_cs, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d_starts, starts_xy, (size_t)n_starts * 16, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    k_raywalk<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(img_on_device ? img : d_img, hh, ww, d_cs, n_angles,
+                                                                d_starts, (int)n_rays, d_out);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(out, d_out, (size_t)n_rays * 5 * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  if (e != cudaSuccess) rc = fail(nullptr, YSM_ECUDA, std::string("ysm_raytrace: ") + cudaGetErrorString(e));
+  if (d_img) cudaFree(d_img);
+  if (d_cs) cudaFree(d_cs);
+  if (d_starts) cudaFree(d_starts);
+  if (d_out) cudaFree(d_out);
+  return rc;
+}

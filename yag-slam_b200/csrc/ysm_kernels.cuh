@@ -1,0 +1,671 @@
+// ysm_kernels.cuh -- sm_100a device code of the correlative scan matcher.
+//
+// Every kernel cites the Karto function it replaces (the Karto C++
+// itself is not in the reference tree -- it ships as the wheel karto_scanmatcher==1.0.0,
+// reference setup.py:46 -- so citations are to the survey's restatement and to the reference's
+// python twins in yag_slam/helpers.py).
+//
+// Compile with -fmad=false: cell indices come from Round(double) and must see the same
+// separately-rounded IEEE-754 operations as an x86-64 build of Karto (no FMA contraction).
+// No device sin/cos/atan2 anywhere: every transcendental is evaluated by the host runtime with
+// libm and handed in as a table, so results are bit-identical to the CPU reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ysm {
+
+#define YSM_KT_TOLERANCE 1e-06
+#define YSM_INVALID_CELL 0xFFFFFFFFu
+
+// Sizes of one correlation grid (ScanMatcher::Create / CorrelationGrid).
+struct GridC {
+  int roi, border, stride, width, height, data_size;
+  int half_kernel, K, Wk;  // Wk = 32-bit words a stamp row can straddle
+  int stride4;             // stride / 4
+  double scale;            // 1 / resolution
+  long long grid_bytes;    // bytes between consecutive slots (16-B aligned)
+};
+
+struct PenaltyC {
+  double distance_variance_penalty, angle_variance_penalty;
+  double minimum_distance_penalty, minimum_angle_penalty;
+};
+
+// One MatchScan call of the current wave (grid build inputs).
+struct MatchDev {
+  int slot;
+  int base_begin, base_end;  // range in the wave's base_idx array (pool scan ids)
+  int cells_off;             // offset of this match's cell list / point scratch
+  double vpx, vpy;           // FindValidPoints viewpoint = query sensor position
+  double gox, goy;           // CorrelationGrid converter offset
+};
+
+// One GridIndexLookup::ComputeOffsets table.
+struct TableDev {
+  int q_start, P, Ppad, nA;
+  int trig_off;  // cos/sin of each search angle: trig[2*(trig_off+a)], trig[2*(trig_off+a)+1]
+  int out_off;   // int32 element offset into the offsets buffer (multiple of 4)
+  double px, py;                // scan sensor position
+  double r00, r01, r10, r11;    // Transform(sensorPose).m_InverseRotation (host libm)
+  double gox, goy;
+};
+
+// One CorrelateScan call.
+struct PassDev {
+  int slot, table, nA, nX, nY, P, Ppad, fine, penalize;
+  int sums_off;   // u32 element offset into the sums buffer, layout [iy][ix][a]
+  int htrig_off;  // cos/sin of NormalizeAngle(angle_a), for the tie average
+  int ang_off;    // int element offset into the angular-covariance sums buffer
+  double cx, cy, ch;              // search centre
+  double offx, offy, resx, resy;  // search space offset / resolution
+  double angle_offset, angle_res;
+  double gox, goy;
+};
+
+// Per-pass reduction result, finished on the host (atan2 via libm).
+struct PassOut {
+  double best;          // best response before the clamp to 1
+  double avg_x, avg_y;  // tie-averaged position
+  double tx, ty;        // mean cos / mean sin of the tied headings
+  double norm, axx, axy, ayy;  // ComputePositionalCovariance accumulators
+  int n_ties;
+  int pad;
+};
+
+__device__ __forceinline__ double kt_round(double v) { return v >= 0.0 ? floor(v + 0.5) : ceil(v - 0.5); }
+__device__ __forceinline__ bool kt_double_equal(double a, double b) { return fabs(a - b) <= YSM_KT_TOLERANCE; }
+__device__ __forceinline__ int world_to_grid1(double w, double off, double scale) {
+  return (int)kt_round((w - off) * scale);
+}
+
+// Byte-wise max of two packed u8x4 words whose bytes are all < 128 (grid values are <= 100).
+__device__ __forceinline__ uint32_t vmax4_lt128(uint32_t a, uint32_t b) {
+  uint32_t d = (a | 0x80808080u) - b;  // per byte: a + 128 - b, never borrows
+  uint32_t m = ((d & 0x80808080u) >> 7) * 0xFFu;  // 0xFF where a >= b
+  return (a & m) | (b & ~m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a  ScanMatcher::FindValidPoints + the WorldToGrid/ROI test of AddScan (python
+// analogue yag_slam/helpers.py:298-329). One CTA per match, one warp per base scan.
+// The sequential "trailing iterator" filter is restated as: next[i] = first j>i farther than
+// 10 cm from point i (parallel), the trigger chain 0 -> next[0] -> ... (one lane, shared
+// memory pointer chase), then every segment [t_k, t_k+1) is kept iff the side test ss >= 0
+// (parallel). Output: the match's occupied cells in Karto's processing order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restrict__ base_idx,
+             const int* __restrict__ scan_start, const int* __restrict__ scan_count,
+             const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
+             uint32_t* __restrict__ cells, int* __restrict__ cell_count, int pmax) {
+  extern __shared__ unsigned char smem_raw[];
+  const int nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned short* s_next = reinterpret_cast<unsigned short*>(smem_raw) + (size_t)warp * 2 * pmax;
+  unsigned short* s_trig = s_next + pmax;
+  int* s_scan_emit = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * 4 * pmax);  // [nbase]
+
+  const MatchDev m = matches[blockIdx.x];
+  const int nbase = m.base_end - m.base_begin;
+  const double msd = 0.1 * 0.1;  // math::Square(0.1)
+
+  // scan-local offsets inside the match's scratch: prefix of scan counts
+  // (recomputed per warp; nbase is small)
+  for (int b = warp; b < nbase; b += nwarps) {
+    int off = 0;
+    for (int bb = 0; bb < b; bb++) off += scan_count[base_idx[m.base_begin + bb]];
+    const int s = base_idx[m.base_begin + b];
+    const int n = scan_count[s];
+    const double* pts = pool + 2 * (size_t)scan_start[s];
+    uint32_t* out = pt_cell + m.cells_off + off;
+    for (int i = lane; i < n; i += 32) out[i] = YSM_INVALID_CELL;
+    int emitted = 0;
+    if (n > 0) {
+      for (int i = lane; i < n; i += 32) {
+        const double fx = pts[2 * i], fy = pts[2 * i + 1];
+        int j = i + 1;
+        while (j < n) {
+          const double dx = fx - pts[2 * j], dy = fy - pts[2 * j + 1];
+          if (dx * dx + dy * dy > msd) break;
+          j++;
+        }
+        s_next[i] = (unsigned short)j;
+      }
+      __syncwarp();
+      int ntrig = 0;
+      if (lane == 0) {
+        int t = 0;
+        while (t < n) {
+          s_trig[ntrig++] = (unsigned short)t;
+          t = s_next[t];
+        }
+      }
+      ntrig = __shfl_sync(0xffffffffu, ntrig, 0);
+      __syncwarp();
+      for (int k = lane; k < ntrig - 1; k += 32) {
+        const int f = s_trig[k], c = s_trig[k + 1];
+        const double fx = pts[2 * f], fy = pts[2 * f + 1];
+        const double cx = pts[2 * c], cy = pts[2 * c + 1];
+        const double a = m.vpy - fy;
+        const double b2 = fx - m.vpx;
+        const double cc = fy * m.vpx - fx * m.vpy;
+        const double ss = cx * a + cy * b2 + cc;
+        if (!(ss < 0.0)) {
+          for (int j = f; j < c; j++) {
+            const double vx = (pts[2 * j] - m.gox) * g.scale;
+            const double vy = (pts[2 * j + 1] - m.goy) * g.scale;
+            if (vx > -1.0 && vy > -1.0 && vx < 1e9 && vy < 1e9) {
+              const int gx = (int)kt_round(vx), gy = (int)kt_round(vy);
+              if (gx >= 0 && gx < g.roi && gy >= 0 && gy < g.roi) {
+                out[j] = (uint32_t)(gx + g.border) | ((uint32_t)(gy + g.border) << 16);
+                emitted++;
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
+    if (lane == 0) s_scan_emit[b] = emitted;
+    __syncwarp();
+  }
+  __syncthreads();
+  // ordered compaction (scan order, then point order)
+  for (int b = warp; b < nbase; b += nwarps) {
+    int off = 0, dst = 0;
+    for (int bb = 0; bb < b; bb++) {
+      off += scan_count[base_idx[m.base_begin + bb]];
+      dst += s_scan_emit[bb];
+    }
+    const int n = scan_count[base_idx[m.base_begin + b]];
+    const uint32_t* in = pt_cell + m.cells_off + off;
+    uint32_t* outc = cells + m.cells_off;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t c = (i < n) ? in[i] : YSM_INVALID_CELL;
+      const unsigned bal = __ballot_sync(0xffffffffu, c != YSM_INVALID_CELL);
+      if (c != YSM_INVALID_CELL) outc[dst + __popc(bal & ((1u << lane) - 1u))] = c;
+      dst += __popc(bal);
+    }
+  }
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
+    cell_count[blockIdx.x] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
+// yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so it is applied as
+// a parallel scatter: one lane per (cell, stamp row, 32-bit word), byte-wise max of four grid
+// cells at a time, committed with a compare-and-swap on the word in L2. The stamp row is
+// pre-shifted for the four possible byte alignments in shared memory.
+// mode 0: stamp (max); mode 1: clear the same footprint back to zero after the match.
+// grid = (chunks, matches_in_wave)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
+        const int* __restrict__ cell_count, const uint8_t* __restrict__ kernel,
+        uint8_t* __restrict__ grids, int mode) {
+  extern __shared__ uint32_t s_k[];  // [4][K][Wk]
+  const int K = g.K, Wk = g.Wk, h = g.half_kernel;
+  const int nks = 4 * K * Wk;
+  for (int t = threadIdx.x; t < nks; t += blockDim.x) {
+    const int w = t % Wk, j = (t / Wk) % K, s = t / (Wk * K);
+    uint32_t word = 0;
+    for (int b = 0; b < 4; b++) {
+      const int i = w * 4 + b - s;  // stamp column
+      if (i >= 0 && i < K) word |= (uint32_t)kernel[i + K * j] << (8 * b);
+    }
+    s_k[t] = word;
+  }
+  __syncthreads();
+  const MatchDev m = matches[blockIdx.y];
+  const int ncells = cell_count[blockIdx.y];
+  const int per = K * Wk;
+  const long long items = (long long)ncells * per;
+  uint32_t* grid32 = reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes);
+  const uint32_t* mc = cells + m.cells_off;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int pt = (int)(it / per);
+    const int rem = (int)(it - (long long)pt * per);
+    const int j = rem / Wk, w = rem - j * Wk;
+    const uint32_t c = mc[pt];
+    const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+    const int x0 = ax - h;
+    const int s = x0 & 3;
+    const uint32_t kw = s_k[(s * K + j) * Wk + w];
+    if (kw == 0u) continue;
+    uint32_t* addr = grid32 + (size_t)(ay + j - h) * g.stride4 + (x0 >> 2) + w;
+    if (mode == 1) {
+      *addr = 0u;
+      continue;
+    }
+    uint32_t old = __ldcg(addr);
+    while (true) {
+      const uint32_t nw = vmax4_lt128(old, kw);
+      if (nw == old) break;
+      const uint32_t prev = atomicCAS(addr, old, nw);
+      if (prev == old) break;
+      old = prev;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  GridIndexLookup::ComputeOffsets (python analogue _rotate_points,
+// yag_slam/helpers.py:76-78). One thread per (angle, 4 points): inverse-transform the query's
+// world readings into the sensor frame, rotate by the search angle (cos/sin from the host),
+// round to cells exactly as Karto (including the add-then-subtract of the grid offset) and
+// store int4-vectorised, point index fastest. grid = (ceil(nA*Ppad/4 / 256), n_tables)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict__ trig,
+          const double* __restrict__ pool, int* __restrict__ offsets) {
+  const TableDev t = tables[blockIdx.y];
+  const int p4n = t.Ppad >> 2;
+  const int work = t.nA * p4n;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < work; it += gridDim.x * blockDim.x) {
+    const int a = it / p4n, p0 = (it - a * p4n) << 2;
+    const double cosine = trig[2 * (t.trig_off + a)], sine = trig[2 * (t.trig_off + a) + 1];
+    int o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = p0 + k;
+      int v = 0;
+      if (p < t.P) {
+        const double wx = pool[2 * (size_t)(t.q_start + p)], wy = pool[2 * (size_t)(t.q_start + p) + 1];
+        const double dx = wx - t.px, dy = wy - t.py;
+        const double lx = t.r00 * dx + t.r01 * dy;
+        const double ly = t.r10 * dx + t.r11 * dy;
+        const double ox = cosine * lx - sine * ly;
+        const double oy = sine * lx + cosine * ly;
+        const int gx = world_to_grid1(ox + t.gox, t.gox, g.scale);
+        const int gy = world_to_grid1(oy + t.goy, t.goy, g.scale);
+        v = gx + gy * g.stride;
+      }
+      o[k] = v;
+    }
+    *reinterpret_cast<int4*>(offsets + t.out_off + (size_t)a * t.Ppad + p0) = make_int4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  CorrelateScan / GetResponse sweep, lattice form (python twin
+// find_best_pose, yag_slam/helpers.py:156-295). CTA = one (pass, angle); the angle's lookup
+// offsets are staged in shared memory; a warp owns one lattice row (lanes = adjacent x poses, so
+// one warp load touches one contiguous span of a grid row); each lane accumulates its pose's
+// response as an exact integer. grid = (n_pass_angles, task_chunks, p_chunks).
+// ---------------------------------------------------------------------------------------------
+struct PassAngle {
+  int pass, a;
+};
+
+template <bool kAtomic>
+__global__ void __launch_bounds__(256)
+k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __restrict__ pa_list,
+                const TableDev* __restrict__ tables, const int* __restrict__ offsets,
+                const uint8_t* __restrict__ grids, uint32_t* __restrict__ sums, int tasks_per_cta,
+                int p_chunk) {
+  extern __shared__ int s_i[];
+  const PassAngle pa = pa_list[blockIdx.x];
+  const PassDev ps = passes[pa.pass];
+  const int nxc = (ps.nX + 31) >> 5;
+  const int ntasks = ps.nY * nxc;
+  const int task0 = blockIdx.y * tasks_per_cta;
+  if (task0 >= ntasks) return;
+  const int task1 = min(ntasks, task0 + tasks_per_cta);
+  const int pbeg = blockIdx.z * p_chunk;
+  const int pend = min(ps.P, pbeg + p_chunk);
+  if (pbeg >= pend) return;
+  int* s_off = s_i;                // [p_chunk]
+  int* s_col = s_i + p_chunk;      // [nX]
+  int* s_row = s_col + ps.nX;      // [nY]
+  const TableDev tb = tables[ps.table];
+  const int* goff = offsets + tb.out_off + (size_t)pa.a * tb.Ppad;
+  for (int p = pbeg + threadIdx.x; p < pend; p += blockDim.x) s_off[p - pbeg] = goff[p];
+  const double startX = -ps.offx, startY = -ps.offy;
+  for (int i = threadIdx.x; i < ps.nX; i += blockDim.x) {
+    const double x = startX + (double)i * ps.resx;
+    s_col[i] = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+  }
+  for (int i = threadIdx.x; i < ps.nY; i += blockDim.x) {
+    const double y = startY + (double)i * ps.resy;
+    s_row[i] = (world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border) * g.stride;
+  }
+  __syncthreads();
+  const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int np = pend - pbeg;
+  const unsigned dsz = (unsigned)g.data_size;
+  for (int task = task0 + warp; task < task1; task += nwarps) {
+    const int iy = task / nxc, xc = task - iy * nxc;
+    const int ix = (xc << 5) + lane;
+    const bool active = ix < ps.nX;
+    const int base = s_row[iy] + s_col[active ? ix : 0];
+    unsigned sum = 0;
+    int p = 0;
+    for (; p + 8 <= np; p += 8) {
+      unsigned v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned idx = (unsigned)(base + s_off[p + k]);
+        v[k] = (idx < dsz) ? (unsigned)__ldg(grid + idx) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += v[k];
+    }
+    for (; p < np; p++) {
+      const unsigned idx = (unsigned)(base + s_off[p]);
+      if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+    }
+    if (active) {
+      uint32_t* dst = sums + ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a;
+      if (kAtomic) atomicAdd(dst, sum); else *dst = sum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3'  GetResponse sweep, point-parallel form for small search volumes (the fine pass,
+// 3 x 3 x nA poses): one warp per pose, lanes stride the query points, integer partial sums
+// combined with warp shuffles. grid = (ceil(nposes / warps_per_cta), n_fine_passes)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sweep_points(GridC g, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
+               const TableDev* __restrict__ tables, const int* __restrict__ offsets,
+               const uint8_t* __restrict__ grids, uint32_t* __restrict__ sums) {
+  const PassDev ps = passes[pass_ids[blockIdx.y]];
+  const int nposes = ps.nX * ps.nY * ps.nA;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int pose = blockIdx.x * nwarps + warp;
+  if (pose >= nposes) return;
+  const int iy = pose / (ps.nX * ps.nA);
+  const int rem = pose - iy * ps.nX * ps.nA;
+  const int ix = rem / ps.nA, a = rem - ix * ps.nA;
+  const double x = -ps.offx + (double)ix * ps.resx;
+  const double y = -ps.offy + (double)iy * ps.resy;
+  const int gx = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+  const int gy = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
+  const int base = gx + gy * g.stride;
+  const TableDev tb = tables[ps.table];
+  const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
+  const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+  const unsigned dsz = (unsigned)g.data_size;
+  unsigned sum = 0;
+  for (int p = lane; p < ps.P; p += 32) {
+    const unsigned idx = (unsigned)(base + goff[p]);
+    if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) sums[ps.sums_off + pose] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b/K4  CorrelateScan epilogue: response normalisation + odometry penalty,
+// best response, Karto's average-of-ties best pose (sequential, in y/x/angle storage order so
+// the double sums round exactly as the CPU's), then ComputePositionalCovariance accumulators
+// (coarse, A.9) or the per-angle response sums ComputeAngularCovariance needs (fine, A.9).
+// One CTA per pass.
+// ---------------------------------------------------------------------------------------------
+#define YSM_TIE_CAP 1024
+
+__device__ __forceinline__ double pose_response(const PassDev& ps, const PenaltyC& pen,
+                                                const uint32_t* __restrict__ sums, int idx,
+                                                double denom) {
+  double r = (double)sums[idx] / denom;
+  if (ps.penalize && !kt_double_equal(r, 0.0)) {
+    const int iy = idx / (ps.nX * ps.nA);
+    const int rem = idx - iy * ps.nX * ps.nA;
+    const int ix = rem / ps.nA, a = rem - ix * ps.nA;
+    const double x = -ps.offx + (double)ix * ps.resx;
+    const double y = -ps.offy + (double)iy * ps.resy;
+    const double sqd = x * x + y * y;
+    double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
+    dp = dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
+    const double angle = (ps.ch - ps.angle_offset) + (double)a * ps.angle_res;
+    const double da = angle - ps.ch;
+    const double sqa = da * da;
+    double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
+    ap = ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
+    r *= (dp * ap);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double block_reduce_max(double v, double* s_tmp) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = s_tmp[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = s_tmp[w] > r ? s_tmp[w] : r;
+  return r;
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += s_tmp[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_reduce(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
+         const TableDev* __restrict__ tables, const int* __restrict__ offsets,
+         const uint32_t* __restrict__ sums, const double* __restrict__ trig,
+         const uint8_t* __restrict__ grids, PassOut* __restrict__ outs, int* __restrict__ angsums) {
+  __shared__ double s_tmp[8];
+  __shared__ int s_list[YSM_TIE_CAP];
+  __shared__ int s_sorted[YSM_TIE_CAP];
+  __shared__ int s_count;
+  __shared__ unsigned s_bits[8];
+  __shared__ double s_acc[4];
+  __shared__ int s_n;
+
+  const PassDev ps = passes[blockIdx.x];
+  const uint32_t* psums = sums + ps.sums_off;
+  const int nposes = ps.nX * ps.nY * ps.nA;
+  const double denom = (double)((unsigned)ps.P * 100u);
+  const int tid = threadIdx.x;
+  if (tid == 0) s_count = 0;
+
+  // best response (init -1)
+  double best = -1.0;
+  for (int i = tid; i < nposes; i += blockDim.x) {
+    const double r = pose_response(ps, pen, psums, i, denom);
+    best = r > best ? r : best;
+  }
+  best = block_reduce_max(best, s_tmp);
+
+  // poses tied with the best, in storage order
+  for (int i = tid; i < nposes; i += blockDim.x) {
+    const double r = pose_response(ps, pen, psums, i, denom);
+    if (kt_double_equal(r, best)) {
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < YSM_TIE_CAP) s_list[pos] = i;
+    }
+  }
+  __syncthreads();
+  const int nt = s_count;
+  const double startX = -ps.offx, startY = -ps.offy;
+  const double* htrig = trig + 2 * (size_t)ps.htrig_off;
+  if (nt <= YSM_TIE_CAP) {
+    for (int e = tid; e < nt; e += blockDim.x) {
+      const int v = s_list[e];
+      int rank = 0;
+      for (int k = 0; k < nt; k++) rank += (s_list[k] < v);
+      s_sorted[rank] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+      for (int e = 0; e < nt; e++) {
+        const int idx = s_sorted[e];
+        const int iy = idx / (ps.nX * ps.nA);
+        const int rem = idx - iy * ps.nX * ps.nA;
+        const int ix = rem / ps.nA, a = rem - ix * ps.nA;
+        sx += ps.cx + (startX + (double)ix * ps.resx);
+        sy += ps.cy + (startY + (double)iy * ps.resy);
+        tx += htrig[2 * a];
+        ty += htrig[2 * a + 1];
+      }
+      s_acc[0] = sx; s_acc[1] = sy; s_acc[2] = tx; s_acc[3] = ty;
+      s_n = nt;
+    }
+  } else {
+    // degenerate case (e.g. best == 0: every pose ties): ordered chunks of blockDim poses,
+    // one thread accumulates sequentially so the rounding matches the CPU loop
+    double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+    int n = 0;
+    for (int c0 = 0; c0 < nposes; c0 += blockDim.x) {
+      const int i = c0 + tid;
+      bool tie = false;
+      if (i < nposes) tie = kt_double_equal(pose_response(ps, pen, psums, i, denom), best);
+      const unsigned bal = __ballot_sync(0xffffffffu, tie);
+      if ((tid & 31) == 0) s_bits[tid >> 5] = bal;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+          unsigned b = s_bits[w];
+          while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            const int idx = c0 + w * 32 + bit;
+            const int iy = idx / (ps.nX * ps.nA);
+            const int rem = idx - iy * ps.nX * ps.nA;
+            const int ix = rem / ps.nA, a = rem - ix * ps.nA;
+            sx += ps.cx + (startX + (double)ix * ps.resx);
+            sy += ps.cy + (startY + (double)iy * ps.resy);
+            tx += htrig[2 * a];
+            ty += htrig[2 * a + 1];
+            n++;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      s_acc[0] = sx; s_acc[1] = sy; s_acc[2] = tx; s_acc[3] = ty;
+      s_n = n;
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  const double cnt = (double)n;
+  const double avg_x = n > 0 ? s_acc[0] / cnt : 0.0;
+  const double avg_y = n > 0 ? s_acc[1] / cnt : 0.0;
+  PassOut* po = outs + blockIdx.x;
+  if (tid == 0) {
+    po->best = best;
+    po->avg_x = avg_x;
+    po->avg_y = avg_y;
+    po->tx = n > 0 ? s_acc[2] / cnt : 0.0;
+    po->ty = n > 0 ? s_acc[3] / cnt : 0.0;
+    po->n_ties = n;
+    po->pad = 0;
+  }
+  if (!ps.fine) {
+    // ComputePositionalCovariance accumulators over the (y, x) lattice; probs(x, y) is the
+    // max response over angles of that lattice cell (m_pSearchSpaceProbs).
+    double norm = 0.0, axx = 0.0, axy = 0.0, ayy = 0.0;
+    if (!(best < YSM_KT_TOLERANCE)) {
+      const double dx = avg_x - ps.cx, dy = avg_y - ps.cy;
+      const int ncell = ps.nX * ps.nY;
+      for (int c = tid; c < ncell; c += blockDim.x) {
+        const int iy = c / ps.nX, ix = c - iy * ps.nX;
+        double pm = 0.0;  // probs grid is cleared to 0 and max'ed with every response
+        for (int a = 0; a < ps.nA; a++) {
+          const double r = pose_response(ps, pen, psums, c * ps.nA + a, denom);
+          pm = r > pm ? r : pm;
+        }
+        if (pm >= (best - 0.1)) {
+          const double x = startX + (double)ix * ps.resx;
+          const double y = startY + (double)iy * ps.resy;
+          norm += pm;
+          axx += ((x - dx) * (x - dx) * pm);
+          axy += ((x - dx) * (y - dy) * pm);
+          ayy += ((y - dy) * (y - dy) * pm);
+        }
+      }
+    }
+    norm = block_reduce_sum(norm, s_tmp);
+    axx = block_reduce_sum(axx, s_tmp);
+    axy = block_reduce_sum(axy, s_tmp);
+    ayy = block_reduce_sum(ayy, s_tmp);
+    if (tid == 0) {
+      po->norm = norm; po->axx = axx; po->axy = axy; po->ayy = ayy;
+    }
+  } else {
+    // ComputeAngularCovariance: un-penalised GetResponse at the best cell for every fine angle
+    if (tid == 0) { po->norm = 0.0; po->axx = 0.0; po->axy = 0.0; po->ayy = 0.0; }
+    if (n > 0) {
+      const int gx = world_to_grid1(avg_x, ps.gox, g.scale) + g.border;
+      const int gy = world_to_grid1(avg_y, ps.goy, g.scale) + g.border;
+      const int base = gx + gy * g.stride;
+      const TableDev tb = tables[ps.table];
+      const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+      const unsigned dsz = (unsigned)g.data_size;
+      const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+      for (int a = warp; a < ps.nA; a += nwarps) {
+        const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
+        unsigned sum = 0;
+        for (int p = lane; p < ps.P; p += 32) {
+          const unsigned idx = (unsigned)(base + goff[p]);
+          if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) angsums[ps.ang_off + a] = (int)sum;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  trace_ray / run_raytracing_sweep (reference yag_slam/raytracing.py:63-92, numeric model
+// SURVEY Appendix F): one thread per (start, angle) ray; float32 state advanced in float64,
+// round-half-even cell index, uint8 map read through the read-only path.
+// cs = per-angle (cos, sin) evaluated on the host with libm.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_raywalk(const uint8_t* __restrict__ img, int h, int w, const double* __restrict__ cs,
+          int n_angles, const double* __restrict__ starts, int n_rays, float* __restrict__ out) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  const int s = ray / n_angles, a = ray - s * n_angles;
+  const double c = cs[2 * a], sn = cs[2 * a + 1];
+  const float spx = (float)starts[2 * s], spy = (float)starts[2 * s + 1];
+  float x = spx, y = spy;
+  bool run = true;
+  int guard = 4 * (w + h) + 16;
+  while (run && guard-- > 0) {
+    int yi = __float2int_rn(y), xi = __float2int_rn(x);
+    unsigned val = 0;
+    if (xi >= 0 && xi < w && yi >= 0 && yi < h) val = __ldg(img + (size_t)yi * w + xi);
+    if (val < 210u) run = false;
+    x = __double2float_rn((double)x + c);
+    y = __double2float_rn((double)y + sn);
+    if (val > 180u && val < 210u && !run) {
+      x = __double2float_rn((double)x + 1000.0 * c);
+      y = __double2float_rn((double)y + 1000.0 * sn);
+    }
+    yi = __float2int_rn(y);
+    xi = __float2int_rn(x);
+    if (yi < 1 || xi < 1 || xi >= w - 1 || yi >= h - 1) run = false;
+  }
+  const float dx = x - spx, dy = y - spy;
+  float* o = out + (size_t)ray * 5;
+  o[0] = spx; o[1] = spy; o[2] = x; o[3] = y;
+  o[4] = sqrtf(dx * dx + dy * dy);
+}
+
+}  // namespace ysm

@@ -1,0 +1,165 @@
+"""Drop-in replacement for the external `karto_scanmatcher` pybind11 module (reference
+setup.py:46), restricted to what yag_slam's untouched consumers import:
+    Wrapper, ScanMatcherConfig, LaserScanConfig, LocalizedRangeScan, Pose2
+(reference yag_slam/graph_slam.py:18, models.py:16-18, serde.py:19, helpers.py:20,
+test.py:18-20). Class names and attribute sets are exact because serde keys on them
+(yag_slam/serde.py:29-30,56-95).
+
+Call `install()` to register this module as `karto_scanmatcher` in sys.modules; then the
+reference's scan_matching.py / models.py / serde.py / graph_slam.py run unmodified with
+Wrapper.match_scan executing on the B200 kernels.
+"""
+import sys
+
+import numpy as np
+
+from . import _capi
+from .matcher import DEFAULTS, ScanMatcherB200, pack_pool
+
+
+class Pose2(object):
+    """karto Pose2(x, y, yaw) (reference serde.py:73, test.py:36)."""
+
+    def __init__(self, x=0.0, y=0.0, yaw=0.0):
+        self.x, self.y, self.yaw = float(x), float(y), float(yaw)
+
+    def __repr__(self):
+        return "Pose2(x={}, y={}, yaw={})".format(self.x, self.y, self.yaw)
+
+
+class LaserScanConfig(object):
+    """(min_angle, max_angle, angular_resolution, min_range, max_range, range_threshold,
+    sensor_name) -- reference serde.py:74-86, models.py:38, test.py:27."""
+
+    def __init__(self, min_angle, max_angle, angular_resolution, min_range, max_range, range_threshold,
+                 sensor_name=""):
+        self.min_angle = float(min_angle)
+        self.max_angle = float(max_angle)
+        self.angular_resolution = float(angular_resolution)
+        self.min_range = float(min_range)
+        self.max_range = float(max_range)
+        self.range_threshold = float(range_threshold)
+        self.sensor_name = sensor_name
+
+
+class LocalizedRangeScan(object):
+    """(config, ranges, odom_pose, corrected_pose, num, time) with mutable num / odom_pose /
+    corrected_pose (reference models.py:37-39,62,72,75; test.py:30-34).
+
+    Like Karto's LocalizedRangeScan it caches its filtered world point readings and refreshes
+    them when the corrected pose changes (LocalizedRangeScan::Update); the sensor
+    pose is the corrected pose (yag_slam passes no laser offset)."""
+
+    def __init__(self, config, ranges, odom_pose, corrected_pose, num=0, time=0.0):
+        self.config = config
+        self.ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+        self._odom_pose = odom_pose
+        self._corrected_pose = corrected_pose
+        self.num = num
+        self.time = time
+        self._points = None
+
+    @property
+    def odom_pose(self):
+        return self._odom_pose
+
+    @odom_pose.setter
+    def odom_pose(self, p):
+        self._odom_pose = p
+
+    @property
+    def corrected_pose(self):
+        return self._corrected_pose
+
+    @corrected_pose.setter
+    def corrected_pose(self, p):
+        self._corrected_pose = p
+        self._points = None
+
+    def sensor_pose(self):
+        p = self._corrected_pose
+        return (p.x, p.y, p.yaw)
+
+    def point_readings(self):
+        if self._points is None:
+            c, p = self.config, self._corrected_pose
+            self._points = _capi.point_readings(self.ranges, c.min_angle, c.angular_resolution, c.min_range,
+                                                c.range_threshold, p.x, p.y, p.yaw)
+        return self._points
+
+
+class ScanMatcherConfig(object):
+    """Default-constructible; its public attributes are exactly the parameter keys of
+    yag_slam/helpers.py:339-351 (serde enumerates them with dir(), serde.py:88-92)."""
+
+    def __init__(self):
+        for k, v in DEFAULTS.items():
+            if k != "minimum_distance_penalty":
+                setattr(self, k, v)
+        self._minimum_distance_penalty = DEFAULTS["minimum_distance_penalty"]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k in DEFAULTS if k != "minimum_distance_penalty"}
+        d["minimum_distance_penalty"] = self._minimum_distance_penalty
+        return d
+
+
+class MatchResult(object):
+    """What Wrapper.match_scan returns: .response, .covariance (3x3), .best_pose (Pose2)."""
+
+    def __init__(self, response, covariance, best_pose):
+        self.response = response
+        self.covariance = covariance
+        self.best_pose = best_pose
+
+
+class Wrapper(object):
+    """karto_scanmatcher.Wrapper(config) (reference scan_matching.py:38,41; test.py:25,38).
+    The GPU handle is created on construction, like ScanMatcher::Create."""
+
+    def __init__(self, config, device=0, max_slots=0, max_grid_bytes=0):
+        self.config = config
+        cfg = config.as_dict() if hasattr(config, "as_dict") else dict(config)
+        self._m = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
+
+    @property
+    def matcher(self):
+        return self._m
+
+    def match_scan(self, query, base_scans, penalty=True, do_fine=False):
+        return self.match_scan_batch([query], [base_scans], penalty, do_fine)[0]
+
+    def match_scan_batch(self, queries, base_sets, penalty=True, do_fine=False):
+        """Independent (query, base set) matches in one launch sequence. Scans shared between
+        matches are uploaded once."""
+        index, scans = {}, []
+
+        def sid(s):
+            k = id(s)
+            if k not in index:
+                index[k] = len(scans)
+                scans.append(s)
+            return index[k]
+
+        qidx = [sid(q) for q in queries]
+        base_ptr, base_idx = [0], []
+        for bs in base_sets:
+            base_idx.extend(sid(b) for b in bs)
+            base_ptr.append(len(base_idx))
+        pool, starts, counts = pack_pool([s.point_readings() for s in scans])
+        poses = np.array([q.sensor_pose() for q in queries], dtype=np.float64).reshape(-1, 3)
+        res = self._m.match_pool(pool, starts, counts, qidx, poses, base_ptr, base_idx, penalty, do_fine)
+        return [MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
+                            Pose2(float(r["x"]), float(r["y"]), float(r["heading"]))) for r in res]
+
+
+def create_occupancy_grid(scans, resolution, range_threshold):
+    """karto_scanmatcher.create_occupancy_grid (reference graph_slam.py:341-342). SURVEY.md 8f-1
+    ranks it as the first "next" row; it is not part of the hot path built so far."""
+    raise NotImplementedError("create_occupancy_grid: SURVEY.md 8(f)-1, not built yet")
+
+
+def install(name="karto_scanmatcher"):
+    """Register this module under the reference's import name."""
+    sys.modules[name] = sys.modules[__name__]
+    return sys.modules[__name__]
