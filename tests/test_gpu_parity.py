@@ -1,0 +1,394 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs. Bars (BASELINE.json north_star):
+  * response and best pose: BIT-EXACT (the response sums are integers; every transcendental
+    is evaluated by the same libm on both sides);
+  * covariance: relative error <= 1e-5 (COV_RTOL below; the positional sums are reduced in
+    parallel on the GPU, sequentially on the CPU);
+  * intermediate products (smear kernel, correlation grid bytes, lookup-offset tables): exact.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+COV_RTOL = 1e-5
+LOOP = dict(search_size=4.0, resolution=0.05)
+
+
+def _matcher(cfg=None, **kw):
+    from yag_slam_b200.matcher import ScanMatcherB200
+    return ScanMatcherB200(cfg, **kw)
+
+
+def _run(m, b, penalty, do_fine):
+    return m.match_pool(b["pool"], b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"],
+                        b["base_idx"], penalty, do_fine)
+
+
+def _assert_parity(out, ref, what=""):
+    ref = np.asarray(ref).reshape(-1, 13)
+    assert len(out) == len(ref)
+    assert (out["status"] == 0).all()
+    for k, col in (("response", 0), ("x", 1), ("y", 2), ("heading", 3)):
+        bad = np.where(out[k].view(np.uint64) != ref[:, col].copy().view(np.uint64))[0]
+        assert len(bad) == 0, f"{what}: {k} differs at matches {bad[:8]}: gpu {out[k][bad[:4]]} ref {ref[bad[:4], col]}"
+    cov, rc = out["cov"], ref[:, 4:]
+    err = np.abs(cov - rc)
+    tol = COV_RTOL * np.abs(rc)
+    assert (err <= tol).all(), f"{what}: covariance rel err {np.max(err / np.maximum(np.abs(rc), 1e-300)):.3e}"
+
+
+def test_smear_kernel_exact():
+    from oracle.oracle import KartoOracle
+    for cfg in (None, LOOP, dict(search_size=0.3, smear_deviation=0.07), dict(smear_deviation=0.03)):
+        m = _matcher(cfg, max_slots=1)
+        o = KartoOracle(cfg)
+        d, od = m.dims(), o.dims()
+        for k in ("side", "margin", "roi", "half_kernel", "kernel_size", "border", "width", "height", "stride"):
+            assert d[k] == od[k], k
+        assert d["grid_bytes"] == od["data_size"]
+        assert (m.debug_kernel() == o.kernel()).all()
+        m.close()
+
+
+def test_correlation_grid_bytes_and_offset_tables_exact(world):
+    import scenarios
+    from oracle.oracle import KartoOracle
+    from yag_slam_b200 import _capi
+    for cfg, P, nb, seed in ((None, 360, 1, 21), (None, 720, 10, 22), (LOOP, 720, 10, 23),
+                             (dict(search_size=0.3, smear_deviation=0.07), 500, 3, 24)):
+        b = scenarios.make_batch(world, 3, P, nb, seed)
+        m = _matcher(cfg, max_slots=4)
+        m.set_debug(_capi.DEBUG_KEEP_GRIDS)
+        _run(m, b, False, False)
+        o = KartoOracle(cfg)
+        for i in range(3):
+            bases = [b["points"][s] for s in b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]]]
+            ref_grid = o.build_grid(b["query_pose"][i], bases)
+            got = m.debug_grid(i)
+            assert ref_grid.max() == 100
+            assert (got == ref_grid).all(), f"grid bytes differ: {np.argwhere(got != ref_grid)[:5]}"
+            q = b["points"][b["query_scan"][i]]
+            pose = b["query_pose"][i]
+            cfgd = o.params
+            ref_off = o.compute_offsets(q, pose, pose[2], cfgd.coarse_search_angle_offset, cfgd.coarse_angle_resolution)
+            got_off = m.debug_offsets(i)
+            assert got_off.shape == ref_off.shape and (got_off == ref_off).all()
+        # after the debug flag is dropped the slots are cleared again: a different batch is exact
+        m.set_debug(0)
+        b2 = scenarios.make_batch(world, 3, P, nb, seed + 100)
+        _assert_parity(_run(m, b2, True, True), scenarios.oracle_results(cfg, b2, True, True), "after-clear")
+        m.close()
+
+
+def test_committed_golden_vectors():
+    g = np.load(os.path.join(HERE, "golden", "matcher_golden.npz"))
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_matcher_golden as mk
+    for name, (cfg, kw, pen, fine) in mk.CASES.items():
+        m = _matcher(cfg, max_slots=8)
+        b = {k: g[f"{name}_{k}"] for k in ("pool", "starts", "counts", "query_scan", "query_pose", "base_ptr", "base_idx")}
+        _assert_parity(_run(m, b, pen, fine), g[f"{name}_ref"], name)
+        m.close()
+    # the reference's own smoke geometry (test.py:23-43)
+    from yag_slam_b200.matcher import pack_pool
+    pool, starts, counts = pack_pool([g["testpy_query"], g["testpy_base"]])
+    m = _matcher(None, max_slots=1)
+    out = m.match_pool(pool, starts, counts, [0], g["testpy_pose"][None, :], [0, 1], [1], True, True)
+    _assert_parity(out, g["testpy_ref"][None, :], "test.py geometry")
+    m.close()
+
+
+@pytest.mark.parametrize("penalty,do_fine", [(True, True), (True, False), (False, True), (False, False)])
+def test_seq_config_vs_oracle(world, penalty, do_fine):
+    import scenarios
+    b = scenarios.make_batch(world, 16, 720, 10, 31)
+    m = _matcher(None, max_slots=16)
+    _assert_parity(_run(m, b, penalty, do_fine), scenarios.oracle_results(None, b, penalty, do_fine), "seq")
+    m.close()
+
+
+def test_loop_config_with_degenerate_chains_and_expansion(world):
+    import scenarios
+    b = scenarios.make_batch(world, 40, 720, 10, 4, perturb=(1.0, 0.2), degenerate_frac=0.25)
+    m = _matcher(LOOP)
+    out = _run(m, b, False, False)
+    _assert_parity(out, scenarios.oracle_results(LOOP, b, False, False), "loop")
+    assert (out["n_passes"] == 4).sum() >= 4  # degenerate chains ran all three expansions
+    assert (out["n_ties"][out["n_passes"] == 4] == 41 * 41 * 81).all()
+    # expansion disabled: a single pass for the same chains
+    cfg = dict(LOOP, use_response_expansion=False)
+    m2 = _matcher(cfg)
+    out2 = _run(m2, b, False, True)
+    _assert_parity(out2, scenarios.oracle_results(cfg, b, False, True), "loop-noexp")
+    m.close()
+    m2.close()
+
+
+def test_shared_query_and_multiwave(world):
+    import scenarios
+    b = scenarios.make_batch(world, 32, 720, 10, 5, perturb=(1.0, 0.2), shared_query=True)
+    ref = scenarios.oracle_results(LOOP, b, False, False)
+    m = _matcher(LOOP)
+    _assert_parity(_run(m, b, False, False), ref, "shared")
+    m.close()
+    m = _matcher(LOOP, max_slots=5)  # 7 waves
+    _assert_parity(_run(m, b, False, False), ref, "shared-multiwave")
+    m.close()
+
+
+def test_ragged_and_empty_inputs(world):
+    import scenarios
+    from yag_slam_b200.matcher import pack_pool
+    b = scenarios.make_batch(world, 3, 360, 2, 41)
+    pts = list(b["points"])
+    empty = len(pts)
+    pts.append(np.zeros((0, 2)))
+    short = len(pts)
+    pts.append(pts[0][:7].copy())
+    pool, starts, counts = pack_pool(pts)
+    q = b["query_scan"]
+    query_scan = [q[0], empty, q[1], short, q[2]]
+    poses = np.array([b["query_pose"][0], [1.0, 2.0, 0.3], b["query_pose"][1], b["query_pose"][0], b["query_pose"][2]])
+    base_ptr = [0, 2, 4, 4, 6, 9]  # third match has NO base scans; last has 3 incl. an empty one
+    bi = b["base_idx"]
+    base_idx = [bi[0], bi[1], bi[0], bi[1], bi[2], bi[3], bi[4], empty, bi[5]]
+    bb = dict(pool=pool, starts=starts, counts=counts, query_scan=np.array(query_scan, np.int32), query_pose=poses,
+              base_ptr=np.array(base_ptr, np.int32), base_idx=np.array(base_idx, np.int32))
+    m = _matcher(None, max_slots=2)
+    out = _run(m, bb, True, True)
+    _assert_parity(out, scenarios.oracle_results(None, bb, True, True), "ragged")
+    assert out["response"][1] == 0.0 and out["n_passes"][1] == 0 and out["cov"][1][0] == 500.0  # empty query
+    assert out["n_passes"][2] == 5  # no base points: coarse + 3 expansions + fine
+    assert len(m.match_pool(pool, starts, counts, [], np.zeros((0, 3)), [0], [], True, True)) == 0
+    m.close()
+
+
+def test_ros_node_config_and_other_resolutions(world):
+    import scenarios
+    for cfg, P in ((dict(search_size=0.3, smear_deviation=0.07), 720), (dict(resolution=0.02, search_size=0.6), 360),
+                   (dict(smear_deviation=0.03, coarse_angle_resolution=0.02, fine_search_angle_resolution=0.002), 500)):
+        b = scenarios.make_batch(world, 6, P, 5, 51)
+        m = _matcher(cfg, max_slots=6)
+        _assert_parity(_run(m, b, True, True), scenarios.oracle_results(cfg, b, True, True), str(cfg))
+        m.close()
+
+
+def test_parameter_errors():
+    with pytest.raises(ValueError):
+        _matcher(dict(smear_deviation=0.2))  # > 10 * resolution (Karto runtime_error)
+    with pytest.raises(ValueError):
+        _matcher(dict(smear_deviation=0.001))
+    with pytest.raises(NotImplementedError):
+        _matcher(dict(resolution=0.005, search_size=1.0))  # smear = 10 * res: order-dependent Karto regime
+
+
+def test_dropin_api_single_and_batch(world):
+    """Scan2DMatcherCpp.match_scan / match_scan_batch (reference scan_matching.py:32-42) with
+    yag_slam.models.LocalizedRangeScan-like objects (`._scan` is the karto-compatible scan)."""
+    from oracle.oracle import KartoOracle
+    from yag_slam_b200 import karto_compat as kc
+    from yag_slam_b200 import synth
+    from yag_slam_b200.scan_matching import Scan2DMatcherCpp
+
+    class Scan(object):  # the part of yag_slam/models.py the matcher touches
+        def __init__(self, ranges, lp, pose):
+            cfg = kc.LaserScanConfig(lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], "")
+            self._scan = kc.LocalizedRangeScan(cfg, ranges, kc.Pose2(*pose), kc.Pose2(*pose), 0, 0.0)
+
+    P = 360
+    lp = synth.laser_params(P)
+    rng = np.random.default_rng(61)
+    path = synth.loop_path(12)
+    scans = [Scan(synth.cast_scan(world, p, P, rng), lp, p + rng.normal(0, [0.03, 0.03, 0.01])) for p in path]
+    seq = Scan2DMatcherCpp({}, max_slots=8)
+    o = KartoOracle()
+    singles = []
+    for k in range(4, 12):
+        r = seq.match_scan(scans[k], scans[k - 4:k], True, True)
+        er, ep, ec = o.match(scans[k]._scan.point_readings(), scans[k]._scan.sensor_pose(),
+                             [s._scan.point_readings() for s in scans[k - 4:k]], True, True)
+        assert r.response == er and r.meta is None
+        assert (r.best_pose.x, r.best_pose.y) == (ep[0], ep[1]) and abs(r.best_pose.euler[-1] - ep[2]) < 1e-12
+        assert np.allclose(np.array(r.covariance), ec, rtol=COV_RTOL, atol=0)
+        assert np.linalg.inv(np.array(r.covariance)).shape == (3, 3) and r.covariance[0][0] > 0
+        singles.append(r)
+    batch = seq.match_scan_batch(scans[4:12], [scans[k - 4:k] for k in range(4, 12)], True, True)
+    for a, b in zip(singles, batch):
+        assert a.response == b.response and a.best_pose.x == b.best_pose.x and a.best_pose.y == b.best_pose.y
+    loop = Scan2DMatcherCpp({}, loop=True, max_slots=8)
+    assert loop.config.resolution == 0.05 and loop.config.search_size == 4.0
+    r = loop.match_scan(scans[11], scans[0:10], False, False)
+    assert 0 < r.response <= 1
+    with pytest.raises(TypeError):
+        Scan2DMatcherCpp(None)  # reference: dict.update(None) raises (scan_matching.py:36)
+
+
+def test_sequential_mapping_loop_matches_oracle(world):
+    """cfg-2 shaped driver: loop-carried running-scan matching (graph_slam.py:306-339 without the
+    graph bookkeeping), GPU vs oracle pose-for-pose."""
+    from oracle.oracle import KartoOracle
+    from yag_slam_b200 import _capi, synth
+    from yag_slam_b200.matcher import pack_pool
+    P, n = 720, 40
+    lp = synth.laser_params(P)
+    rng = np.random.default_rng(2)
+    path = synth.loop_path(n)
+    odom = synth.noisy_odometry(path, rng)
+    ranges = [synth.cast_scan(world, p, P, rng) for p in path]
+    m = _matcher(None, max_slots=1)
+    o = KartoOracle()
+
+    def run(match_fn):
+        corrected = [odom[0].copy()]
+        pts = [_capi.point_readings(ranges[0], lp[0], lp[2], lp[3], lp[5], *corrected[0])]
+        resp = []
+        for k in range(1, n):
+            d = odom[k] - odom[k - 1]
+            c, s = np.cos(odom[k - 1][2]), np.sin(odom[k - 1][2])
+            loc = np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1], d[2]])
+            c, s = np.cos(corrected[-1][2]), np.sin(corrected[-1][2])
+            guess = corrected[-1] + np.array([c * loc[0] - s * loc[1], s * loc[0] + c * loc[1], loc[2]])
+            q = _capi.point_readings(ranges[k], lp[0], lp[2], lp[3], lp[5], *guess)
+            r, pose = match_fn(q, guess, pts[-10:])
+            resp.append(r)
+            corrected.append(np.array(pose))
+            pts.append(_capi.point_readings(ranges[k], lp[0], lp[2], lp[3], lp[5], *pose))
+        return np.array(resp), np.array(corrected)
+
+    def gpu_fn(q, guess, bases):
+        pool, starts, counts = pack_pool([q] + list(bases))
+        r = m.match_pool(pool, starts, counts, [0], guess[None, :], [0, len(bases)], np.arange(1, len(bases) + 1), True, True)[0]
+        return r["response"], (r["x"], r["y"], r["heading"])
+
+    def cpu_fn(q, guess, bases):
+        r, p, _ = o.match(q, guess, bases, True, True)
+        return r, p
+
+    gr, gc = run(gpu_fn)
+    cr, cc = run(cpu_fn)
+    assert (gr == cr).all() and (gc == cc).all()
+    assert np.abs(gc[:, :2] - path[:, :2]).max() < 0.25
+    m.close()
+
+
+def test_fullsize_loop_closure_batch_properties(world):
+    """BASELINE cfg 3 size: one query vs 4,096 candidate chains x 10 scans (P=720, loop config,
+    expansion on, 10% degenerate). Size-independent properties + an oracle-checked sample."""
+    import scenarios
+    n = 4096
+    b = scenarios.make_batch(world, n, 720, 10, 3, perturb=(1.0, 0.2), degenerate_frac=0.1, shared_query=True)
+    m = _matcher(LOOP)
+    out = _run(m, b, False, False)
+    assert m.launch_count() > 0 and (out["status"] == 0).all()
+    # (a) permutation invariance: shuffling the chains permutes the results, bit for bit
+    perm = np.random.default_rng(0).permutation(n)
+    nb = np.diff(b["base_ptr"])
+    base_ptr = np.concatenate([[0], np.cumsum(nb[perm])]).astype(np.int32)
+    base_idx = np.concatenate([b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]] for i in perm]).astype(np.int32)
+    bp = dict(b, query_scan=b["query_scan"][perm], query_pose=b["query_pose"][perm], base_ptr=base_ptr, base_idx=base_idx)
+    outp = _run(m, bp, False, False)
+    assert outp.tobytes() == out[perm].tobytes()
+    # (b) idempotence / determinism: a second run is byte-identical (grids were cleared correctly)
+    assert _run(m, b, False, False).tobytes() == out.tobytes()
+    # (c) chains that are the same scan set give the same record (the generator cycles 7 sets)
+    key = [tuple(b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]]) for i in range(n)]
+    first = {}
+    for i, k in enumerate(key):
+        if k in first:
+            assert out[i].tobytes() == out[first[k]].tobytes()
+        else:
+            first[k] = i
+    # (d) base-scan order does not matter (the smear is a pure max)
+    rev = np.concatenate([b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]][::-1] for i in range(64)]).astype(np.int32)
+    br = dict(b, query_scan=b["query_scan"][:64], query_pose=b["query_pose"][:64], base_ptr=b["base_ptr"][:65], base_idx=rev)
+    assert _run(m, br, False, False).tobytes() == out[:64].tobytes()
+    # (e) every distinct chain set against the oracle
+    idx = np.array(sorted(first.values()))[:16]
+    sub_ptr = np.concatenate([[0], np.cumsum(nb[idx])]).astype(np.int32)
+    sub_idx = np.concatenate([b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]] for i in idx]).astype(np.int32)
+    bs = dict(b, query_scan=b["query_scan"][idx], query_pose=b["query_pose"][idx], base_ptr=sub_ptr, base_idx=sub_idx)
+    _assert_parity(out[idx], scenarios.oracle_results(LOOP, bs, False, False), "cfg3 sample")
+    # responses are multiples of 1 / (P * 100) (integer sums), no penalty
+    P = b["counts"][b["query_scan"][0]]
+    q = out["response"] * (P * 100)
+    assert np.abs(q - np.round(q)).max() < 1e-6
+    m.close()
+
+
+def test_fullsize_sequential_log_rematch_properties(world):
+    """BASELINE cfg 2 size: 2,000 scans x 720 beams re-matched against their 10 running scans
+    (the bench workload). Wave-size independence + an oracle-checked sample."""
+    import scenarios
+    n = 2000
+    b = scenarios.make_batch(world, n, 720, 10, 2, perturb=(0.1, 0.05))
+    m = _matcher(None)
+    out = _run(m, b, True, True)
+    m.close()
+    m2 = _matcher(None, max_slots=333)
+    out2 = _run(m2, b, True, True)
+    m2.close()
+    assert out.tobytes() == out2.tobytes()
+    idx = np.arange(0, n, 67)
+    nb = np.diff(b["base_ptr"])
+    sub_ptr = np.concatenate([[0], np.cumsum(nb[idx])]).astype(np.int32)
+    sub_idx = np.concatenate([b["base_idx"][b["base_ptr"][i]:b["base_ptr"][i + 1]] for i in idx]).astype(np.int32)
+    bs = dict(b, query_scan=b["query_scan"][idx], query_pose=b["query_pose"][idx], base_ptr=sub_ptr, base_idx=sub_idx)
+    _assert_parity(out[idx], scenarios.oracle_results(None, bs, True, True), "cfg2 sample")
+    assert (out["response"] > 0.5).mean() > 0.95  # the log re-matches well
+
+
+def test_highres_config_one_match(world):
+    """BASELINE cfg 4 shape (P=1081, res 0.005, search 1.0, fine 0.00175) with smear 0.045
+    (K=37). smear = 10*res exactly is Karto's order-dependent regime, not supported yet."""
+    import scenarios
+    cfg = dict(resolution=0.005, search_size=1.0, fine_search_angle_resolution=0.00175, smear_deviation=0.045)
+    b = scenarios.make_batch(world, 2, 1081, 1, 4, perturb=(0.1, 0.03))
+    m = _matcher(cfg, max_slots=2)
+    assert m.dims()["roi"] == 8201 and m.dims()["kernel_size"] == 37
+    _assert_parity(_run(m, b, True, True), scenarios.oracle_results(cfg, b, True, True), "cfg4-like")
+    m.close()
+
+
+def test_device_resident_pool_and_stream(world):
+    import torch
+    import scenarios
+    b = scenarios.make_batch(world, 12, 720, 10, 71)
+    m = _matcher(None, max_slots=12)
+    ref = _run(m, b, True, True)
+    dpool = torch.from_numpy(b["pool"]).cuda()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        out = m.match_pool(dpool, b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"],
+                           b["base_idx"], True, True, stream=st.cuda_stream)
+    assert out.tobytes() == ref.tobytes()
+    pinned = torch.from_numpy(b["pool"]).pin_memory()
+    out = m.match_pool(pinned, b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"],
+                       b["base_idx"], True, True)
+    assert out.tobytes() == ref.tobytes()
+    m.close()
+
+
+def test_single_rank_nccl_gather(world):
+    import torch
+    import torch.distributed as dist
+    import scenarios
+    from yag_slam_b200 import distributed
+    b = scenarios.make_batch(world, 9, 360, 3, 81)
+    m = _matcher(None, max_slots=9)
+    ref = _run(m, b, True, True)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda:0"))
+    try:
+        full = distributed.match_pool_sharded(m.match_pool, b["pool"], b["starts"], b["counts"], b["query_scan"],
+                                              b["query_pose"], b["base_ptr"], b["base_idx"], True, True,
+                                              device=torch.device("cuda:0"))
+    finally:
+        dist.destroy_process_group()
+    assert full.tobytes() == ref.tobytes()
+    m.close()

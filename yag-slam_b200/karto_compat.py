@@ -98,7 +98,7 @@ class ScanMatcherConfig(object):
                 setattr(self, k, v)
         self._minimum_distance_penalty = DEFAULTS["minimum_distance_penalty"]
 
-    def as_dict(self):
+    def _as_dict(self):
         d = {k: getattr(self, k) for k in DEFAULTS if k != "minimum_distance_penalty"}
         d["minimum_distance_penalty"] = self._minimum_distance_penalty
         return d
@@ -119,7 +119,7 @@ class Wrapper(object):
 
     def __init__(self, config, device=0, max_slots=0, max_grid_bytes=0):
         self.config = config
-        cfg = config.as_dict() if hasattr(config, "as_dict") else dict(config)
+        cfg = config._as_dict() if hasattr(config, "_as_dict") else dict(config)
         self._m = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
 
     @property
