@@ -138,6 +138,13 @@ int64_t ysm_launch_count(const ysm_handle *h);
 int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, double *reduce_ms,
                        double *total_ms);
 
+/* work done by the last ysm_match_batch call (for roofline accounting in bench.py):
+ * out[0] grid lookups of the coarse lattice sweeps (L), out[1] lattice sweep launches,
+ * out[2] lookup-offset table entries computed (T), out[3] poses evaluated,
+ * out[4] grid lookups of the fine / angular-covariance passes, out[5] base points stamped (upper bound),
+ * out[6] host->device bytes, out[7] device->host bytes */
+int ysm_last_work(const ysm_handle *h, int64_t out[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,7 +45,7 @@ assert RESULT_DTYPE.itemsize == 128
 EXPORTS = [
     "ysm_create", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
     "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
-    "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms",
+    "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def lib():
     L.ysm_launch_count.argtypes = [vp]
     L.ysm_last_kernel_ms.restype = C.c_int
     L.ysm_last_kernel_ms.argtypes = [vp] + [C.POINTER(f64)] * 4
+    L.ysm_last_work.restype = C.c_int
+    L.ysm_last_work.argtypes = [vp, C.POINTER(C.c_int64)]
     _lib = L
     return L
 

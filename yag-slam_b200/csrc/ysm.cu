@@ -176,6 +176,7 @@ struct ysm_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
+  int64_t work[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 #define CK(call)                                                                     \
@@ -352,6 +353,12 @@ extern "C" int ysm_set_debug(ysm_handle* h, int32_t flags) {
 
 extern "C" int64_t ysm_launch_count(const ysm_handle* h) { return h ? h->launches : 0; }
 
+extern "C" int ysm_last_work(const ysm_handle* h, int64_t out[8]) {
+  if (!h || !out) return YSM_EINVAL;
+  for (int i = 0; i < 8; i++) out[i] = h->work[i];
+  return YSM_OK;
+}
+
 extern "C" int ysm_last_kernel_ms(const ysm_handle* h, double* sweep_ms, double* build_ms,
                                   double* reduce_ms, double* total_ms) {
   if (!h) return YSM_EINVAL;
@@ -460,6 +467,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   const GridC& g = h->g;
   const bool timing = (h->debug & YSM_DEBUG_TIME_KERNELS) && h->ev_ok;
   h->t_sweep = h->t_build = h->t_reduce = h->t_total = 0.0;
+  for (int i = 0; i < 8; i++) h->work[i] = 0;
   if (b->n_matches == 0) return YSM_OK;
 
   // deferred clear from a previous KEEP_GRIDS batch
@@ -493,6 +501,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     CK(h->d_pool.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
     if (b->n_points > 0)
       CK(cudaMemcpyAsync(h->d_pool.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
+    h->work[6] += (int64_t)b->n_points * 16;
     d_pool = (const double*)h->d_pool.p;
   }
   CK(h->d_scan_start.ensure((size_t)std::max(1, b->n_scans) * 4));
@@ -500,6 +509,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   if (b->n_scans > 0) {
     CK(cudaMemcpyAsync(h->d_scan_start.p, b->scan_start, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_scan_count.p, b->scan_count, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
+    h->work[6] += (int64_t)b->n_scans * 8;
   }
 
   if (timing) CK(cudaEventRecord(h->ev[6], st));
@@ -594,6 +604,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     CK(cudaMemcpyAsync(h->d_matches.p, hm.data(), sizeof(MatchDev) * (size_t)nw, cudaMemcpyHostToDevice, st));
     if (!hbase.empty())
       CK(cudaMemcpyAsync(h->d_base_idx.p, hbase.data(), hbase.size() * 4, cudaMemcpyHostToDevice, st));
+    h->work[6] += (int64_t)(sizeof(MatchDev) * (size_t)nw + hbase.size() * 4);
+    h->work[5] += cells_total;
 
     // ---- K1: grid build -----------------------------------------------------------------------
     if (timing) CK(cudaEventRecord(h->ev[0], st));
@@ -719,6 +731,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         hph.push_back(ph);
         if (!ph.fine) {
           for (int a = 0; a < ph.nA; a++) hpa.push_back(PassAngle{pid, a});
+          h->work[0] += (int64_t)ph.nX * ph.nY * ph.nA * s.P;
           max_lat_P = std::max(max_lat_P, s.P);
           max_lat_nx = std::max(max_lat_nx, ph.nX);
           max_lat_ny = std::max(max_lat_ny, ph.nY);
@@ -731,6 +744,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
           }
         } else {
           hfine.push_back(pid);
+          h->work[4] += (int64_t)(ph.nX * ph.nY + 1) * ph.nA * s.P;
           max_fine_poses = std::max(max_fine_poses, ph.nX * ph.nY * ph.nA);
         }
       }
@@ -755,6 +769,10 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       if (!hfine.empty()) memcpy(hb + o_fine, hfine.data(), sizeof(int) * hfine.size());
       memcpy(hb + o_trig, htrig.data(), sizeof(double) * htrig.size());
       CK(cudaMemcpyAsync(h->d_blob.p, hb, blob, cudaMemcpyHostToDevice, st));
+      h->work[6] += (int64_t)blob;
+      h->work[7] += (int64_t)(sizeof(PassOut) * (size_t)npass + (size_t)ang_elems * 4);
+      h->work[2] += (int64_t)off_elems;
+      h->work[3] += (int64_t)sums_elems;
       const char* db = (const char*)h->d_blob.p;
       const TableDev* d_tab = (const TableDev*)(db + o_tab);
       const PassDev* d_pass = (const PassDev*)(db + o_pass);
@@ -808,6 +826,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
                                                           h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
         }
         h->launches++;
+        h->work[1]++;
       }
       if (timing) CK(cudaEventRecord(h->ev[3], st));
       if (!hfine.empty()) {
