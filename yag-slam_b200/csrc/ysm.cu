@@ -389,12 +389,18 @@ extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_an
 }
 
 // --------------------------------------------------------------------------------------------
+// CTAs per match for the stamp / clear kernels: a match's CTAs are adjacent in launch order, so
+// with >= 24 of them only a few dozen matches are in flight and their grid lines stay in L2.
+static int stamp_chunks(const ysm_handle* h, int n) {
+  return std::max(24, std::min(96, (h->num_sms * 8 + n - 1) / n));
+}
+
 // clear the footprint of a set of matches (wave) -- the grids return to all-zero
 static int clear_wave(ysm_handle* h, const MatchDev* d_matches, int n, cudaStream_t st) {
   if (n <= 0) return YSM_OK;
   const GridC& g = h->g;
   const size_t smem = (size_t)4 * g.K * g.Wk * 4;
-  int chunks = std::max(1, std::min(64, (h->num_sms * 8 + n - 1) / n));
+  const int chunks = stamp_chunks(h, n);
   dim3 grid(chunks, n);
   k_stamp<<<grid, 256, smem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p, (const int*)h->d_cellcount.p,
                                     h->d_kernel, h->d_grids, 1);
@@ -622,7 +628,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
                                                    (int*)h->d_cellcount.p, pmax);
       h->launches++;
       const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
-      int chunks = std::max(1, std::min(64, (h->num_sms * 8 + nw - 1) / nw));
+      const int chunks = stamp_chunks(h, nw);
       dim3 grid(chunks, nw);
       k_stamp<<<grid, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
                                         (const int*)h->d_cellcount.p, h->d_kernel, h->d_grids, 0);
@@ -798,32 +804,38 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       // ---- K3 sweeps ----------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[2], st));
       if (!hpa.empty()) {
-        // enough CTAs to fill the machine: split lattice rows, then the points, when the batch is small
+        // one warp per lattice row-task; CTAs of up to 32 warps. Small batches: split the rows
+        // over more CTAs, then the points (atomic partial sums), until the machine is full.
         const int npa = (int)hpa.size();
-        const int target = h->num_sms * 8;
-        int task_chunks = 1, p_chunks = 1;
-        if (npa < target) {
-          task_chunks = std::min(std::max(1, (max_lat_tasks + 7) / 8), (target + npa - 1) / npa);
-          if (npa * task_chunks < target) p_chunks = std::min(std::max(1, max_lat_P / 64), (target + npa * task_chunks - 1) / (npa * task_chunks));
+        const int target = h->num_sms * 2;
+        int tpc = std::min(max_lat_tasks, 32);
+        int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+        int p_chunks = 1;
+        if (npa * task_chunks < target) {
+          const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
+          tpc = std::max(4, std::min(tpc, (max_lat_tasks + want - 1) / want));
+          task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+          if (npa * task_chunks < target)
+            p_chunks = std::min(std::max(1, max_lat_P / 64), (target + npa * task_chunks - 1) / (npa * task_chunks));
         }
-        const int tpc = (max_lat_tasks + task_chunks - 1) / task_chunks;
-        task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-        const int p_chunk = (max_lat_P + p_chunks - 1) / p_chunks;
+        int p_chunk = (max_lat_P + p_chunks - 1) / p_chunks;
+        p_chunk = (p_chunk + 7) & ~7;
         p_chunks = (max_lat_P + p_chunk - 1) / p_chunk;
-        const size_t smem = (size_t)(p_chunk + max_lat_nx + max_lat_ny) * 4;
+        const int threads = 32 * std::min(tpc, 32);
+        const size_t smem = (size_t)(((p_chunk + 3) & ~3) + max_lat_nx + max_lat_ny) * 4;
         if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
         dim3 grid(npa, task_chunks, p_chunks);
         if (p_chunks > 1) {
           CK(cudaMemsetAsync(h->d_sums.p, 0, sums_elems * 4, st));
           if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(k_sweep_lattice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_sweep_lattice<true><<<grid, 256, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                         h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
+          k_sweep_lattice<true><<<grid, threads, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                             h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
         } else {
           if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(k_sweep_lattice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_sweep_lattice<false><<<grid, 256, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                          h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
+          k_sweep_lattice<false><<<grid, threads, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                              h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
         }
         h->launches++;
         h->work[1]++;

@@ -296,21 +296,58 @@ k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict
 // ---------------------------------------------------------------------------------------------
 // K3  CorrelateScan / GetResponse sweep, lattice form (python twin
 // find_best_pose, yag_slam/helpers.py:156-295). CTA = one (pass, angle); the angle's lookup
-// offsets are staged in shared memory; a warp owns one lattice row (lanes = adjacent x poses, so
-// one warp load touches one contiguous span of a grid row); each lane accumulates its pose's
-// response as an exact integer. grid = (n_pass_angles, task_chunks, p_chunks).
+// offsets are staged in shared memory; ONE WARP PER LATTICE ROW (lanes = adjacent x poses, so a
+// warp load touches one contiguous span of a grid row) and all rows of the lattice walk the
+// query points together, so the rows' overlapping windows are served by L1 and only a dozen
+// matches are in flight chip-wide (their grid lines stay L2-resident). Each lane accumulates
+// its pose's response as an exact integer. grid = (n_pass_angles, task_chunks, p_chunks).
 // ---------------------------------------------------------------------------------------------
 struct PassAngle {
   int pass, a;
 };
 
+// s_off holds offsets biased by the CTA-wide minimum (so they are non-negative and extend to
+// 64 bits for free); gp / base already include that minimum.
+template <bool kChecked>
+__device__ __forceinline__ unsigned sweep_row(const uint8_t* __restrict__ gp, const unsigned* __restrict__ s_off,
+                                              int np, int base, unsigned dsz) {
+  unsigned sum0 = 0, sum1 = 0;
+  int p = 0;
+  for (; p + 8 <= np; p += 8) {
+    const uint4 o0 = *reinterpret_cast<const uint4*>(s_off + p);
+    const uint4 o1 = *reinterpret_cast<const uint4*>(s_off + p + 4);
+    unsigned v0, v1, v2, v3, v4, v5, v6, v7;
+    if (kChecked) {
+      v0 = ((unsigned)(base + o0.x) < dsz) ? (unsigned)__ldg(gp + o0.x) : 0u;
+      v1 = ((unsigned)(base + o0.y) < dsz) ? (unsigned)__ldg(gp + o0.y) : 0u;
+      v2 = ((unsigned)(base + o0.z) < dsz) ? (unsigned)__ldg(gp + o0.z) : 0u;
+      v3 = ((unsigned)(base + o0.w) < dsz) ? (unsigned)__ldg(gp + o0.w) : 0u;
+      v4 = ((unsigned)(base + o1.x) < dsz) ? (unsigned)__ldg(gp + o1.x) : 0u;
+      v5 = ((unsigned)(base + o1.y) < dsz) ? (unsigned)__ldg(gp + o1.y) : 0u;
+      v6 = ((unsigned)(base + o1.z) < dsz) ? (unsigned)__ldg(gp + o1.z) : 0u;
+      v7 = ((unsigned)(base + o1.w) < dsz) ? (unsigned)__ldg(gp + o1.w) : 0u;
+    } else {
+      v0 = __ldg(gp + o0.x); v1 = __ldg(gp + o0.y); v2 = __ldg(gp + o0.z); v3 = __ldg(gp + o0.w);
+      v4 = __ldg(gp + o1.x); v5 = __ldg(gp + o1.y); v6 = __ldg(gp + o1.z); v7 = __ldg(gp + o1.w);
+    }
+    sum0 += v0 + v1 + v2 + v3;
+    sum1 += v4 + v5 + v6 + v7;
+  }
+  for (; p < np; p++) {
+    const unsigned o = s_off[p];
+    if (!kChecked || (unsigned)(base + o) < dsz) sum0 += (unsigned)__ldg(gp + o);
+  }
+  return sum0 + sum1;
+}
+
 template <bool kAtomic>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __restrict__ pa_list,
                 const TableDev* __restrict__ tables, const int* __restrict__ offsets,
                 const uint8_t* __restrict__ grids, uint32_t* __restrict__ sums, int tasks_per_cta,
                 int p_chunk) {
-  extern __shared__ int s_i[];
+  extern __shared__ __align__(16) int s_i[];
+  __shared__ int s_minmax[4];  // min off, max off, min base, max base
   const PassAngle pa = pa_list[blockIdx.x];
   const PassDev ps = passes[pa.pass];
   const int nxc = (ps.nX + 31) >> 5;
@@ -321,22 +358,67 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
   const int pbeg = blockIdx.z * p_chunk;
   const int pend = min(ps.P, pbeg + p_chunk);
   if (pbeg >= pend) return;
-  int* s_off = s_i;                // [p_chunk]
-  int* s_col = s_i + p_chunk;      // [nX]
-  int* s_row = s_col + ps.nX;      // [nY]
+  const int pc4 = (p_chunk + 3) & ~3;
+  int* s_off = s_i;             // [pc4]
+  int* s_col = s_i + pc4;       // [nX]
+  int* s_row = s_col + ps.nX;   // [nY]
+  if (threadIdx.x == 0) {
+    s_minmax[0] = 0x7fffffff; s_minmax[1] = (int)0x80000000;
+    s_minmax[2] = 0x7fffffff; s_minmax[3] = (int)0x80000000;
+  }
+  __syncthreads();
   const TableDev tb = tables[ps.table];
   const int* goff = offsets + tb.out_off + (size_t)pa.a * tb.Ppad;
-  for (int p = pbeg + threadIdx.x; p < pend; p += blockDim.x) s_off[p - pbeg] = goff[p];
+  int mn = 0x7fffffff, mx = (int)0x80000000;
+  for (int p = pbeg + threadIdx.x; p < pend; p += blockDim.x) {
+    const int o = goff[p];
+    s_off[p - pbeg] = o;
+    mn = min(mn, o);
+    mx = max(mx, o);
+  }
   const double startX = -ps.offx, startY = -ps.offy;
+  int bmn = 0x7fffffff, bmx = (int)0x80000000;
   for (int i = threadIdx.x; i < ps.nX; i += blockDim.x) {
     const double x = startX + (double)i * ps.resx;
-    s_col[i] = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+    const int c = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+    s_col[i] = c;
   }
   for (int i = threadIdx.x; i < ps.nY; i += blockDim.x) {
     const double y = startY + (double)i * ps.resy;
-    s_row[i] = (world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border) * g.stride;
+    const int r = (world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border) * g.stride;
+    s_row[i] = r;
+    bmn = min(bmn, r);
+    bmx = max(bmx, r);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bmn = min(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
+    bmx = max(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_minmax[0], mn);
+    atomicMax(&s_minmax[1], mx);
+    if (bmn != 0x7fffffff) { atomicMin(&s_minmax[2], bmn); atomicMax(&s_minmax[3], bmx); }
   }
   __syncthreads();
+  // column extents from shared memory (nX is small); rows + columns + offsets give a conservative bound
+  int colmin = 0x7fffffff, colmax = (int)0x80000000;
+  for (int i = (int)(threadIdx.x & 31); i < ps.nX; i += 32) {
+    colmin = min(colmin, s_col[i]);
+    colmax = max(colmax, s_col[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    colmin = min(colmin, __shfl_xor_sync(0xffffffffu, colmin, o));
+    colmax = max(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
+  }
+  const int minoff = s_minmax[0];
+  for (int p = threadIdx.x; p < pend - pbeg; p += blockDim.x) s_off[p] -= minoff;  // own entries only
+  __syncthreads();
+  const long long lo = (long long)s_minmax[0] + s_minmax[2] + colmin;
+  const long long hi = (long long)s_minmax[1] + s_minmax[3] + colmax;
+  const bool safe = lo >= 0 && hi < (long long)g.data_size;  // CTA-uniform: no lookup can leave the grid
+
   const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int np = pend - pbeg;
@@ -345,23 +427,10 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
     const int iy = task / nxc, xc = task - iy * nxc;
     const int ix = (xc << 5) + lane;
     const bool active = ix < ps.nX;
-    const int base = s_row[iy] + s_col[active ? ix : 0];
-    unsigned sum = 0;
-    int p = 0;
-    for (; p + 8 <= np; p += 8) {
-      unsigned v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const unsigned idx = (unsigned)(base + s_off[p + k]);
-        v[k] = (idx < dsz) ? (unsigned)__ldg(grid + idx) : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; k++) sum += v[k];
-    }
-    for (; p < np; p++) {
-      const unsigned idx = (unsigned)(base + s_off[p]);
-      if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
-    }
+    const int base = s_row[iy] + s_col[active ? ix : 0] + minoff;
+    const uint8_t* gp = grid + base;
+    const unsigned* uoff = reinterpret_cast<const unsigned*>(s_off);
+    const unsigned sum = safe ? sweep_row<false>(gp, uoff, np, base, dsz) : sweep_row<true>(gp, uoff, np, base, dsz);
     if (active) {
       uint32_t* dst = sums + ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a;
       if (kAtomic) atomicAdd(dst, sum); else *dst = sum;
