@@ -163,6 +163,7 @@ struct ysm_handle {
   int num_sms = 148;
   // device workspaces
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
+  DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
   PinBuf h_blob, h_outs, h_angsums;
   // last-batch debug info
@@ -324,7 +325,8 @@ extern "C" void ysm_destroy(ysm_handle* h) {
   if (h->d_grids) cudaFree(h->d_grids);
   if (h->d_kernel) cudaFree(h->d_kernel);
   DevBuf* bufs[] = {&h->d_pool, &h->d_scan_start, &h->d_scan_count, &h->d_base_idx, &h->d_matches,
-                    &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_tables, &h->d_passes,
+                    &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
+                    &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
                     &h->d_angsums, &h->d_blob};
   for (DevBuf* b : bufs) b->release();
@@ -389,21 +391,12 @@ extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_an
 }
 
 // --------------------------------------------------------------------------------------------
-// CTAs per match for the stamp / clear kernels: a match's CTAs are adjacent in launch order, so
-// with >= 24 of them only a few dozen matches are in flight and their grid lines stay in L2.
-static int stamp_chunks(const ysm_handle* h, int n) {
-  return std::max(24, std::min(96, (h->num_sms * 8 + n - 1) / n));
-}
-
-// clear the footprint of a set of matches (wave) -- the grids return to all-zero
+// zero the tiles of the last built wave (its work list is still resident) -- the grids
+// return to all-zero
 static int clear_wave(ysm_handle* h, const MatchDev* d_matches, int n, cudaStream_t st) {
   if (n <= 0) return YSM_OK;
-  const GridC& g = h->g;
-  const size_t smem = (size_t)4 * g.K * g.Wk * 4;
-  const int chunks = stamp_chunks(h, n);
-  dim3 grid(chunks, n);
-  k_stamp<<<grid, 256, smem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p, (const int*)h->d_cellcount.p,
-                                    h->d_kernel, h->d_grids, 1);
+  k_tile_clear<<<h->num_sms * 8, 256, 0, st>>>(h->g, d_matches, (const int2*)h->d_work.p,
+                                               (const int*)h->d_workcount.p, h->d_grids);
   h->launches++;
   return YSM_OK;
 }
@@ -520,6 +513,10 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
 
   if (timing) CK(cudaEventRecord(h->ev[6], st));
 
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const int tiles_per_grid = tnx * tnx;
+  const int tps1 = (2 * g.half_kernel + YSM_TILE - 1) / YSM_TILE + 1;  // tiles a stamp can span per axis
+  const int tiles_per_stamp = tps1 * tps1;
   const double csx = 0.5 * (h->side - 1) * h->res_eff;
   const double crx = 2 * h->res_eff;
   const int S = h->slots;
@@ -550,7 +547,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     states.assign(nw, MatchState());
     hm.assign(nw, MatchDev());
     hbase.clear();
-    long long cells_total = 0;
+    long long cells_total = 0, gbox_total = 0, work_cap = 0;
     int nbase_max = 1;
     int n_active = 0;
     for (int i = 0; i < nw; i++) {
@@ -586,7 +583,11 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       m.base_end = (int)hbase.size();
       nbase_max = std::max(nbase_max, m.base_end - m.base_begin);
       m.cells_off = (int)cells_total;
+      m.gbox_off = (int)gbox_total;
+      m.pad0 = 0;
       cells_total += mc;
+      gbox_total += (mc + 31) / 32;
+      work_cap += std::min<long long>((long long)tiles_per_grid, mc * tiles_per_stamp);
       m.vpx = s.pose[0]; m.vpy = s.pose[1];
       m.gox = s.gox; m.goy = s.goy;
       if (s.P == 0) {
@@ -607,6 +608,10 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     CK(h->d_cells.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
     CK(h->d_ptcell.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
     CK(h->d_cellcount.ensure((size_t)nw * 4));
+    CK(h->d_gbox.ensure(std::max<size_t>(8, (size_t)gbox_total * 8)));
+    CK(h->d_work.ensure(std::max<size_t>(8, (size_t)work_cap * 8)));
+    CK(h->d_workcount.ensure(4));
+    CK(cudaMemsetAsync(h->d_workcount.p, 0, 4, st));
     CK(cudaMemcpyAsync(h->d_matches.p, hm.data(), sizeof(MatchDev) * (size_t)nw, cudaMemcpyHostToDevice, st));
     if (!hbase.empty())
       CK(cudaMemcpyAsync(h->d_base_idx.p, hbase.data(), hbase.size() * 4, cudaMemcpyHostToDevice, st));
@@ -616,22 +621,26 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     // ---- K1: grid build -----------------------------------------------------------------------
     if (timing) CK(cudaEventRecord(h->ev[0], st));
     {
+      const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
+      const size_t fixed = 4 * (size_t)nbase_max + bits_bytes;
       int nwarps = 8;
-      while (nwarps > 1 && (size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max > 200 * 1024) nwarps >>= 1;
-      const size_t smem = (size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max;
-      if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points for the filter kernel");
+      while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
+      const size_t smem = (size_t)nwarps * 4 * pmax + fixed;
+      if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points / tiles for the filter kernel");
       if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, (const MatchDev*)h->d_matches.p, (const int*)h->d_base_idx.p,
                                                    (const int*)h->d_scan_start.p, (const int*)h->d_scan_count.p,
                                                    d_pool, (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
-                                                   (int*)h->d_cellcount.p, pmax);
+                                                   (int*)h->d_cellcount.p, (uint2*)h->d_gbox.p, (int2*)h->d_work.p,
+                                                   (int*)h->d_workcount.p, pmax, nbase_max);
       h->launches++;
       const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
-      const int chunks = stamp_chunks(h, nw);
-      dim3 grid(chunks, nw);
-      k_stamp<<<grid, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
-                                        (const int*)h->d_cellcount.p, h->d_kernel, h->d_grids, 0);
+      const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
+      k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
+                                                       (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
+                                                       (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
+                                                       h->d_kernel, h->d_grids);
       h->launches++;
     }
     if (timing) CK(cudaEventRecord(h->ev[1], st));

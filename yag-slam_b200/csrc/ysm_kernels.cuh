@@ -17,6 +17,7 @@ namespace ysm {
 
 #define YSM_KT_TOLERANCE 1e-06
 #define YSM_INVALID_CELL 0xFFFFFFFFu
+#define YSM_TILE 32  // correlation-grid tile edge (cells) of the build / clear kernels
 
 // Sizes of one correlation grid (ScanMatcher::Create / CorrelationGrid).
 struct GridC {
@@ -37,6 +38,8 @@ struct MatchDev {
   int slot;
   int base_begin, base_end;  // range in the wave's base_idx array (pool scan ids)
   int cells_off;             // offset of this match's cell list / point scratch
+  int gbox_off;              // offset of this match's per-32-cell bounding boxes
+  int pad0;
   double vpx, vpy;           // FindValidPoints viewpoint = query sensor position
   double gox, goy;           // CorrelationGrid converter offset
 };
@@ -98,13 +101,21 @@ __global__ void __launch_bounds__(256)
 k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restrict__ base_idx,
              const int* __restrict__ scan_start, const int* __restrict__ scan_count,
              const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
-             uint32_t* __restrict__ cells, int* __restrict__ cell_count, int pmax) {
+             uint32_t* __restrict__ cells, int* __restrict__ cell_count, uint2* __restrict__ gbox,
+             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_tile_total, s_tile_base;
   const int nwarps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned short* s_next = reinterpret_cast<unsigned short*>(smem_raw) + (size_t)warp * 2 * pmax;
   unsigned short* s_trig = s_next + pmax;
-  int* s_scan_emit = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * 4 * pmax);  // [nbase]
+  int* s_scan_emit = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * 4 * pmax);  // [nbase_max]
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_scan_emit + nbase_max);         // touched-tile bitmap
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const int nbitw = (tnx * tnx + 31) >> 5;
+  for (int i = threadIdx.x; i < nbitw; i += blockDim.x) s_bits[i] = 0u;
+  if (threadIdx.x == 0) s_tile_total = 0;
+  __syncthreads();
 
   const MatchDev m = matches[blockIdx.x];
   const int nbase = m.base_end - m.base_begin;
@@ -158,8 +169,17 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
             if (vx > -1.0 && vy > -1.0 && vx < 1e9 && vy < 1e9) {
               const int gx = (int)kt_round(vx), gy = (int)kt_round(vy);
               if (gx >= 0 && gx < g.roi && gy >= 0 && gy < g.roi) {
-                out[j] = (uint32_t)(gx + g.border) | ((uint32_t)(gy + g.border) << 16);
+                const int ax = gx + g.border, ay = gy + g.border;
+                out[j] = (uint32_t)ax | ((uint32_t)ay << 16);
                 emitted++;
+                // every tile the K x K stamp of this cell overlaps
+                const int tx0 = (ax - g.half_kernel) / YSM_TILE, tx1 = (ax + g.half_kernel) / YSM_TILE;
+                const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
+                for (int ty = ty0; ty <= ty1; ty++)
+                  for (int tx = tx0; tx <= tx1; tx++) {
+                    const int t = ty * tnx + tx;
+                    atomicOr(&s_bits[t >> 5], 1u << (t & 31));
+                  }
               }
             }
           }
@@ -189,27 +209,74 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
       dst += __popc(bal);
     }
   }
-  if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
-    cell_count[blockIdx.x] = tot;
+  int tot = 0;
+  for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
+  if (threadIdx.x == 0) cell_count[blockIdx.x] = tot;
+  // touched tiles -> the wave's (match, tile) work list
+  int cnt = 0;
+  for (int i = threadIdx.x; i < nbitw; i += blockDim.x) cnt += __popc(s_bits[i]);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0 && cnt) atomicAdd(&s_tile_total, cnt);
+  __syncthreads();  // also orders the compacted cells before the bounding-box pass below
+  if (threadIdx.x == 0) s_tile_base = s_tile_total ? atomicAdd(work_count, s_tile_total) : 0;
+  if (threadIdx.x == 0) s_tile_total = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbitw; i += blockDim.x) {
+    unsigned b = s_bits[i];
+    if (!b) continue;
+    int pos = s_tile_base + atomicAdd(&s_tile_total, __popc(b));
+    while (b) {
+      const int bit = __ffs(b) - 1;
+      b &= b - 1;
+      work[pos++] = make_int2((int)blockIdx.x, i * 32 + bit);
+    }
+  }
+  // bounding box of every group of 32 consecutive cells (scan order keeps them spatially close)
+  __threadfence_block();
+  const uint32_t* mcells = cells + m.cells_off;
+  for (int g0 = warp * 32; g0 < tot; g0 += nwarps * 32) {
+    const int i = g0 + lane;
+    int xlo = 0xFFFF, xhi = 0, ylo = 0xFFFF, yhi = 0;
+    if (i < tot) {
+      const uint32_t c = mcells[i];
+      xlo = xhi = (int)(c & 0xFFFFu);
+      ylo = yhi = (int)(c >> 16);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+      xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+      ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+      yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+    if (lane == 0) gbox[m.gbox_off + (g0 >> 5)] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
-// yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so it is applied as
-// a parallel scatter: one lane per (cell, stamp row, 32-bit word), byte-wise max of four grid
-// cells at a time, committed with a compare-and-swap on the word in L2. The stamp row is
-// pre-shifted for the four possible byte alignments in shared memory.
-// mode 0: stamp (max); mode 1: clear the same footprint back to zero after the match.
-// grid = (chunks, matches_in_wave)
+// yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so each touched
+// 32 x 32 tile of the grid is OWNED by one CTA: it collects the match's cells whose stamp
+// reaches the tile (groups of 32 consecutive cells are pre-filtered by their bounding box),
+// every thread max-reduces the stamps over its own 4-cell word in a register (byte-wise max,
+// stamp rows pre-shifted for the four byte alignments in shared memory) and the tile is
+// written exactly once -- no atomics, no read-modify-write. Persistent grid-stride over the
+// wave's (match, tile) work list.
 // ---------------------------------------------------------------------------------------------
+#define YSM_TILE_LIST 2048    // candidate cells staged per round (64 groups x 32)
+#define YSM_TILE_CELLCAP 6144 // cells of one match staged in shared memory (else read from L2)
+#define YSM_TILE_CHUNK 16     // consecutive work items (tiles of one match) per CTA step
+
 __global__ void __launch_bounds__(256)
-k_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
-        const int* __restrict__ cell_count, const uint8_t* __restrict__ kernel,
-        uint8_t* __restrict__ grids, int mode) {
-  extern __shared__ uint32_t s_k[];  // [4][K][Wk]
+k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
+             const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
+             const int2* __restrict__ work, const int* __restrict__ work_count,
+             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids) {
+  extern __shared__ uint32_t s_k[];  // [4][K][Wk] pre-shifted stamp rows
+  __shared__ uint32_t s_list[YSM_TILE_LIST];
+  __shared__ uint32_t s_cells[YSM_TILE_CELLCAP];
+  __shared__ uint2 s_box[YSM_TILE_CELLCAP / 32];
+  __shared__ int s_groups[YSM_TILE_LIST / 32];
+  __shared__ int s_n, s_ng;
   const int K = g.K, Wk = g.Wk, h = g.half_kernel;
   const int nks = 4 * K * Wk;
   for (int t = threadIdx.x; t < nks; t += blockDim.x) {
@@ -221,37 +288,98 @@ k_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restric
     }
     s_k[t] = word;
   }
-  __syncthreads();
-  const MatchDev m = matches[blockIdx.y];
-  const int ncells = cell_count[blockIdx.y];
-  const int per = K * Wk;
-  const long long items = (long long)ncells * per;
-  uint32_t* grid32 = reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes);
-  const uint32_t* mc = cells + m.cells_off;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int pt = (int)(it / per);
-    const int rem = (int)(it - (long long)pt * per);
-    const int j = rem / Wk, w = rem - j * Wk;
-    const uint32_t c = mc[pt];
-    const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
-    const int x0 = ax - h;
-    const int s = x0 & 3;
-    const uint32_t kw = s_k[(s * K + j) * Wk + w];
-    if (kw == 0u) continue;
-    uint32_t* addr = grid32 + (size_t)(ay + j - h) * g.stride4 + (x0 >> 2) + w;
-    if (mode == 1) {
-      *addr = 0u;
-      continue;
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;  // this thread's row / word of the tile
+  const int nwork = *work_count;
+  int staged = -1;  // match whose cells are in shared memory
+  for (int w0 = blockIdx.x * YSM_TILE_CHUNK; w0 < nwork; w0 += gridDim.x * YSM_TILE_CHUNK) {
+    const int w1 = min(nwork, w0 + YSM_TILE_CHUNK);
+    for (int wi = w0; wi < w1; wi++) {
+      const int2 wk = work[wi];
+      const MatchDev m = matches[wk.x];
+      const int ncells = cell_count[wk.x];
+      const bool in_smem = ncells <= YSM_TILE_CELLCAP;
+      if (in_smem && staged != wk.x) {
+        __syncthreads();
+        const uint32_t* mcg = cells + m.cells_off;
+        const uint2* mbg = gbox + m.gbox_off;
+        for (int i = threadIdx.x; i < ncells; i += blockDim.x) s_cells[i] = mcg[i];
+        for (int i = threadIdx.x; i < ((ncells + 31) >> 5); i += blockDim.x) s_box[i] = mbg[i];
+        staged = wk.x;
+      }
+      const uint32_t* mc = in_smem ? s_cells : cells + m.cells_off;
+      const uint2* mb = in_smem ? s_box : gbox + m.gbox_off;
+      const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
+      const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
+      const int ngroups = (ncells + 31) >> 5;
+      const int row = y0t + r;          // grid row of this thread
+      const int gw = (x0t >> 2) + wd;   // grid word column of this thread
+      uint32_t v = 0;
+      for (int gb = 0; gb < ngroups; gb += YSM_TILE_LIST / 32) {
+        __syncthreads();
+        if (threadIdx.x == 0) { s_n = 0; s_ng = 0; }
+        __syncthreads();
+        // (1) groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
+        const int ge = min(ngroups, gb + YSM_TILE_LIST / 32);
+        for (int gi = gb + threadIdx.x; gi < ge; gi += blockDim.x) {
+          const uint2 bb = mb[gi];
+          const int xlo = (int)(bb.x & 0xFFFFu), xhi = (int)(bb.x >> 16);
+          const int ylo = (int)(bb.y & 0xFFFFu), yhi = (int)(bb.y >> 16);
+          if (!(xhi + h < x0t || xlo - h > x0t + YSM_TILE - 1 || yhi + h < y0t || ylo - h > y0t + YSM_TILE - 1))
+            s_groups[atomicAdd(&s_ng, 1)] = gi;
+        }
+        __syncthreads();
+        // (2) their cells that reach the tile -> candidate list
+        const int ng = s_ng;
+        for (int q = warp; q < ng; q += nwarps) {
+          const int i = s_groups[q] * 32 + lane;
+          uint32_t c = 0;
+          bool hit = false;
+          if (i < ncells) {
+            c = mc[i];
+            const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+            hit = ax + h >= x0t && ax - h <= x0t + YSM_TILE - 1 && ay + h >= y0t && ay - h <= y0t + YSM_TILE - 1;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (hit) s_list[base + __popc(bal & ((1u << lane) - 1u))] = c;
+        }
+        __syncthreads();
+        // (3) every thread max-reduces the candidates' stamps over its own word
+        const int n = s_n;
+        for (int e = 0; e < n; e++) {
+          const uint32_t c = s_list[e];
+          const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+          const int j = row - ay + h;            // stamp row
+          const int xs = ax - h;                 // first column of the stamp
+          const int rel = gw - (xs >> 2);        // word of the stamp row
+          if ((unsigned)j < (unsigned)K && (unsigned)rel < (unsigned)Wk)
+            v = vmax4_lt128(v, s_k[((xs & 3) * K + j) * Wk + rel]);
+        }
+      }
+      if (row < g.height && gw < g.stride4)
+        reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes)[(size_t)row * g.stride4 + gw] = v;
     }
-    uint32_t old = __ldcg(addr);
-    while (true) {
-      const uint32_t nw = vmax4_lt128(old, kw);
-      if (nw == old) break;
-      const uint32_t prev = atomicCAS(addr, old, nw);
-      if (prev == old) break;
-      old = prev;
-    }
+  }
+}
+
+// zero the tiles a wave touched (the slot grids are kept all-zero between matches)
+__global__ void __launch_bounds__(256)
+k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
+             const int* __restrict__ work_count, uint8_t* __restrict__ grids) {
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;
+  const int nwork = *work_count;
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int2 wk = work[wi];
+    const int slot = matches[wk.x].slot;
+    const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
+    const int row = ty * YSM_TILE + r, gw = ((tx * YSM_TILE) >> 2) + wd;
+    if (row < g.height && gw < g.stride4)
+      reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes)[(size_t)row * g.stride4 + gw] = 0u;
   }
 }
 
