@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,6 +29,21 @@ static_assert(sizeof(ysm_result) == 128, "ysm_result must be a 128-byte record")
 #define MAX_VARIANCE 500.0
 
 static std::string g_create_error;
+
+#include <chrono>
+struct PhaseTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  PhaseTrace() : on(getenv("YSM_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+  void mark(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ysm] %-28s +%8.1f us (t=%8.1f)\n", what,
+            std::chrono::duration<double, std::micro>(now - last).count(),
+            std::chrono::duration<double, std::micro>(now - t0).count());
+    last = now;
+  }
+};
 
 namespace {
 
@@ -177,6 +193,7 @@ struct ysm_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
+  size_t sweep_smem_attr = 0, find_smem_attr = 0;
   int64_t work[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -462,6 +479,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   if (!h || !b || !out) return YSM_EINVAL;
   if (b->n_matches < 0 || b->n_scans < 0) return fail(h, YSM_EINVAL, "negative sizes");
   cudaStream_t st = (cudaStream_t)stream;
+  PhaseTrace tr;
   CK(cudaSetDevice(h->device));
   const GridC& g = h->g;
   const bool timing = (h->debug & YSM_DEBUG_TIME_KERNELS) && h->ev_ok;
@@ -512,6 +530,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   }
 
   if (timing) CK(cudaEventRecord(h->ev[6], st));
+  tr.mark("validate + pool H2D");
 
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int tiles_per_grid = tnx * tnx;
@@ -618,17 +637,21 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     h->work[6] += (int64_t)(sizeof(MatchDev) * (size_t)nw + hbase.size() * 4);
     h->work[5] += cells_total;
 
+    tr.mark("wave setup + H2D");
     // ---- K1: grid build -----------------------------------------------------------------------
     if (timing) CK(cudaEventRecord(h->ev[0], st));
     {
       const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
       const size_t fixed = 4 * (size_t)nbase_max + bits_bytes;
-      int nwarps = 8;
+      // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
+      int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
       while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
       const size_t smem = (size_t)nwarps * 4 * pmax + fixed;
       if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points / tiles for the filter kernel");
-      if (smem > 48 * 1024)
+      if (smem > 48 * 1024 && smem > h->find_smem_attr) {
         CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->find_smem_attr = smem;
+      }
       k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, (const MatchDev*)h->d_matches.p, (const int*)h->d_base_idx.p,
                                                    (const int*)h->d_scan_start.p, (const int*)h->d_scan_count.p,
                                                    d_pool, (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
@@ -640,12 +663,13 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
                                                        (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
-                                                       h->d_kernel, h->d_grids);
+                                                       h->d_kernel, h->d_grids, std::max(1, std::min(16, nw / 8)));
       h->launches++;
     }
     if (timing) CK(cudaEventRecord(h->ev[1], st));
     CK(cudaGetLastError());
 
+    tr.mark("build launches");
     // ---- pass iterations ------------------------------------------------------------------------
     int iter = 0;
     while (true) {
@@ -774,7 +798,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       size_t o_pa = o_pass + sizeof(PassDev) * hpass.size();
       size_t o_fine = o_pa + sizeof(PassAngle) * hpa.size();
       size_t o_trig = (o_fine + sizeof(int) * hfine.size() + 15) / 16 * 16;
-      size_t blob = o_trig + sizeof(double) * htrig.size();
+      size_t o_pmax = o_trig + sizeof(double) * htrig.size();
+      size_t blob = o_pmax + sizeof(double) * hpass.size();
       CK(h->h_blob.ensure(blob));
       CK(h->d_blob.ensure(blob));
       char* hb = (char*)h->h_blob.p;
@@ -783,6 +808,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       if (!hpa.empty()) memcpy(hb + o_pa, hpa.data(), sizeof(PassAngle) * hpa.size());
       if (!hfine.empty()) memcpy(hb + o_fine, hfine.data(), sizeof(int) * hfine.size());
       memcpy(hb + o_trig, htrig.data(), sizeof(double) * htrig.size());
+      memset(hb + o_pmax, 0, sizeof(double) * hpass.size());  // per-pass best response, max-accumulated on the GPU
       CK(cudaMemcpyAsync(h->d_blob.p, hb, blob, cudaMemcpyHostToDevice, st));
       h->work[6] += (int64_t)blob;
       h->work[7] += (int64_t)(sizeof(PassOut) * (size_t)npass + (size_t)ang_elems * 4);
@@ -794,14 +820,16 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       const PassAngle* d_pa = (const PassAngle*)(db + o_pa);
       const int* d_fine = (const int*)(db + o_fine);
       const double* d_trig = (const double*)(db + o_trig);
+      double* d_pmax = (double*)((char*)h->d_blob.p + o_pmax);
 
       CK(h->d_offsets.ensure(std::max<size_t>(16, off_elems * 4)));
-      CK(h->d_sums.ensure(std::max<size_t>(16, sums_elems * 4)));
+      CK(h->d_sums.ensure(std::max<size_t>(16, sums_elems * 8)));  // penalised responses, f64 [iy][ix][a]
       CK(h->d_outs.ensure(sizeof(PassOut) * (size_t)npass));
       CK(h->d_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
       CK(h->h_outs.ensure(sizeof(PassOut) * (size_t)npass));
       CK(h->h_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
 
+      tr.mark("pass prep (host libm) + blob");
       // ---- K2 offsets ---------------------------------------------------------------------------
       {
         int maxwork = 1;
@@ -814,59 +842,48 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       if (timing) CK(cudaEventRecord(h->ev[2], st));
       if (!hpa.empty()) {
         // one warp per lattice row-task; CTAs of up to 32 warps. Small batches: split the rows
-        // over more CTAs, then the points (atomic partial sums), until the machine is full.
+        // over more CTAs until the machine is full.
         const int npa = (int)hpa.size();
         const int target = h->num_sms * 2;
         int tpc = std::min(max_lat_tasks, 32);
         int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-        int p_chunks = 1;
         if (npa * task_chunks < target) {
           const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
-          tpc = std::max(4, std::min(tpc, (max_lat_tasks + want - 1) / want));
+          tpc = std::max(2, std::min(tpc, (max_lat_tasks + want - 1) / want));
           task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-          if (npa * task_chunks < target)
-            p_chunks = std::min(std::max(1, max_lat_P / 64), (target + npa * task_chunks - 1) / (npa * task_chunks));
         }
-        int p_chunk = (max_lat_P + p_chunks - 1) / p_chunks;
-        p_chunk = (p_chunk + 7) & ~7;
-        p_chunks = (max_lat_P + p_chunk - 1) / p_chunk;
         const int threads = 32 * std::min(tpc, 32);
-        const size_t smem = (size_t)(((p_chunk + 3) & ~3) + max_lat_nx + max_lat_ny) * 4;
+        const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny) * 4;
         if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
-        dim3 grid(npa, task_chunks, p_chunks);
-        if (p_chunks > 1) {
-          CK(cudaMemsetAsync(h->d_sums.p, 0, sums_elems * 4, st));
-          if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_sweep_lattice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_sweep_lattice<true><<<grid, threads, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                             h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
-        } else {
-          if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_sweep_lattice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_sweep_lattice<false><<<grid, threads, smem, st>>>(g, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                              h->d_grids, (uint32_t*)h->d_sums.p, tpc, p_chunk);
+        if (smem > 48 * 1024 && smem > h->sweep_smem_attr) {
+          CK(cudaFuncSetAttribute(k_sweep_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          h->sweep_smem_attr = smem;
         }
+        dim3 grid(npa, task_chunks, 1);
+        k_sweep_lattice<<<grid, threads, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                     h->d_grids, (double*)h->d_sums.p, d_pmax, tpc);
         h->launches++;
         h->work[1]++;
       }
       if (timing) CK(cudaEventRecord(h->ev[3], st));
       if (!hfine.empty()) {
         dim3 grid((max_fine_poses + 7) / 8, (unsigned)hfine.size());
-        k_sweep_points<<<grid, 256, 0, st>>>(g, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
-                                             (uint32_t*)h->d_sums.p);
+        k_sweep_points<<<grid, 256, 0, st>>>(g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
+                                             (double*)h->d_sums.p, d_pmax);
         h->launches++;
       }
       // ---- K3b/K4 reduce ------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[4], st));
-      k_reduce<<<npass, 256, 0, st>>>(g, h->pen, d_pass, d_tab, (const int*)h->d_offsets.p,
-                                      (const uint32_t*)h->d_sums.p, d_trig, h->d_grids, (PassOut*)h->d_outs.p,
-                                      (int*)h->d_angsums.p);
+      k_reduce<<<npass, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
+                                      d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p);
       h->launches++;
       if (timing) CK(cudaEventRecord(h->ev[5], st));
       CK(cudaMemcpyAsync(h->h_outs.p, h->d_outs.p, sizeof(PassOut) * (size_t)npass, cudaMemcpyDeviceToHost, st));
       if (ang_elems > 0)
         CK(cudaMemcpyAsync(h->h_angsums.p, h->d_angsums.p, (size_t)ang_elems * 4, cudaMemcpyDeviceToHost, st));
+      tr.mark("pass launches");
       CK(cudaStreamSynchronize(st));
+      tr.mark("sync");
       CK(cudaGetLastError());
       if (timing) {
         float ms = 0;
@@ -926,6 +943,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       iter++;
     }
 
+    tr.mark("host finalize");
     // ---- results + clear ------------------------------------------------------------------------
     for (int i = 0; i < nw; i++) {
       const MatchState& s = states[i];

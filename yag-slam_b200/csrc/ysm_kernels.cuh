@@ -97,7 +97,7 @@ __device__ __forceinline__ uint32_t vmax4_lt128(uint32_t a, uint32_t b) {
 // memory pointer chase), then every segment [t_k, t_k+1) is kept iff the side test ss >= 0
 // (parallel). Output: the match's occupied cells in Karto's processing order.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restrict__ base_idx,
              const int* __restrict__ scan_start, const int* __restrict__ scan_count,
              const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
@@ -264,13 +264,12 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
 // ---------------------------------------------------------------------------------------------
 #define YSM_TILE_LIST 2048    // candidate cells staged per round (64 groups x 32)
 #define YSM_TILE_CELLCAP 6144 // cells of one match staged in shared memory (else read from L2)
-#define YSM_TILE_CHUNK 16     // consecutive work items (tiles of one match) per CTA step
 
 __global__ void __launch_bounds__(256)
 k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
              const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
              const int2* __restrict__ work, const int* __restrict__ work_count,
-             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids) {
+             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, int chunk) {
   extern __shared__ uint32_t s_k[];  // [4][K][Wk] pre-shifted stamp rows
   __shared__ uint32_t s_list[YSM_TILE_LIST];
   __shared__ uint32_t s_cells[YSM_TILE_CELLCAP];
@@ -293,8 +292,8 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
   const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;  // this thread's row / word of the tile
   const int nwork = *work_count;
   int staged = -1;  // match whose cells are in shared memory
-  for (int w0 = blockIdx.x * YSM_TILE_CHUNK; w0 < nwork; w0 += gridDim.x * YSM_TILE_CHUNK) {
-    const int w1 = min(nwork, w0 + YSM_TILE_CHUNK);
+  for (int w0 = blockIdx.x * chunk; w0 < nwork; w0 += gridDim.x * chunk) {  // `chunk` consecutive tiles (one match, mostly)
+    const int w1 = min(nwork, w0 + chunk);
     for (int wi = w0; wi < w1; wi++) {
       const int2 wk = work[wi];
       const MatchDev m = matches[wk.x];
@@ -434,6 +433,33 @@ struct PassAngle {
   int pass, a;
 };
 
+// GetResponse normalisation + the odometry penalty of CorrelateScan for the
+// pose (ix, iy, a) whose integer lookup sum is `sum`.
+__device__ __forceinline__ double response_of(const PassDev& ps, const PenaltyC& pen, unsigned sum, int ix,
+                                              int iy, int a) {
+  double r = (double)sum / (double)((unsigned)ps.P * 100u);
+  if (ps.penalize && !kt_double_equal(r, 0.0)) {
+    const double x = -ps.offx + (double)ix * ps.resx;
+    const double y = -ps.offy + (double)iy * ps.resy;
+    const double sqd = x * x + y * y;
+    double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
+    dp = dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
+    const double angle = (ps.ch - ps.angle_offset) + (double)a * ps.angle_res;
+    const double da = angle - ps.ch;
+    const double sqa = da * da;
+    double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
+    ap = ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
+    r *= (dp * ap);
+  }
+  return r;
+}
+
+// responses are >= 0, so their IEEE bit patterns order like unsigned integers
+__device__ __forceinline__ void pass_max_update(double* passmax, int pass, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(passmax + pass), (unsigned long long)__double_as_longlong(v));
+}
+
+
 // s_off holds offsets biased by the CTA-wide minimum (so they are non-negative and extend to
 // 64 bits for free); gp / base already include that minimum.
 template <bool kChecked>
@@ -468,14 +494,15 @@ __device__ __forceinline__ unsigned sweep_row(const uint8_t* __restrict__ gp, co
   return sum0 + sum1;
 }
 
-template <bool kAtomic>
-__global__ void __launch_bounds__(1024)
-k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __restrict__ pa_list,
-                const TableDev* __restrict__ tables, const int* __restrict__ offsets,
-                const uint8_t* __restrict__ grids, uint32_t* __restrict__ sums, int tasks_per_cta,
-                int p_chunk) {
+__global__ void __launch_bounds__(1024, 2)
+k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
+                const PassAngle* __restrict__ pa_list, const TableDev* __restrict__ tables,
+                const int* __restrict__ offsets, const uint8_t* __restrict__ grids,
+                double* __restrict__ resp, double* __restrict__ passmax, int tasks_per_cta) {
   extern __shared__ __align__(16) int s_i[];
   __shared__ int s_minmax[4];  // min off, max off, min base, max base
+  __shared__ double s_wmax[32];
+  const int p_chunk = (passes[pa_list[blockIdx.x].pass].P + 7) & ~7;
   const PassAngle pa = pa_list[blockIdx.x];
   const PassDev ps = passes[pa.pass];
   const int nxc = (ps.nX + 31) >> 5;
@@ -483,9 +510,8 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
   const int task0 = blockIdx.y * tasks_per_cta;
   if (task0 >= ntasks) return;
   const int task1 = min(ntasks, task0 + tasks_per_cta);
-  const int pbeg = blockIdx.z * p_chunk;
-  const int pend = min(ps.P, pbeg + p_chunk);
-  if (pbeg >= pend) return;
+  const int pbeg = 0;
+  const int pend = ps.P;
   const int pc4 = (p_chunk + 3) & ~3;
   int* s_off = s_i;             // [pc4]
   int* s_col = s_i + pc4;       // [nX]
@@ -551,6 +577,7 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int np = pend - pbeg;
   const unsigned dsz = (unsigned)g.data_size;
+  double wmax = 0.0;
   for (int task = task0 + warp; task < task1; task += nwarps) {
     const int iy = task / nxc, xc = task - iy * nxc;
     const int ix = (xc << 5) + lane;
@@ -560,9 +587,22 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
     const unsigned* uoff = reinterpret_cast<const unsigned*>(s_off);
     const unsigned sum = safe ? sweep_row<false>(gp, uoff, np, base, dsz) : sweep_row<true>(gp, uoff, np, base, dsz);
     if (active) {
-      uint32_t* dst = sums + ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a;
-      if (kAtomic) atomicAdd(dst, sum); else *dst = sum;
+      const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
+      resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
+      wmax = rr > wmax ? rr : wmax;
     }
+  }
+  // best response of this CTA -> the pass maximum (CorrelateScan's bestResponse)
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, wmax, o);
+    wmax = t > wmax ? t : wmax;
+  }
+  if (lane == 0) s_wmax[warp] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = s_wmax[0];
+    for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
+    pass_max_update(passmax, pa.pass, m);
   }
 }
 
@@ -572,10 +612,11 @@ k_sweep_lattice(GridC g, const PassDev* __restrict__ passes, const PassAngle* __
 // combined with warp shuffles. grid = (ceil(nposes / warps_per_cta), n_fine_passes)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_sweep_points(GridC g, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
+k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
                const TableDev* __restrict__ tables, const int* __restrict__ offsets,
-               const uint8_t* __restrict__ grids, uint32_t* __restrict__ sums) {
-  const PassDev ps = passes[pass_ids[blockIdx.y]];
+               const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax) {
+  const int pid = pass_ids[blockIdx.y];
+  const PassDev ps = passes[pid];
   const int nposes = ps.nX * ps.nY * ps.nA;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int pose = blockIdx.x * nwarps + warp;
@@ -598,7 +639,11 @@ k_sweep_points(GridC g, const PassDev* __restrict__ passes, const int* __restric
     if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) sums[ps.sums_off + pose] = sum;
+  if (lane == 0) {
+    const double rr = response_of(ps, pen, sum, ix, iy, a);
+    resp[ps.sums_off + pose] = rr;
+    pass_max_update(passmax, pid, rr);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -609,29 +654,6 @@ k_sweep_points(GridC g, const PassDev* __restrict__ passes, const int* __restric
 // One CTA per pass.
 // ---------------------------------------------------------------------------------------------
 #define YSM_TIE_CAP 1024
-
-__device__ __forceinline__ double pose_response(const PassDev& ps, const PenaltyC& pen,
-                                                const uint32_t* __restrict__ sums, int idx,
-                                                double denom) {
-  double r = (double)sums[idx] / denom;
-  if (ps.penalize && !kt_double_equal(r, 0.0)) {
-    const int iy = idx / (ps.nX * ps.nA);
-    const int rem = idx - iy * ps.nX * ps.nA;
-    const int ix = rem / ps.nA, a = rem - ix * ps.nA;
-    const double x = -ps.offx + (double)ix * ps.resx;
-    const double y = -ps.offy + (double)iy * ps.resy;
-    const double sqd = x * x + y * y;
-    double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
-    dp = dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
-    const double angle = (ps.ch - ps.angle_offset) + (double)a * ps.angle_res;
-    const double da = angle - ps.ch;
-    const double sqa = da * da;
-    double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
-    ap = ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
-    r *= (dp * ap);
-  }
-  return r;
-}
 
 __device__ __forceinline__ double block_reduce_max(double v, double* s_tmp) {
   for (int o = 16; o > 0; o >>= 1) {
@@ -656,37 +678,32 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-k_reduce(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
-         const TableDev* __restrict__ tables, const int* __restrict__ offsets,
-         const uint32_t* __restrict__ sums, const double* __restrict__ trig,
+__global__ void __launch_bounds__(512)
+k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict__ tables,
+         const int* __restrict__ offsets, const double* __restrict__ resp,
+         const double* __restrict__ passmax, const double* __restrict__ trig,
          const uint8_t* __restrict__ grids, PassOut* __restrict__ outs, int* __restrict__ angsums) {
-  __shared__ double s_tmp[8];
+  __shared__ double s_tmp[16];
   __shared__ int s_list[YSM_TIE_CAP];
   __shared__ int s_sorted[YSM_TIE_CAP];
   __shared__ int s_count;
-  __shared__ unsigned s_bits[8];
+  __shared__ unsigned s_bits[16];
   __shared__ double s_acc[4];
   __shared__ int s_n;
 
   const PassDev ps = passes[blockIdx.x];
-  const uint32_t* psums = sums + ps.sums_off;
+  const double* pr = resp + ps.sums_off;
   const int nposes = ps.nX * ps.nY * ps.nA;
-  const double denom = (double)((unsigned)ps.P * 100u);
   const int tid = threadIdx.x;
   if (tid == 0) s_count = 0;
-
-  // best response (init -1)
-  double best = -1.0;
-  for (int i = tid; i < nposes; i += blockDim.x) {
-    const double r = pose_response(ps, pen, psums, i, denom);
-    best = r > best ? r : best;
-  }
-  best = block_reduce_max(best, s_tmp);
+  // best response: accumulated by the sweep kernels (max over all poses; Karto's init of -1
+  // never survives because every pass has at least one pose and responses are >= 0)
+  const double best = passmax[blockIdx.x];
+  __syncthreads();
 
   // poses tied with the best, in storage order
   for (int i = tid; i < nposes; i += blockDim.x) {
-    const double r = pose_response(ps, pen, psums, i, denom);
+    const double r = pr[i];
     if (kt_double_equal(r, best)) {
       const int pos = atomicAdd(&s_count, 1);
       if (pos < YSM_TIE_CAP) s_list[pos] = i;
@@ -727,7 +744,7 @@ k_reduce(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
     for (int c0 = 0; c0 < nposes; c0 += blockDim.x) {
       const int i = c0 + tid;
       bool tie = false;
-      if (i < nposes) tie = kt_double_equal(pose_response(ps, pen, psums, i, denom), best);
+      if (i < nposes) tie = kt_double_equal(pr[i], best);
       const unsigned bal = __ballot_sync(0xffffffffu, tie);
       if ((tid & 31) == 0) s_bits[tid >> 5] = bal;
       __syncthreads();
@@ -782,7 +799,7 @@ k_reduce(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
         const int iy = c / ps.nX, ix = c - iy * ps.nX;
         double pm = 0.0;  // probs grid is cleared to 0 and max'ed with every response
         for (int a = 0; a < ps.nA; a++) {
-          const double r = pose_response(ps, pen, psums, c * ps.nA + a, denom);
+          const double r = pr[(size_t)c * ps.nA + a];
           pm = r > pm ? r : pm;
         }
         if (pm >= (best - 0.1)) {
