@@ -663,7 +663,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
                                                        (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
-                                                       h->d_kernel, h->d_grids, std::max(1, std::min(16, nw / 8)));
+                                                       h->d_kernel, h->d_grids);
       h->launches++;
     }
     if (timing) CK(cudaEventRecord(h->ev[1], st));

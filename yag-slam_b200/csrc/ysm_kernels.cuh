@@ -255,27 +255,65 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
 // ---------------------------------------------------------------------------------------------
 // K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
 // yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so each touched
-// 32 x 32 tile of the grid is OWNED by one CTA: it collects the match's cells whose stamp
-// reaches the tile (groups of 32 consecutive cells are pre-filtered by their bounding box),
-// every thread max-reduces the stamps over its own 4-cell word in a register (byte-wise max,
-// stamp rows pre-shifted for the four byte alignments in shared memory) and the tile is
-// written exactly once -- no atomics, no read-modify-write. Persistent grid-stride over the
-// wave's (match, tile) work list.
+// 32 x 32 tile of the grid is OWNED by one warp: it keeps the tile in a private 1 KB block of
+// shared memory, collects the match's cells whose stamp reaches the tile (groups of 32
+// consecutive cells are pre-filtered by their bounding box), scatters every candidate's
+// clipped stamp into the tile -- lanes = 4 tile rows x 8 words, byte-wise max of four cells
+// per lane, stamp rows pre-shifted for the four byte alignments -- and writes the tile to the
+// grid exactly once: no atomics, no global read-modify-write. Warps stride the wave's
+// (match, tile) work list.
 // ---------------------------------------------------------------------------------------------
-#define YSM_TILE_LIST 2048    // candidate cells staged per round (64 groups x 32)
-#define YSM_TILE_CELLCAP 6144 // cells of one match staged in shared memory (else read from L2)
+#define YSM_TILE_LIST 224   // candidate cells staged per warp between flushes
+
+__device__ __forceinline__ void tile_scatter(uint32_t* __restrict__ tile, const uint32_t* __restrict__ list,
+                                             int n, const uint32_t* __restrict__ s_k, int K, int Wk, int h,
+                                             int x0t, int y0t, int lane) {
+  const int wt0 = x0t >> 2;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    // lane-parallel set-up of up to 32 candidates: the stamp clipped to the tile
+    // (rows [r0, r1], words [w0, w1]) packed into two words that are broadcast below
+    uint32_t p0 = 0, p1 = 0;
+    if (e0 + lane < n) {
+      const uint32_t c = list[e0 + lane];
+      const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+      const int xs = ax - h, ys = ay - h;  // top-left cell of the stamp
+      const int wrel = (xs >> 2) - wt0;    // tile word of the stamp's first word
+      const int r0 = max(0, ys - y0t), r1 = min(YSM_TILE - 1, ys + K - 1 - y0t);
+      const int w0 = max(0, wrel), w1 = min(7, wrel + Wk - 1);
+      const int nwd = w1 - w0 + 1;
+      const int items = (r1 - r0 + 1) * nwd;                                   // <= 256
+      const unsigned rcp = (65536u + (unsigned)nwd - 1u) / (unsigned)nwd;      // it / nwd for it < 256
+      const int koff = ((xs & 3) * K + (y0t + r0 - ys)) * Wk + (w0 - wrel);    // < 4*K*Wk <= 2048
+      p0 = (uint32_t)(r0 * 8 + w0) | ((uint32_t)nwd << 8) | ((uint32_t)items << 12);
+      p1 = (uint32_t)koff | (rcp << 11);
+    }
+    const int cnt = min(32, n - e0);
+    for (int k = 0; k < cnt; k++) {
+      const uint32_t q0 = __shfl_sync(0xffffffffu, p0, k), q1 = __shfl_sync(0xffffffffu, p1, k);
+      const int nwd = (int)((q0 >> 8) & 15u), items = (int)(q0 >> 12);
+      const unsigned rcp = q1 >> 11;
+      const uint32_t* ks = s_k + (q1 & 2047u);
+      uint32_t* t0 = tile + (q0 & 255u);
+      for (int it = lane; it < items; it += 32) {
+        const int jr = (int)(((unsigned)it * rcp) >> 16);
+        const int ww = it - jr * nwd;
+        const uint32_t kw = ks[jr * Wk + ww];
+        uint32_t* tp = t0 + jr * 8 + ww;
+        *tp = vmax4_lt128(*tp, kw);
+      }
+      __syncwarp();
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256)
 k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
              const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
              const int2* __restrict__ work, const int* __restrict__ work_count,
-             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, int chunk) {
+             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids) {
   extern __shared__ uint32_t s_k[];  // [4][K][Wk] pre-shifted stamp rows
-  __shared__ uint32_t s_list[YSM_TILE_LIST];
-  __shared__ uint32_t s_cells[YSM_TILE_CELLCAP];
-  __shared__ uint2 s_box[YSM_TILE_CELLCAP / 32];
-  __shared__ int s_groups[YSM_TILE_LIST / 32];
-  __shared__ int s_n, s_ng;
+  __shared__ uint32_t s_tile[8][YSM_TILE * YSM_TILE / 4];
+  __shared__ uint32_t s_list[8][YSM_TILE_LIST + 32];
   const int K = g.K, Wk = g.Wk, h = g.half_kernel;
   const int nks = 4 * K * Wk;
   for (int t = threadIdx.x; t < nks; t += blockDim.x) {
@@ -287,81 +325,69 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
     }
     s_k[t] = word;
   }
+  __syncthreads();
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;  // this thread's row / word of the tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* tile = s_tile[warp];
+  uint32_t* list = s_list[warp];
   const int nwork = *work_count;
-  int staged = -1;  // match whose cells are in shared memory
-  for (int w0 = blockIdx.x * chunk; w0 < nwork; w0 += gridDim.x * chunk) {  // `chunk` consecutive tiles (one match, mostly)
-    const int w1 = min(nwork, w0 + chunk);
-    for (int wi = w0; wi < w1; wi++) {
-      const int2 wk = work[wi];
-      const MatchDev m = matches[wk.x];
-      const int ncells = cell_count[wk.x];
-      const bool in_smem = ncells <= YSM_TILE_CELLCAP;
-      if (in_smem && staged != wk.x) {
-        __syncthreads();
-        const uint32_t* mcg = cells + m.cells_off;
-        const uint2* mbg = gbox + m.gbox_off;
-        for (int i = threadIdx.x; i < ncells; i += blockDim.x) s_cells[i] = mcg[i];
-        for (int i = threadIdx.x; i < ((ncells + 31) >> 5); i += blockDim.x) s_box[i] = mbg[i];
-        staged = wk.x;
+  const int nwarps_total = gridDim.x * 8;
+  for (int wi = blockIdx.x * 8 + warp; wi < nwork; wi += nwarps_total) {
+    const int2 wk = work[wi];
+    const MatchDev m = matches[wk.x];
+    const int ncells = cell_count[wk.x];
+    const uint32_t* mc = cells + m.cells_off;
+    const uint2* mb = gbox + m.gbox_off;
+    const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
+    const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
+    const int ngroups = (ncells + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tile[k * 32 + lane] = 0u;
+    __syncwarp();
+    int n = 0;
+    for (int g0 = 0; g0 < ngroups; g0 += 32) {
+      // groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
+      bool ghit = false;
+      if (g0 + lane < ngroups) {
+        const uint2 bb = mb[g0 + lane];
+        const int xlo = (int)(bb.x & 0xFFFFu), xhi = (int)(bb.x >> 16);
+        const int ylo = (int)(bb.y & 0xFFFFu), yhi = (int)(bb.y >> 16);
+        ghit = !(xhi + h < x0t || xlo - h > x0t + YSM_TILE - 1 || yhi + h < y0t || ylo - h > y0t + YSM_TILE - 1);
       }
-      const uint32_t* mc = in_smem ? s_cells : cells + m.cells_off;
-      const uint2* mb = in_smem ? s_box : gbox + m.gbox_off;
-      const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
-      const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
-      const int ngroups = (ncells + 31) >> 5;
-      const int row = y0t + r;          // grid row of this thread
-      const int gw = (x0t >> 2) + wd;   // grid word column of this thread
-      uint32_t v = 0;
-      for (int gb = 0; gb < ngroups; gb += YSM_TILE_LIST / 32) {
-        __syncthreads();
-        if (threadIdx.x == 0) { s_n = 0; s_ng = 0; }
-        __syncthreads();
-        // (1) groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
-        const int ge = min(ngroups, gb + YSM_TILE_LIST / 32);
-        for (int gi = gb + threadIdx.x; gi < ge; gi += blockDim.x) {
-          const uint2 bb = mb[gi];
-          const int xlo = (int)(bb.x & 0xFFFFu), xhi = (int)(bb.x >> 16);
-          const int ylo = (int)(bb.y & 0xFFFFu), yhi = (int)(bb.y >> 16);
-          if (!(xhi + h < x0t || xlo - h > x0t + YSM_TILE - 1 || yhi + h < y0t || ylo - h > y0t + YSM_TILE - 1))
-            s_groups[atomicAdd(&s_ng, 1)] = gi;
-        }
-        __syncthreads();
-        // (2) their cells that reach the tile -> candidate list
-        const int ng = s_ng;
-        for (int q = warp; q < ng; q += nwarps) {
-          const int i = s_groups[q] * 32 + lane;
-          uint32_t c = 0;
-          bool hit = false;
-          if (i < ncells) {
-            c = mc[i];
-            const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
-            hit = ax + h >= x0t && ax - h <= x0t + YSM_TILE - 1 && ay + h >= y0t && ay - h <= y0t + YSM_TILE - 1;
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          int base = 0;
-          if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (hit) s_list[base + __popc(bal & ((1u << lane) - 1u))] = c;
-        }
-        __syncthreads();
-        // (3) every thread max-reduces the candidates' stamps over its own word
-        const int n = s_n;
-        for (int e = 0; e < n; e++) {
-          const uint32_t c = s_list[e];
+      unsigned gm = __ballot_sync(0xffffffffu, ghit);
+      while (gm) {
+        const int gi = g0 + __ffs(gm) - 1;
+        gm &= gm - 1;
+        const int i = gi * 32 + lane;
+        uint32_t c = 0;
+        bool hit = false;
+        if (i < ncells) {
+          c = mc[i];
           const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
-          const int j = row - ay + h;            // stamp row
-          const int xs = ax - h;                 // first column of the stamp
-          const int rel = gw - (xs >> 2);        // word of the stamp row
-          if ((unsigned)j < (unsigned)K && (unsigned)rel < (unsigned)Wk)
-            v = vmax4_lt128(v, s_k[((xs & 3) * K + j) * Wk + rel]);
+          hit = ax + h >= x0t && ax - h <= x0t + YSM_TILE - 1 && ay + h >= y0t && ay - h <= y0t + YSM_TILE - 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[n + __popc(bal & ((1u << lane) - 1u))] = c;
+        n += __popc(bal);
+        if (n > YSM_TILE_LIST) {  // warp-uniform
+          __syncwarp();
+          tile_scatter(tile, list, n, s_k, K, Wk, h, x0t, y0t, lane);
+          n = 0;
         }
       }
-      if (row < g.height && gw < g.stride4)
-        reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes)[(size_t)row * g.stride4 + gw] = v;
     }
+    __syncwarp();
+    tile_scatter(tile, list, n, s_k, K, Wk, h, x0t, y0t, lane);
+    // the tile is written exactly once
+    uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes);
+    const int dr = lane >> 3, wd = lane & 7;
+    const int gw = (x0t >> 2) + wd;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int row = y0t + k * 4 + dr;
+      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = tile[(k * 4 + dr) * 8 + wd];
+    }
+    __syncwarp();
   }
 }
 
