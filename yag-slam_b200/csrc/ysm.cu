@@ -31,6 +31,33 @@ static_assert(sizeof(ysm_result) == 128, "ysm_result must be a 128-byte record")
 static std::string g_create_error;
 
 #include <chrono>
+struct KernelTrace {
+  bool on = false;
+  cudaEvent_t ev[32];
+  const char* name[32];
+  int n = 0;
+  cudaStream_t st = nullptr;
+  void init(bool enable, cudaStream_t s) {
+    on = enable; st = s; n = 0;
+    if (on) for (int i = 0; i < 32; i++) cudaEventCreate(&ev[i]);
+  }
+  void mark(const char* what) {
+    if (!on || n >= 32) return;
+    name[n] = what;
+    cudaEventRecord(ev[n++], st);
+  }
+  void dump() {
+    if (!on) return;
+    cudaEventSynchronize(ev[n - 1]);
+    for (int i = 1; i < n; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "[ysm-gpu] %-22s %8.1f us\n", name[i], ms * 1e3);
+    }
+    for (int i = 0; i < 32; i++) cudaEventDestroy(ev[i]);
+    n = 0; on = false;
+  }
+};
 struct PhaseTrace {
   bool on;
   std::chrono::steady_clock::time_point t0, last;
@@ -480,6 +507,9 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   if (b->n_matches < 0 || b->n_scans < 0) return fail(h, YSM_EINVAL, "negative sizes");
   cudaStream_t st = (cudaStream_t)stream;
   PhaseTrace tr;
+  KernelTrace kt;
+  kt.init(getenv("YSM_TRACE_GPU") != nullptr, st);
+  kt.mark("start");
   CK(cudaSetDevice(h->device));
   const GridC& g = h->g;
   const bool timing = (h->debug & YSM_DEBUG_TIME_KERNELS) && h->ev_ok;
@@ -646,7 +676,15 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
       int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
       while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
-      const size_t smem = (size_t)nwarps * 4 * pmax + fixed;
+      size_t smem = (size_t)nwarps * 4 * pmax + fixed;
+      int stage = 0;
+      if (nw < 2 * h->num_sms) {  // latency mode: stage scan points in shared memory if they fit
+        const size_t with_pts = ((smem + 15) & ~(size_t)15) + (size_t)nwarps * 16 * pmax;
+        if (with_pts <= 200 * 1024) {
+          smem = with_pts;
+          stage = 1;
+        }
+      }
       if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points / tiles for the filter kernel");
       if (smem > 48 * 1024 && smem > h->find_smem_attr) {
         CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -656,8 +694,9 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
                                                    (const int*)h->d_scan_start.p, (const int*)h->d_scan_count.p,
                                                    d_pool, (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
                                                    (int*)h->d_cellcount.p, (uint2*)h->d_gbox.p, (int2*)h->d_work.p,
-                                                   (int*)h->d_workcount.p, pmax, nbase_max);
+                                                   (int*)h->d_workcount.p, pmax, nbase_max, stage);
       h->launches++;
+      kt.mark("k_find_valid");
       const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
       const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
@@ -665,6 +704,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
                                                        (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
                                                        h->d_kernel, h->d_grids);
       h->launches++;
+      kt.mark("k_tile_stamp");
     }
     if (timing) CK(cudaEventRecord(h->ev[1], st));
     CK(cudaGetLastError());
@@ -837,6 +877,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         dim3 grid((maxwork + 255) / 256, (unsigned)htab.size());
         k_offsets<<<grid, 256, 0, st>>>(g, d_tab, d_trig, d_pool, (int*)h->d_offsets.p);
         h->launches++;
+        kt.mark("k_offsets");
       }
       // ---- K3 sweeps ----------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[2], st));
@@ -847,13 +888,21 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         const int target = h->num_sms * 2;
         int tpc = std::min(max_lat_tasks, 32);
         int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+        int psplit = 1;
         if (npa * task_chunks < target) {
+          // small batch: fewer row-tasks per CTA, and several warps per row-task (point slices)
           const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
           tpc = std::max(2, std::min(tpc, (max_lat_tasks + want - 1) / want));
           task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+          psplit = std::max(1, std::min(std::min(8, 32 / tpc), max_lat_P / 64));
+          // every CTA must see exactly one task iteration per warp group (barriers inside the loop)
+          bool uniform = true;
+          for (const PassHost& q : hph)
+            if (!q.fine && q.nY * ((q.nX + 31) / 32) != max_lat_tasks) uniform = false;
+          if (!uniform || max_lat_tasks % tpc != 0) psplit = 1;
         }
-        const int threads = 32 * std::min(tpc, 32);
-        const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny) * 4;
+        const int threads = 32 * std::min(tpc, 32) * psplit;
+        const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny + (psplit > 1 ? threads : 0)) * 4;
         if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
         if (smem > 48 * 1024 && smem > h->sweep_smem_attr) {
           CK(cudaFuncSetAttribute(k_sweep_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -861,9 +910,10 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         }
         dim3 grid(npa, task_chunks, 1);
         k_sweep_lattice<<<grid, threads, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                     h->d_grids, (double*)h->d_sums.p, d_pmax, tpc);
+                                                     h->d_grids, (double*)h->d_sums.p, d_pmax, tpc, psplit);
         h->launches++;
         h->work[1]++;
+        kt.mark("k_sweep_lattice");
       }
       if (timing) CK(cudaEventRecord(h->ev[3], st));
       if (!hfine.empty()) {
@@ -871,17 +921,20 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         k_sweep_points<<<grid, 256, 0, st>>>(g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
                                              (double*)h->d_sums.p, d_pmax);
         h->launches++;
+        kt.mark("k_sweep_points");
       }
       // ---- K3b/K4 reduce ------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[4], st));
       k_reduce<<<npass, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
                                       d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p);
       h->launches++;
+      kt.mark("k_reduce");
       if (timing) CK(cudaEventRecord(h->ev[5], st));
       CK(cudaMemcpyAsync(h->h_outs.p, h->d_outs.p, sizeof(PassOut) * (size_t)npass, cudaMemcpyDeviceToHost, st));
       if (ang_elems > 0)
         CK(cudaMemcpyAsync(h->h_angsums.p, h->d_angsums.p, (size_t)ang_elems * 4, cudaMemcpyDeviceToHost, st));
       tr.mark("pass launches");
+      kt.mark("d2h");
       CK(cudaStreamSynchronize(st));
       tr.mark("sync");
       CK(cudaGetLastError());
@@ -944,6 +997,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     }
 
     tr.mark("host finalize");
+    kt.dump();
     // ---- results + clear ------------------------------------------------------------------------
     for (int i = 0; i < nw; i++) {
       const MatchState& s = states[i];

@@ -102,7 +102,7 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
              const int* __restrict__ scan_start, const int* __restrict__ scan_count,
              const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
              uint32_t* __restrict__ cells, int* __restrict__ cell_count, uint2* __restrict__ gbox,
-             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max) {
+             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max, int stage) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_tile_total, s_tile_base;
   const int nwarps = blockDim.x >> 5;
@@ -113,9 +113,15 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
   unsigned* s_bits = reinterpret_cast<unsigned*>(s_scan_emit + nbase_max);         // touched-tile bitmap
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int nbitw = (tnx * tnx + 31) >> 5;
+  // small waves: each warp stages its scan's points in shared memory (SoA) so the filter's
+  // dependent loads are LDS instead of L2 round trips
+  double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
+  double* s_py = s_px + pmax;
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) s_bits[i] = 0u;
   if (threadIdx.x == 0) s_tile_total = 0;
   __syncthreads();
+#define YSM_PX(i) (stage ? s_px[i] : pts[2 * (i)])
+#define YSM_PY(i) (stage ? s_py[i] : pts[2 * (i) + 1])
 
   const MatchDev m = matches[blockIdx.x];
   const int nbase = m.base_end - m.base_begin;
@@ -133,11 +139,18 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
     for (int i = lane; i < n; i += 32) out[i] = YSM_INVALID_CELL;
     int emitted = 0;
     if (n > 0) {
+      if (stage) {
+        for (int i = lane; i < n; i += 32) {
+          s_px[i] = pts[2 * i];
+          s_py[i] = pts[2 * i + 1];
+        }
+        __syncwarp();
+      }
       for (int i = lane; i < n; i += 32) {
-        const double fx = pts[2 * i], fy = pts[2 * i + 1];
+        const double fx = YSM_PX(i), fy = YSM_PY(i);
         int j = i + 1;
         while (j < n) {
-          const double dx = fx - pts[2 * j], dy = fy - pts[2 * j + 1];
+          const double dx = fx - YSM_PX(j), dy = fy - YSM_PY(j);
           if (dx * dx + dy * dy > msd) break;
           j++;
         }
@@ -156,16 +169,16 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
       __syncwarp();
       for (int k = lane; k < ntrig - 1; k += 32) {
         const int f = s_trig[k], c = s_trig[k + 1];
-        const double fx = pts[2 * f], fy = pts[2 * f + 1];
-        const double cx = pts[2 * c], cy = pts[2 * c + 1];
+        const double fx = YSM_PX(f), fy = YSM_PY(f);
+        const double cx = YSM_PX(c), cy = YSM_PY(c);
         const double a = m.vpy - fy;
         const double b2 = fx - m.vpx;
         const double cc = fy * m.vpx - fx * m.vpy;
         const double ss = cx * a + cy * b2 + cc;
         if (!(ss < 0.0)) {
           for (int j = f; j < c; j++) {
-            const double vx = (pts[2 * j] - m.gox) * g.scale;
-            const double vy = (pts[2 * j + 1] - m.goy) * g.scale;
+            const double vx = (YSM_PX(j) - m.gox) * g.scale;
+            const double vy = (YSM_PY(j) - m.goy) * g.scale;
             if (vx > -1.0 && vy > -1.0 && vx < 1e9 && vy < 1e9) {
               const int gx = (int)kt_round(vx), gy = (int)kt_round(vy);
               if (gx >= 0 && gx < g.roi && gy >= 0 && gy < g.roi) {
@@ -524,7 +537,7 @@ __global__ void __launch_bounds__(1024, 2)
 k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
                 const PassAngle* __restrict__ pa_list, const TableDev* __restrict__ tables,
                 const int* __restrict__ offsets, const uint8_t* __restrict__ grids,
-                double* __restrict__ resp, double* __restrict__ passmax, int tasks_per_cta) {
+                double* __restrict__ resp, double* __restrict__ passmax, int tasks_per_cta, int psplit) {
   extern __shared__ __align__(16) int s_i[];
   __shared__ int s_minmax[4];  // min off, max off, min base, max base
   __shared__ double s_wmax[32];
@@ -604,14 +617,29 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
   const int np = pend - pbeg;
   const unsigned dsz = (unsigned)g.data_size;
   double wmax = 0.0;
-  for (int task = task0 + warp; task < task1; task += nwarps) {
+  // psplit > 1 (small batches): `psplit` warps share one row-task, each sums a slice of the
+  // points; the slices are combined through shared memory (exact: integer sums)
+  const int chunk = warp % psplit, wtask = warp / psplit, ntw = nwarps / psplit;
+  const int plen = (((np + psplit - 1) / psplit) + 7) & ~7;
+  const int pb = min(np, chunk * plen), pe = min(np, pb + plen);
+  unsigned* s_part = reinterpret_cast<unsigned*>(s_row + ps.nY);  // [nwarps][32] when psplit > 1
+  for (int task = task0 + wtask; task < task1; task += ntw) {
     const int iy = task / nxc, xc = task - iy * nxc;
     const int ix = (xc << 5) + lane;
     const bool active = ix < ps.nX;
     const int base = s_row[iy] + s_col[active ? ix : 0] + minoff;
     const uint8_t* gp = grid + base;
-    const unsigned* uoff = reinterpret_cast<const unsigned*>(s_off);
-    const unsigned sum = safe ? sweep_row<false>(gp, uoff, np, base, dsz) : sweep_row<true>(gp, uoff, np, base, dsz);
+    const unsigned* uoff = reinterpret_cast<const unsigned*>(s_off) + pb;
+    unsigned sum = safe ? sweep_row<false>(gp, uoff, pe - pb, base, dsz) : sweep_row<true>(gp, uoff, pe - pb, base, dsz);
+    if (psplit > 1) {
+      // all warps of the CTA run the same number of task iterations (host sizes tasks_per_cta == ntw)
+      s_part[warp * 32 + lane] = sum;
+      __syncthreads();
+      if (chunk == 0)
+        for (int c = 1; c < psplit; c++) sum += s_part[(warp + c) * 32 + lane];
+      __syncthreads();
+      if (chunk != 0) continue;
+    }
     if (active) {
       const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
       resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
@@ -660,9 +688,12 @@ k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
   const unsigned dsz = (unsigned)g.data_size;
   unsigned sum = 0;
-  for (int p = lane; p < ps.P; p += 32) {
-    const unsigned idx = (unsigned)(base + goff[p]);
-    if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+  for (int p0 = lane; p0 < ps.P; p0 += 128) {
+    unsigned idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) idx[u] = (p0 + 32 * u < ps.P) ? (unsigned)(base + goff[p0 + 32 * u]) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (idx[u] < dsz) sum += (unsigned)__ldg(grid + idx[u]);
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if (lane == 0) {
@@ -727,12 +758,20 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
   const double best = passmax[blockIdx.x];
   __syncthreads();
 
-  // poses tied with the best, in storage order
-  for (int i = tid; i < nposes; i += blockDim.x) {
-    const double r = pr[i];
-    if (kt_double_equal(r, best)) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < YSM_TIE_CAP) s_list[pos] = i;
+  // poses tied with the best, in storage order (loads batched 4 deep to overlap L2 latency)
+  for (int i0 = tid; i0 < nposes; i0 += 4 * blockDim.x) {
+    double r[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * blockDim.x;
+      r[u] = i < nposes ? pr[i] : -1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (r[u] >= 0.0 && kt_double_equal(r[u], best)) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < YSM_TIE_CAP) s_list[pos] = i0 + u * blockDim.x;
+      }
     }
   }
   __syncthreads();
@@ -824,8 +863,16 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
       for (int c = tid; c < ncell; c += blockDim.x) {
         const int iy = c / ps.nX, ix = c - iy * ps.nX;
         double pm = 0.0;  // probs grid is cleared to 0 and max'ed with every response
-        for (int a = 0; a < ps.nA; a++) {
-          const double r = pr[(size_t)c * ps.nA + a];
+        const double* pc = pr + (size_t)c * ps.nA;
+        int a = 0;
+        for (; a + 4 <= ps.nA; a += 4) {
+          const double r0 = pc[a], r1 = pc[a + 1], r2 = pc[a + 2], r3 = pc[a + 3];
+          const double m01 = r0 > r1 ? r0 : r1, m23 = r2 > r3 ? r2 : r3;
+          const double m = m01 > m23 ? m01 : m23;
+          pm = m > pm ? m : pm;
+        }
+        for (; a < ps.nA; a++) {
+          const double r = pc[a];
           pm = r > pm ? r : pm;
         }
         if (pm >= (best - 0.1)) {
@@ -859,9 +906,12 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
       for (int a = warp; a < ps.nA; a += nwarps) {
         const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
         unsigned sum = 0;
-        for (int p = lane; p < ps.P; p += 32) {
-          const unsigned idx = (unsigned)(base + goff[p]);
-          if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+        for (int p0 = lane; p0 < ps.P; p0 += 128) {
+          unsigned idx[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) idx[u] = (p0 + 32 * u < ps.P) ? (unsigned)(base + goff[p0 + 32 * u]) : 0xFFFFFFFFu;
+#pragma unroll
+          for (int u = 0; u < 4; u++) if (idx[u] < dsz) sum += (unsigned)__ldg(grid + idx[u]);
         }
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) angsums[ps.ang_off + a] = (int)sum;
