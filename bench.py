@@ -190,7 +190,7 @@ def run_ours(args, rank, world, local_rank):
     hpool = torch.from_numpy(b["pool"]).pin_memory()
     res = np.zeros(n, dtype=_capi.RESULT_DTYPE)
     acc = {"sweep_ms": 0.0, "build_ms": 0.0, "reduce_ms": 0.0, "total_ms": 0.0, "lookups": 0, "launches": 0,
-           "offset_entries": 0, "poses": 0, "h2d": 0, "d2h": 0, "count": False}
+           "offset_entries": 0, "poses": 0, "h2d": 0, "d2h": 0, "issued": 0, "pruned_launches": 0, "count": False}
 
     def step(pool):
         out = m.match_pool(pool, b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"],
@@ -202,6 +202,7 @@ def run_ours(args, rank, world, local_rank):
             acc["lookups"] += w["lattice_lookups"]; acc["launches"] += w["sweep_launches"]
             acc["offset_entries"] += w["offset_entries"]; acc["poses"] += w["poses"]
             acc["h2d"] += w["h2d_bytes"]; acc["d2h"] += w["d2h_bytes"]
+            acc["issued"] += w["lookups_issued"]; acc["pruned_launches"] += w["pruned_sweep_launches"]
         if world > 1:
             # one all-gather of best poses / responses over NVLink; weak scaling: every
             # rank contributes its own n records
@@ -298,12 +299,15 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "kernel": "k_sweep_lattice (CorrelateScan/GetResponse coarse sweep)",
+            "kernel": ("k_sweep_pruned" if snap["pruned_launches"] else "k_sweep_lattice") +
+                      " (CorrelateScan/GetResponse coarse sweep)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": sweep_bytes / max(snap["launches"], 1),
             "avg_launch_ms": snap["sweep_ms"] / max(snap["launches"], 1), "launches": snap["launches"],
             "lookups_per_s": snap["lookups"] / sweep_s if sweep_s > 0 else None,
+            # exact zero-row pruning: the algorithmic lookups above are Karto's; this many were really issued
+            "lookups_issued_frac": (snap["issued"] / snap["lookups"]) if snap["pruned_launches"] and snap["lookups"] else 1.0,
             "share_of_step": snap["sweep_ms"] / max(snap["total_ms"], 1e-9),
             "build_share": snap["build_ms"] / max(snap["total_ms"], 1e-9),
             "reduce_share": snap["reduce_ms"] / max(snap["total_ms"], 1e-9),

@@ -129,6 +129,30 @@ def test_loop_config_with_degenerate_chains_and_expansion(world):
     m2.close()
 
 
+def test_zero_row_pruning_is_exact(world):
+    """The throughput sweep skips (point, lattice row) spans whose tiles hold no non-zero cell;
+    results must equal the unpruned sweep and the oracle for the sequential config (26 x 26
+    lattice), the loop config (41 x 41: two row groups, two column chunks), penalised or not,
+    including query points whose windows leave the grid (no pruning, flat bounds check)."""
+    import scenarios
+    from yag_slam_b200 import _capi
+    cases = ((None, 720, 10, 31, (0.1, 0.05), True, 20.0), (LOOP, 720, 10, 32, (1.0, 0.2), False, 20.0),
+             (dict(search_size=0.3, smear_deviation=0.07), 360, 2, 33, (0.1, 0.05), True, 20.0),
+             # the query scans keep readings up to 30 m while the matcher grid only spans 12 m
+             (dict(range_threshold=12.0), 360, 3, 34, (0.1, 0.05), True, 30.0))
+    for cfg, P, nb, seed, perturb, penalty, rthr in cases:
+        b = scenarios.make_batch(world, 48, P, nb, seed, perturb=perturb, degenerate_frac=0.1, range_threshold=rthr)
+        ref = scenarios.oracle_results(cfg, b, penalty, False)
+        m = _matcher(cfg, max_slots=48)
+        a = _run(m, b, penalty, False).copy()
+        m.set_debug(_capi.DEBUG_NO_PRUNE)
+        c = _run(m, b, penalty, False).copy()
+        m.close()
+        _assert_parity(a, ref, "pruned sweep %r" % (cfg,))
+        _assert_parity(c, ref, "unpruned sweep %r" % (cfg,))
+        assert a.tobytes() == c.tobytes()
+
+
 def test_shared_query_and_multiwave(world):
     import scenarios
     b = scenarios.make_batch(world, 32, 720, 10, 5, perturb=(1.0, 0.2), shared_query=True)

@@ -15,7 +15,7 @@ PARAM_FIELDS = [
 ]
 
 YSM_OK, YSM_EINVAL, YSM_ECUDA, YSM_ENOMEM, YSM_EMATCH, YSM_EUNSUP = 0, -1, -2, -3, -4, -5
-DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS = 1, 2
+DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS, DEBUG_NO_PRUNE = 1, 2, 4
 
 
 class YsmParams(C.Structure):
@@ -89,7 +89,7 @@ def lib():
     L.ysm_last_kernel_ms.restype = C.c_int
     L.ysm_last_kernel_ms.argtypes = [vp] + [C.POINTER(f64)] * 4
     L.ysm_last_work.restype = C.c_int
-    L.ysm_last_work.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.ysm_last_work.argtypes = [vp, C.POINTER(C.c_int64), i32]
     _lib = L
     return L
 

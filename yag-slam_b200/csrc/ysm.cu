@@ -198,6 +198,8 @@ struct ysm_handle {
   double res_eff = 0.0;
   int slots = 0;
   uint8_t* d_grids = nullptr;
+  uint32_t* d_rowmask = nullptr;  // [slots][tny*tnx]: which rows of every 32x32 tile hold a non-zero cell
+  int tnx = 0, rm_words = 0;
   uint8_t* d_kernel = nullptr;
   std::vector<uint8_t> h_kernel;
   std::string err;
@@ -220,8 +222,9 @@ struct ysm_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
-  size_t sweep_smem_attr = 0, find_smem_attr = 0;
-  int64_t work[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t sweep_smem_attr = 0, find_smem_attr = 0, prune_smem_attr = 0;
+  int64_t work[16] = {0};
+  unsigned long long* d_issued = nullptr;  // device counter: lookups the pruned sweep really issued
 };
 
 #define CK(call)                                                                     \
@@ -342,8 +345,13 @@ extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
   h->slots = (int)slots;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  h->tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  h->rm_words = h->tnx * h->tnx;
   e = cudaMalloc((void**)&h->d_grids, (size_t)slots * g.grid_bytes);
   if (e == cudaSuccess) e = cudaMemset(h->d_grids, 0, (size_t)slots * g.grid_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_rowmask, (size_t)slots * h->rm_words * 4);
+  if (e == cudaSuccess) e = cudaMemset(h->d_rowmask, 0, (size_t)slots * h->rm_words * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_issued, 8);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_kernel, h->h_kernel.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->d_kernel, h->h_kernel.data(), h->h_kernel.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
@@ -354,6 +362,8 @@ extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
   if (e != cudaSuccess) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
     if (h->d_grids) cudaFree(h->d_grids);
+    if (h->d_rowmask) cudaFree(h->d_rowmask);
+    if (h->d_issued) cudaFree(h->d_issued);
     if (h->d_kernel) cudaFree(h->d_kernel);
     delete h;
     return fail(nullptr, YSM_ECUDA, msg);
@@ -367,6 +377,8 @@ extern "C" void ysm_destroy(ysm_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->d_grids) cudaFree(h->d_grids);
+  if (h->d_rowmask) cudaFree(h->d_rowmask);
+  if (h->d_issued) cudaFree(h->d_issued);
   if (h->d_kernel) cudaFree(h->d_kernel);
   DevBuf* bufs[] = {&h->d_pool, &h->d_scan_start, &h->d_scan_count, &h->d_base_idx, &h->d_matches,
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
@@ -399,9 +411,9 @@ extern "C" int ysm_set_debug(ysm_handle* h, int32_t flags) {
 
 extern "C" int64_t ysm_launch_count(const ysm_handle* h) { return h ? h->launches : 0; }
 
-extern "C" int ysm_last_work(const ysm_handle* h, int64_t out[8]) {
-  if (!h || !out) return YSM_EINVAL;
-  for (int i = 0; i < 8; i++) out[i] = h->work[i];
+extern "C" int ysm_last_work(const ysm_handle* h, int64_t* out, int32_t n) {
+  if (!h || !out || n < 0) return YSM_EINVAL;
+  for (int i = 0; i < n; i++) out[i] = i < 16 ? h->work[i] : 0;
   return YSM_OK;
 }
 
@@ -440,7 +452,8 @@ extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_an
 static int clear_wave(ysm_handle* h, const MatchDev* d_matches, int n, cudaStream_t st) {
   if (n <= 0) return YSM_OK;
   k_tile_clear<<<h->num_sms * 8, 256, 0, st>>>(h->g, d_matches, (const int2*)h->d_work.p,
-                                               (const int*)h->d_workcount.p, h->d_grids);
+                                               (const int*)h->d_workcount.p, h->d_grids, h->d_rowmask,
+                                               h->rm_words);
   h->launches++;
   return YSM_OK;
 }
@@ -514,8 +527,9 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   const GridC& g = h->g;
   const bool timing = (h->debug & YSM_DEBUG_TIME_KERNELS) && h->ev_ok;
   h->t_sweep = h->t_build = h->t_reduce = h->t_total = 0.0;
-  for (int i = 0; i < 8; i++) h->work[i] = 0;
+  for (int i = 0; i < 16; i++) h->work[i] = 0;
   if (b->n_matches == 0) return YSM_OK;
+  if (timing) CK(cudaMemsetAsync(h->d_issued, 0, 8, st));
 
   // deferred clear from a previous KEEP_GRIDS batch
   if (h->grids_dirty) {
@@ -702,7 +716,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
                                                        (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
-                                                       h->d_kernel, h->d_grids);
+                                                       h->d_kernel, h->d_grids, h->d_rowmask, h->rm_words);
       h->launches++;
       kt.mark("k_tile_stamp");
     }
@@ -886,31 +900,51 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         // over more CTAs until the machine is full.
         const int npa = (int)hpa.size();
         const int target = h->num_sms * 2;
-        int tpc = std::min(max_lat_tasks, 32);
-        int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-        int psplit = 1;
-        if (npa * task_chunks < target) {
-          // small batch: fewer row-tasks per CTA, and several warps per row-task (point slices)
-          const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
-          tpc = std::max(2, std::min(tpc, (max_lat_tasks + want - 1) / want));
-          task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-          psplit = std::max(1, std::min(std::min(8, 32 / tpc), max_lat_P / 64));
-          // every CTA must see exactly one task iteration per warp group (barriers inside the loop)
-          bool uniform = true;
-          for (const PassHost& q : hph)
-            if (!q.fine && q.nY * ((q.nX + 31) / 32) != max_lat_tasks) uniform = false;
-          if (!uniform || max_lat_tasks % tpc != 0) psplit = 1;
+        const int nrg = (max_lat_ny + 27) / 28, rows_per_cta = (max_lat_ny + nrg - 1) / nrg;
+        const int nxc = (max_lat_nx + 31) / 32, cw = (max_lat_nx + nxc - 1) / nxc;
+        const bool pruned = !(h->debug & YSM_DEBUG_NO_PRUNE) && (long long)npa * nrg * nxc >= target;
+        if (pruned) {
+          // throughput form: zero-row pruning, offsets fused (k_sweep_pruned)
+          int PB = (int)((96 * 1024 / 4 / (2 + rows_per_cta)) & ~31);
+          PB = std::max(32, std::min(PB, (max_lat_P + 31) & ~31));
+          const size_t smem = (size_t)(2 + rows_per_cta) * PB * 4;
+          if (smem > 48 * 1024 && smem > h->prune_smem_attr) {
+            CK(cudaFuncSetAttribute(k_sweep_pruned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            h->prune_smem_attr = smem;
+          }
+          dim3 grid(npa, nrg * nxc, 1);
+          k_sweep_pruned<<<grid, 32 * rows_per_cta, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, d_trig, d_pool, h->d_grids,
+                                                               h->d_rowmask, h->rm_words, h->tnx, (double*)h->d_sums.p,
+                                                               d_pmax, rows_per_cta, cw, PB,
+                                                               timing ? h->d_issued : nullptr);
+          h->work[8]++;
+        } else {
+          int tpc = std::min(max_lat_tasks, 32);
+          int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+          int psplit = 1;
+          if (npa * task_chunks < target) {
+            // small batch: fewer row-tasks per CTA, and several warps per row-task (point slices)
+            const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
+            tpc = std::max(2, std::min(tpc, (max_lat_tasks + want - 1) / want));
+            task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+            psplit = std::max(1, std::min(std::min(8, 32 / tpc), max_lat_P / 64));
+            // every CTA must see exactly one task iteration per warp group (barriers inside the loop)
+            bool uniform = true;
+            for (const PassHost& q : hph)
+              if (!q.fine && q.nY * ((q.nX + 31) / 32) != max_lat_tasks) uniform = false;
+            if (!uniform || max_lat_tasks % tpc != 0) psplit = 1;
+          }
+          const int threads = 32 * std::min(tpc, 32) * psplit;
+          const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny + (psplit > 1 ? threads : 0)) * 4;
+          if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
+          if (smem > 48 * 1024 && smem > h->sweep_smem_attr) {
+            CK(cudaFuncSetAttribute(k_sweep_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            h->sweep_smem_attr = smem;
+          }
+          dim3 grid(npa, task_chunks, 1);
+          k_sweep_lattice<<<grid, threads, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
+                                                       h->d_grids, (double*)h->d_sums.p, d_pmax, tpc, psplit);
         }
-        const int threads = 32 * std::min(tpc, 32) * psplit;
-        const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny + (psplit > 1 ? threads : 0)) * 4;
-        if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
-        if (smem > 48 * 1024 && smem > h->sweep_smem_attr) {
-          CK(cudaFuncSetAttribute(k_sweep_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          h->sweep_smem_attr = smem;
-        }
-        dim3 grid(npa, task_chunks, 1);
-        k_sweep_lattice<<<grid, threads, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                     h->d_grids, (double*)h->d_sums.p, d_pmax, tpc, psplit);
         h->launches++;
         h->work[1]++;
         kt.mark("k_sweep_lattice");
@@ -1031,6 +1065,9 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->t_total = ms;
+    unsigned long long iss = 0;
+    CK(cudaMemcpy(&iss, h->d_issued, 8, cudaMemcpyDeviceToHost));
+    h->work[9] = (int64_t)iss;
   }
   // the clear kernel must not race with a caller that frees / reuses `pool_xy` on the device
   // or with the next call's staging: d_matches/d_cells are reused by the next wave, which is

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(256)
 k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
              const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
              const int2* __restrict__ work, const int* __restrict__ work_count,
-             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids) {
+             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
+             int rm_words) {
   extern __shared__ uint32_t s_k[];  // [4][K][Wk] pre-shifted stamp rows
   __shared__ uint32_t s_tile[8][YSM_TILE * YSM_TILE / 4];
   __shared__ uint32_t s_list[8][YSM_TILE_LIST + 32];
@@ -395,11 +396,18 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
     uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes);
     const int dr = lane >> 3, wd = lane & 7;
     const int gw = (x0t >> 2) + wd;
+    uint32_t rows = 0;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int row = y0t + k * 4 + dr;
-      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = tile[(k * 4 + dr) * 8 + wd];
+      const uint32_t v = tile[(k * 4 + dr) * 8 + wd];
+      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
+      const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        if (nz & (0xFFu << (8 * d))) rows |= 1u << (k * 4 + d);
     }
+    if (lane == 0) rowmask[(size_t)m.slot * rm_words + wk.y] = rows;
     __syncwarp();
   }
 }
@@ -407,7 +415,8 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
 // zero the tiles a wave touched (the slot grids are kept all-zero between matches)
 __global__ void __launch_bounds__(256)
 k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
-             const int* __restrict__ work_count, uint8_t* __restrict__ grids) {
+             const int* __restrict__ work_count, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
+             int rm_words) {
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;
   const int nwork = *work_count;
@@ -418,6 +427,7 @@ k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restri
     const int row = ty * YSM_TILE + r, gw = ((tx * YSM_TILE) >> 2) + wd;
     if (row < g.height && gw < g.stride4)
       reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes)[(size_t)row * g.stride4 + gw] = 0u;
+    if (threadIdx.x == 0) rowmask[(size_t)slot * rm_words + wk.y] = 0u;
   }
 }
 
@@ -428,6 +438,19 @@ k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restri
 // round to cells exactly as Karto (including the add-then-subtract of the grid offset) and
 // store int4-vectorised, point index fastest. grid = (ceil(nA*Ppad/4 / 256), n_tables)
 // ---------------------------------------------------------------------------------------------
+// cell offset (gx, gy) of query point (wx, wy) rotated by the search angle (cosine, sine):
+// the arithmetic of GridIndexLookup::ComputeOffsets, shared by k_offsets and the fused sweep
+__device__ __forceinline__ void offset_cell(const TableDev& t, double scale, double wx, double wy, double cosine,
+                                            double sine, int& gx, int& gy) {
+  const double dx = wx - t.px, dy = wy - t.py;
+  const double lx = t.r00 * dx + t.r01 * dy;
+  const double ly = t.r10 * dx + t.r11 * dy;
+  const double ox = cosine * lx - sine * ly;
+  const double oy = sine * lx + cosine * ly;
+  gx = world_to_grid1(ox + t.gox, t.gox, scale);
+  gy = world_to_grid1(oy + t.goy, t.goy, scale);
+}
+
 __global__ void __launch_bounds__(256)
 k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict__ trig,
           const double* __restrict__ pool, int* __restrict__ offsets) {
@@ -444,13 +467,8 @@ k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict
       int v = 0;
       if (p < t.P) {
         const double wx = pool[2 * (size_t)(t.q_start + p)], wy = pool[2 * (size_t)(t.q_start + p) + 1];
-        const double dx = wx - t.px, dy = wy - t.py;
-        const double lx = t.r00 * dx + t.r01 * dy;
-        const double ly = t.r10 * dx + t.r11 * dy;
-        const double ox = cosine * lx - sine * ly;
-        const double oy = sine * lx + cosine * ly;
-        const int gx = world_to_grid1(ox + t.gox, t.gox, g.scale);
-        const int gy = world_to_grid1(oy + t.goy, t.goy, g.scale);
+        int gx, gy;
+        offset_cell(t, g.scale, wx, wy, cosine, sine, gx, gy);
         v = gx + gy * g.stride;
       }
       o[k] = v;
@@ -657,6 +675,189 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
     double m = s_wmax[0];
     for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
     pass_max_update(passmax, pa.pass, m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3p  CorrelateScan / GetResponse sweep with exact zero-row pruning (throughput form).
+// A lookup only contributes when its cell is non-zero, and most of the (angle, point, lattice
+// row) spans a sweep touches lie in free space. k_tile_stamp leaves one 32-bit word per 32 x 32
+// grid tile saying which tile rows hold a non-zero cell; this kernel
+//   A. computes the angle's lookup offsets itself (ComputeOffsets fused: no table round trip),
+//      and for every query point ORs the <= 3 x 3 tile words under the point's window into a
+//      per-point mask "lattice row r can see a non-zero cell";
+//   B. lets every warp (= one lattice row, lanes = adjacent x poses as in k_sweep_lattice)
+//      compact the offsets of the points whose bit is set into its private shared-memory list;
+//   C. sums only those (identical result: the skipped cells are all zero).
+// CTA = (pass, angle) x (group of <= 28 lattice rows, chunk of <= 32 lattice columns).
+// Windows that could leave the grid (or wrap a row) disable pruning for that batch of points and
+// take Karto's flat bounds check instead.
+// smem: s_flat[PB] | s_mask[PB] | lists[nrows][PB]   (PB = points per batch, host-chosen)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t even_bits64(unsigned long long x) {
+  x &= 0x5555555555555555ull;
+  x = (x | (x >> 1)) & 0x3333333333333333ull;
+  x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+  return (uint32_t)x;
+}
+
+// unchecked: entries are offsets biased by data_size (non-negative), gp already holds -data_size
+__device__ __forceinline__ unsigned sweep_list(const uint8_t* __restrict__ gp, const unsigned* __restrict__ s_e, int n) {
+  unsigned sum0 = 0, sum1 = 0;
+  int p = 0;
+  for (; p + 8 <= n; p += 8) {
+    const uint4 o0 = *reinterpret_cast<const uint4*>(s_e + p);
+    const uint4 o1 = *reinterpret_cast<const uint4*>(s_e + p + 4);
+    const unsigned v0 = __ldg(gp + o0.x), v1 = __ldg(gp + o0.y), v2 = __ldg(gp + o0.z), v3 = __ldg(gp + o0.w);
+    const unsigned v4 = __ldg(gp + o1.x), v5 = __ldg(gp + o1.y), v6 = __ldg(gp + o1.z), v7 = __ldg(gp + o1.w);
+    sum0 += v0 + v1 + v2 + v3;
+    sum1 += v4 + v5 + v6 + v7;
+  }
+  for (; p < n; p++) sum0 += (unsigned)__ldg(gp + s_e[p]);
+  return sum0 + sum1;
+}
+
+// checked: entries are raw (signed) flat offsets; Karto's IsUpTo(index, dataSize) test per lookup
+__device__ __forceinline__ unsigned sweep_list_checked(const uint8_t* __restrict__ grid, int base,
+                                                       const unsigned* __restrict__ s_e, int n, unsigned dsz) {
+  unsigned sum = 0;
+  for (int p = 0; p < n; p++) {
+    const unsigned idx = (unsigned)(base + (int)s_e[p]);
+    if (idx < dsz) sum += (unsigned)__ldg(grid + idx);
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(896, 2)
+k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const PassAngle* __restrict__ pa_list,
+               const TableDev* __restrict__ tables, const double* __restrict__ trig,
+               const double* __restrict__ pool, const uint8_t* __restrict__ grids,
+               const uint32_t* __restrict__ rowmask, int rm_words, int tnx, double* __restrict__ resp,
+               double* __restrict__ passmax, int rows_per_cta, int cw, int PB,
+               unsigned long long* __restrict__ issued) {
+  extern __shared__ __align__(16) uint32_t s_u[];
+  __shared__ double s_wmax[32];
+  __shared__ int s_col[32], s_row[32];
+  __shared__ unsigned s_issued;
+  if (threadIdx.x == 0) s_issued = 0u;
+  const PassAngle pa = pa_list[blockIdx.x];
+  const PassDev ps = passes[pa.pass];
+  const int nxc = (ps.nX + cw - 1) / cw;
+  const int rg = blockIdx.y / nxc, xc = blockIdx.y - rg * nxc;
+  const int iy0 = rg * rows_per_cta, ix0 = xc * cw;
+  if (iy0 >= ps.nY || ix0 >= ps.nX) return;
+  const int nr = min(rows_per_cta, ps.nY - iy0), nxl = min(cw, ps.nX - ix0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int* s_flat = reinterpret_cast<int*>(s_u);
+  uint32_t* s_mask = s_u + PB;
+  uint32_t* s_list = s_u + 2 * PB + (size_t)warp * PB;  // warp-private
+  const TableDev tb = tables[ps.table];
+  const double cosine = trig[2 * (tb.trig_off + pa.a)], sine = trig[2 * (tb.trig_off + pa.a) + 1];
+  const double* qpts = pool + 2 * (size_t)tb.q_start;
+  // lattice cells of this CTA, exactly as CorrelateScan rounds them (A.7)
+  if (threadIdx.x < 32) {
+    if (lane < nxl) {
+      const double x = -ps.offx + (double)(ix0 + lane) * ps.resx;
+      s_col[lane] = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+    }
+    if (lane < nr) {
+      const double y = -ps.offy + (double)(iy0 + lane) * ps.resy;
+      s_row[lane] = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
+    }
+  }
+  __syncthreads();
+  // pruning needs a regular lattice (step 1 or 2 cells): col(i) = col(0) + i*sx, row(i) = row(0) + i*sy
+  const int sx = nxl > 1 ? s_col[1] - s_col[0] : 1, sy = nr > 1 ? s_row[1] - s_row[0] : 1;
+  bool regular = (sx == 1 || sx == 2) && (sy == 1 || sy == 2);
+  if (lane < nxl) regular = regular && s_col[lane] == s_col[0] + lane * sx;
+  if (lane < nr) regular = regular && s_row[lane] == s_row[0] + lane * sy;
+  regular = __all_sync(0xffffffffu, regular);  // every warp evaluates the same 32 entries
+  // window of this CTA for a point at cell offset (gx, gy): columns xa .. xa + xspan, rows ya .. ya + yspan
+  const int xa0 = s_col[0], ya0 = s_row[0];
+  const int xspan = s_col[nxl - 1] - s_col[0], yspan = s_row[nr - 1] - s_row[0];
+  const uint32_t* rm = rowmask + (size_t)ps.slot * rm_words;
+  const uint32_t rows_all = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
+  const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+  const unsigned dsz = (unsigned)g.data_size;
+  const bool row_warp = warp < nr;
+  const bool active = row_warp && lane < nxl;
+  const int base = s_row[row_warp ? warp : 0] * g.stride + s_col[active ? lane : 0];
+  unsigned sum = 0;
+
+  for (int pb = 0; pb < ps.P; pb += PB) {
+    const int nb = min(PB, ps.P - pb);
+    if (pb) __syncthreads();  // the previous batch's s_flat / s_mask are still being read
+    // ---- A: offsets + per-point row masks ----------------------------------------------------
+    int ok = 1;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const double2 w = *reinterpret_cast<const double2*>(qpts + 2 * (size_t)(pb + i));
+      int gx, gy;
+      offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
+      s_flat[i] = gx + gy * g.stride;
+      const int xa = xa0 + gx, ya = ya0 + gy;
+      uint32_t mask = rows_all;
+      if (regular && xa >= 0 && ya >= 0 && xa + xspan < g.width && ya + yspan < g.height) {
+        const int txa = xa >> 5, txb = (xa + xspan) >> 5, tya = ya >> 5, tyb = (ya + yspan) >> 5;
+        uint32_t m[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          if (tya + j <= tyb) {
+            const uint32_t* r = rm + (size_t)(tya + j) * tnx;
+            uint32_t v = __ldg(r + txa);
+            if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
+            if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
+            m[j] = v;
+          }
+        }
+        const int sft = ya & 31;
+        const unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
+        const unsigned long long S = sft ? ((lo >> sft) | ((unsigned long long)m[2] << (64 - sft))) : lo;
+        mask = (sy == 2 ? even_bits64(S) : (uint32_t)S) & rows_all;
+      } else {
+        ok = 0;
+      }
+      s_mask[i] = mask;
+    }
+    const int safe = __syncthreads_and(ok);
+    // ---- B: this warp's list, C: its sums ------------------------------------------------------
+    if (row_warp) {
+      int cnt = 0;
+      const unsigned bias = safe ? dsz : 0u;
+      for (int i0 = 0; i0 < nb; i0 += 32) {
+        const int i = i0 + lane;
+        const bool take = i < nb && (!safe || ((s_mask[i] >> warp) & 1u));
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned)s_flat[i] + bias;
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+      if (issued && lane == 0) atomicAdd(&s_issued, (unsigned)(cnt * nxl));
+      if (safe) sum += sweep_list(grid + (base - (long long)dsz), s_list, cnt);
+      else sum += sweep_list_checked(grid, base, s_list, cnt, dsz);
+      __syncwarp();
+    }
+  }
+  double wmax = 0.0;
+  if (active) {
+    const int ix = ix0 + lane, iy = iy0 + warp;
+    const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
+    resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
+    wmax = rr;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, wmax, o);
+    wmax = t > wmax ? t : wmax;
+  }
+  if (lane == 0) s_wmax[warp] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = s_wmax[0];
+    for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
+    pass_max_update(passmax, pa.pass, m);
+    if (issued) atomicAdd(issued, (unsigned long long)s_issued);  // lookups actually performed (bench accounting)
   }
 }
 

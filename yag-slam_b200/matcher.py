@@ -77,10 +77,11 @@ class ScanMatcherB200(object):
         return dict(zip(("sweep", "build", "reduce", "total"), (x.value for x in v)))
 
     def last_work(self):
-        v = (C.c_int64 * 8)()
-        self._lib.ysm_last_work(self._h, v)
+        v = (C.c_int64 * 16)()
+        self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
-                         "base_points", "h2d_bytes", "d2h_bytes"), (int(x) for x in v)))
+                         "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued"),
+                        (int(x) for x in v)))
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
                    penalty=True, do_fine=False, stream=0, out=None):
