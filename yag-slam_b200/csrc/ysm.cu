@@ -185,9 +185,50 @@ struct PassHost {
   double cx, cy, ch, offx, offy, resx, resy, angle_offset, angle_res;
   int nA, nX, nY;
   int ang_off;
+  bool spec;  // speculative fine pass resolved on the device
 };
 
 }  // namespace
+
+// --------------------------------------------------------------------------------------------
+// One iteration of CorrelateScan passes over the wave (host-side description).
+namespace {
+
+struct PassPlan {
+  std::vector<TableDev> tab;
+  std::vector<PassDev> pass;
+  std::vector<PassHost> ph;
+  std::vector<PassAngle> pa;
+  std::vector<int> fine;       // ids of the fine passes scheduled by the host
+  std::vector<int> spec_fine;  // ids of the speculative fine passes (latency path)
+  std::vector<double> trig;
+  std::vector<int> spec_of;    // coarse pass id -> its speculative fine pass id (-1)
+  std::vector<int> spec_h;     // coarse pass id -> index of its heading table in trig (doubles)
+  std::unordered_map<TableKey, int, TableKeyHash> tab_index;
+  size_t off_elems = 0, sums_elems = 0;
+  int ang_elems = 0;
+  int max_lat_P = 0, max_lat_nx = 0, max_lat_ny = 0, max_lat_tasks = 0, max_fine_poses = 0;
+  int first_spec_table = -1;
+  void clear() {
+    tab.clear(); pass.clear(); ph.clear(); pa.clear(); fine.clear(); spec_fine.clear(); trig.clear();
+    spec_of.clear(); spec_h.clear(); tab_index.clear();
+    off_elems = sums_elems = 0;
+    ang_elems = 0;
+    max_lat_P = max_lat_nx = max_lat_ny = max_lat_tasks = max_fine_poses = 0;
+    first_spec_table = -1;
+  }
+};
+
+// byte layout of one staging blob (host pinned mirror == device copy)
+struct BlobLayout {
+  size_t pool = 0, scan_start = 0, scan_count = 0, matches = 0, base = 0, workcount = 0;  // wave-static part
+  size_t tab = 0, pass = 0, pa = 0, fine = 0, trig = 0, pmax = 0, total = 0;
+};
+
+inline size_t a16(size_t v) { return (v + 15) / 16 * 16; }
+
+}  // namespace
+
 
 struct ysm_handle {
   ysm_params prm;
@@ -210,19 +251,24 @@ struct ysm_handle {
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
   DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
-  PinBuf h_blob, h_outs, h_angsums;
+  DevBuf d_wblob;
+  PinBuf h_blob, h_wblob, h_outs, h_angsums;
+  PassPlan plan;
+  const MatchDev* cur_matches = nullptr;  // device views of the last wave (deferred clear)
+  int* cur_workcount = nullptr;
   // last-batch debug info
   std::vector<int> last_slot_of_match;    // match -> slot (only for the last wave)
   std::vector<int> last_coarse_table_off; // match -> offsets element offset of its first coarse table
   std::vector<int> last_coarse_nA, last_coarse_P, last_coarse_Ppad;
   int last_wave_begin = 0, last_wave_end = 0;
   bool grids_dirty = false;
-  std::vector<MatchDev> dirty_matches;  // for deferred clear in KEEP_GRIDS mode
   // timing
   cudaEvent_t ev[8];
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
   size_t sweep_smem_attr = 0, find_smem_attr = 0, prune_smem_attr = 0;
+  bool ordered_stamps = false;  // wide smear: AddScan's skip rule is order dependent
+  size_t order_smem_attr = 0;
   int64_t work[16] = {0};
   unsigned long long* d_issued = nullptr;  // device counter: lookups the pruned sweep really issued
 };
@@ -313,17 +359,23 @@ extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
     delete h;
     return fail(nullptr, YSM_EUNSUP, "kernel larger than the grid border");
   }
-  // The parallel smear relies on the kernel being 100 only at its centre; when
-  // smear_deviation >= ~9.99 * resolution Karto's "cell already occupied -> skip" test makes
-  // the result depend on point order, which the scatter kernel does not reproduce yet.
+  // The parallel smear is order-independent only while the stamp is 100 at its centre alone. For
+  // smear_deviation >= ~9.99 * resolution its four edge neighbours are 100 as well and Karto's
+  // "cell already occupied -> skip" test makes the set of stamps depend on the point order:
+  // k_stamp_order replays that order before the stamping kernel.
   {
     int hot = 0;
     for (uint8_t v : h->h_kernel) hot += (v == 100);
-    if (hot != 1) {
+    const int hk = g.half_kernel, K = g.K;
+    const bool plus = hot == 5 && h->h_kernel[(size_t)(hk - 1) + (size_t)K * hk] == 100 &&
+                      h->h_kernel[(size_t)(hk + 1) + (size_t)K * hk] == 100 &&
+                      h->h_kernel[(size_t)hk + (size_t)K * (hk - 1)] == 100 &&
+                      h->h_kernel[(size_t)hk + (size_t)K * (hk + 1)] == 100;
+    if (hot != 1 && !plus) {
       delete h;
-      return fail(nullptr, YSM_EUNSUP,
-                  "smear_deviation >= ~9.99*resolution (kernel has several 100-valued taps) is not supported yet");
+      return fail(nullptr, YSM_EUNSUP, "smear kernel with an unexpected set of 100-valued taps");
     }
+    h->ordered_stamps = (hot == 5);
   }
   g.Wk = (g.K + 6) / 4;
   h->pen.distance_variance_penalty = p->distance_variance_penalty;
@@ -384,9 +436,10 @@ extern "C" void ysm_destroy(ysm_handle* h) {
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
                     &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
-                    &h->d_angsums, &h->d_blob};
+                    &h->d_angsums, &h->d_blob, &h->d_wblob};
   for (DevBuf* b : bufs) b->release();
   h->h_blob.release();
+  h->h_wblob.release();
   h->h_outs.release();
   h->h_angsums.release();
   if (h->ev_ok)
@@ -449,11 +502,9 @@ extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_an
 // --------------------------------------------------------------------------------------------
 // zero the tiles of the last built wave (its work list is still resident) -- the grids
 // return to all-zero
-static int clear_wave(ysm_handle* h, const MatchDev* d_matches, int n, cudaStream_t st) {
-  if (n <= 0) return YSM_OK;
-  k_tile_clear<<<h->num_sms * 8, 256, 0, st>>>(h->g, d_matches, (const int2*)h->d_work.p,
-                                               (const int*)h->d_workcount.p, h->d_grids, h->d_rowmask,
-                                               h->rm_words);
+static int clear_wave(ysm_handle* h, const MatchDev* d_matches, cudaStream_t st) {
+  k_tile_clear<<<h->num_sms * 8, 256, 0, st>>>(h->g, d_matches, (const int2*)h->d_work.p, h->cur_workcount, h->d_grids,
+                                               h->d_rowmask, h->rm_words);
   h->launches++;
   return YSM_OK;
 }
@@ -514,6 +565,21 @@ static void finalize_angular(const PassHost& ph, const PassOut& po, double headi
 
 static inline int n_steps(double off, double res) { return (int)(uint32_t)(h_round(off * 2.0 / res) + 1); }
 
+static void fill_inverse_rotation(TableDev& t, const double* pose) {
+  // Transform(sensorPose): m_InverseRotation = FromAxisAngle(0,0,1, 0 - heading)
+  if (pose[0] == 0.0 && pose[1] == 0.0 && pose[2] == 0.0) {
+    t.r00 = 1.0; t.r01 = 0.0; t.r10 = 0.0; t.r11 = 1.0;
+  } else {
+    const double radians = 0.0 - pose[2];
+    const double c = cos(radians), sn = sin(radians);
+    const double omc = 1.0 - c;
+    t.r00 = 0.0 * omc + c;
+    t.r01 = (0.0 * 0.0 * omc) - (1.0 * sn);
+    t.r10 = (0.0 * 0.0 * omc) + (1.0 * sn);
+    t.r11 = 0.0 * omc + c;
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
   if (!h || !b || !out) return YSM_EINVAL;
@@ -533,9 +599,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
 
   // deferred clear from a previous KEEP_GRIDS batch
   if (h->grids_dirty) {
-    clear_wave(h, (const MatchDev*)h->d_matches.p, (int)h->dirty_matches.size(), st);
+    clear_wave(h, h->cur_matches, st);
     h->grids_dirty = false;
-    h->dirty_matches.clear();
   }
 
   // validate + sizes
@@ -554,46 +619,51 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       if (b->base_idx[k] < 0 || b->base_idx[k] >= b->n_scans) return fail(h, YSM_EINVAL, "bad base scan index");
   }
 
-  // pool -> device
+  // Latency path: a handful of matches over a small pool. Everything the GPU needs (points,
+  // descriptors, pass tables) travels in ONE host->device copy, the fine pass is chained on the
+  // device behind the coarse pass (k_reduce points it at the winner), and the host synchronises once.
+  const bool small = b->n_matches <= 8 && b->n_matches <= h->slots &&
+                     (b->pool_on_device || (size_t)b->n_points * 16 <= (1u << 20)) && b->n_scans <= 4096;
+  const bool speculate = small && b->do_refine && !(h->debug & YSM_DEBUG_NO_SPECULATE);
+
+  // pool / scan directory -> device (throughput path: once per call, straight from the caller's memory)
   const double* d_pool = nullptr;
-  if (b->pool_on_device) {
-    d_pool = b->pool_xy;
-  } else {
-    CK(h->d_pool.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
-    if (b->n_points > 0)
-      CK(cudaMemcpyAsync(h->d_pool.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
-    h->work[6] += (int64_t)b->n_points * 16;
-    d_pool = (const double*)h->d_pool.p;
-  }
-  CK(h->d_scan_start.ensure((size_t)std::max(1, b->n_scans) * 4));
-  CK(h->d_scan_count.ensure((size_t)std::max(1, b->n_scans) * 4));
-  if (b->n_scans > 0) {
-    CK(cudaMemcpyAsync(h->d_scan_start.p, b->scan_start, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_scan_count.p, b->scan_count, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
-    h->work[6] += (int64_t)b->n_scans * 8;
+  const int *d_scan_start = nullptr, *d_scan_count = nullptr;
+  if (b->pool_on_device) d_pool = b->pool_xy;
+  if (!small) {
+    if (!b->pool_on_device) {
+      CK(h->d_pool.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
+      if (b->n_points > 0)
+        CK(cudaMemcpyAsync(h->d_pool.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
+      h->work[6] += (int64_t)b->n_points * 16;
+      d_pool = (const double*)h->d_pool.p;
+    }
+    CK(h->d_scan_start.ensure((size_t)std::max(1, b->n_scans) * 4));
+    CK(h->d_scan_count.ensure((size_t)std::max(1, b->n_scans) * 4));
+    if (b->n_scans > 0) {
+      CK(cudaMemcpyAsync(h->d_scan_start.p, b->scan_start, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(h->d_scan_count.p, b->scan_count, (size_t)b->n_scans * 4, cudaMemcpyHostToDevice, st));
+      h->work[6] += (int64_t)b->n_scans * 8;
+    }
+    d_scan_start = (const int*)h->d_scan_start.p;
+    d_scan_count = (const int*)h->d_scan_count.p;
   }
 
   if (timing) CK(cudaEventRecord(h->ev[6], st));
   tr.mark("validate + pool H2D");
 
-  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int tiles_per_grid = tnx * tnx;
+  const int tiles_per_grid = h->tnx * h->tnx;
   const int tps1 = (2 * g.half_kernel + YSM_TILE - 1) / YSM_TILE + 1;  // tiles a stamp can span per axis
   const int tiles_per_stamp = tps1 * tps1;
   const double csx = 0.5 * (h->side - 1) * h->res_eff;
   const double crx = 2 * h->res_eff;
   const int S = h->slots;
+  const int nAf = n_steps(0.5 * h->prm.coarse_angle_resolution, h->prm.fine_search_angle_resolution);
 
   std::vector<MatchState> states;
   std::vector<MatchDev> hm;
   std::vector<int> hbase;
-  std::vector<TableDev> htab;
-  std::vector<PassDev> hpass;
-  std::vector<PassHost> hph;
-  std::vector<PassAngle> hpa;
-  std::vector<int> hfine;
-  std::vector<double> htrig;
-  std::unordered_map<TableKey, int, TableKeyHash> tab_index;
+  PassPlan& pl = h->plan;
 
   h->last_slot_of_match.assign(b->n_matches, -1);
   h->last_coarse_table_off.assign(b->n_matches, -1);
@@ -610,9 +680,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     states.assign(nw, MatchState());
     hm.assign(nw, MatchDev());
     hbase.clear();
-    long long cells_total = 0, gbox_total = 0, work_cap = 0;
+    long long cells_total = 0, gbox_total = 0, work_cap = 0, max_match_cells = 1;
     int nbase_max = 1;
-    int n_active = 0;
     for (int i = 0; i < nw; i++) {
       const int mi = w0 + i;
       MatchState& s = states[i];
@@ -649,6 +718,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       m.gbox_off = (int)gbox_total;
       m.pad0 = 0;
       cells_total += mc;
+      max_match_cells = std::max(max_match_cells, mc);
       gbox_total += (mc + 31) / 32;
       work_cap += std::min<long long>((long long)tiles_per_grid, mc * tiles_per_stamp);
       m.vpx = s.pose[0]; m.vpy = s.pose[1];
@@ -660,78 +730,27 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         s.cov[4] = MAX_VARIANCE;
         s.cov[8] = 4 * h_square(h->prm.coarse_angle_resolution);
         s.best = 0.0;
-      } else {
-        n_active++;
       }
       h->last_slot_of_match[mi] = i;
     }
     if (cells_total > 0x7fffff00LL) return fail(h, YSM_ENOMEM, "wave has too many base points");
-    CK(h->d_matches.ensure(sizeof(MatchDev) * (size_t)nw));
-    CK(h->d_base_idx.ensure(std::max<size_t>(4, hbase.size() * 4)));
     CK(h->d_cells.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
     CK(h->d_ptcell.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
     CK(h->d_cellcount.ensure((size_t)nw * 4));
     CK(h->d_gbox.ensure(std::max<size_t>(8, (size_t)gbox_total * 8)));
     CK(h->d_work.ensure(std::max<size_t>(8, (size_t)work_cap * 8)));
-    CK(h->d_workcount.ensure(4));
-    CK(cudaMemsetAsync(h->d_workcount.p, 0, 4, st));
-    CK(cudaMemcpyAsync(h->d_matches.p, hm.data(), sizeof(MatchDev) * (size_t)nw, cudaMemcpyHostToDevice, st));
-    if (!hbase.empty())
-      CK(cudaMemcpyAsync(h->d_base_idx.p, hbase.data(), hbase.size() * 4, cudaMemcpyHostToDevice, st));
-    h->work[6] += (int64_t)(sizeof(MatchDev) * (size_t)nw + hbase.size() * 4);
     h->work[5] += cells_total;
 
-    tr.mark("wave setup + H2D");
-    // ---- K1: grid build -----------------------------------------------------------------------
-    if (timing) CK(cudaEventRecord(h->ev[0], st));
-    {
-      const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
-      const size_t fixed = 4 * (size_t)nbase_max + bits_bytes;
-      // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
-      int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
-      while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
-      size_t smem = (size_t)nwarps * 4 * pmax + fixed;
-      int stage = 0;
-      if (nw < 2 * h->num_sms) {  // latency mode: stage scan points in shared memory if they fit
-        const size_t with_pts = ((smem + 15) & ~(size_t)15) + (size_t)nwarps * 16 * pmax;
-        if (with_pts <= 200 * 1024) {
-          smem = with_pts;
-          stage = 1;
-        }
-      }
-      if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points / tiles for the filter kernel");
-      if (smem > 48 * 1024 && smem > h->find_smem_attr) {
-        CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->find_smem_attr = smem;
-      }
-      k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, (const MatchDev*)h->d_matches.p, (const int*)h->d_base_idx.p,
-                                                   (const int*)h->d_scan_start.p, (const int*)h->d_scan_count.p,
-                                                   d_pool, (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
-                                                   (int*)h->d_cellcount.p, (uint2*)h->d_gbox.p, (int2*)h->d_work.p,
-                                                   (int*)h->d_workcount.p, pmax, nbase_max, stage);
-      h->launches++;
-      kt.mark("k_find_valid");
-      const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
-      const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
-      k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, (const MatchDev*)h->d_matches.p, (const uint32_t*)h->d_cells.p,
-                                                       (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
-                                                       (const int2*)h->d_work.p, (const int*)h->d_workcount.p,
-                                                       h->d_kernel, h->d_grids, h->d_rowmask, h->rm_words);
-      h->launches++;
-      kt.mark("k_tile_stamp");
-    }
-    if (timing) CK(cudaEventRecord(h->ev[1], st));
-    CK(cudaGetLastError());
+    // device views of the wave-static data (set by upload below)
+    const MatchDev* d_matches = nullptr;
+    const int* d_base_idx = nullptr;
+    int* d_workcount = nullptr;
 
-    tr.mark("build launches");
-    // ---- pass iterations ------------------------------------------------------------------------
-    int iter = 0;
-    while (true) {
-      htab.clear(); hpass.clear(); hph.clear(); hpa.clear(); hfine.clear(); htrig.clear();
-      tab_index.clear();
-      size_t off_elems = 0, sums_elems = 0;
-      int ang_elems = 0;
-      int max_lat_P = 0, max_lat_nx = 0, max_lat_ny = 0, max_lat_tasks = 0, max_fine_poses = 0;
+    // ---- pass planning (host libm) -----------------------------------------------------------
+    // Builds the tables / passes of the next iteration for every match that is not done. With
+    // `spec`, every coarse pass also gets a speculative fine pass resolved on the device.
+    auto plan_passes = [&](bool spec) -> int {
+      pl.clear();
       for (int i = 0; i < nw; i++) {
         MatchState& s = states[i];
         if (s.stage >= 5) continue;
@@ -752,6 +771,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         ph.nX = n_steps(ph.offx, ph.resx);
         ph.nY = n_steps(ph.offy, ph.resy);
         ph.nA = n_steps(ph.angle_offset, ph.angle_res);
+        ph.spec = false;
         if (ph.nA <= 0 || ph.nA > 100000) return fail(h, YSM_EINVAL, "bad angle search window");
         // lookup table (deduplicated: same query scan, pose and angle window share one table)
         TableKey key;
@@ -759,154 +779,370 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         key.b[0] = dbits(s.pose[0]); key.b[1] = dbits(s.pose[1]); key.b[2] = dbits(s.pose[2]);
         key.b[3] = dbits(ph.ch); key.b[4] = dbits(ph.angle_offset); key.b[5] = dbits(ph.angle_res);
         int tid;
-        auto it = tab_index.find(key);
+        auto it = pl.tab_index.find(key);
         const int Ppad = align_up(s.P, 4);
-        if (it == tab_index.end()) {
+        if (it == pl.tab_index.end()) {
           TableDev t;
           t.q_start = b->scan_start[s.q];
           t.P = s.P; t.Ppad = Ppad; t.nA = ph.nA;
-          t.trig_off = (int)(htrig.size() / 2);
-          t.out_off = (int)off_elems;
-          off_elems += (size_t)ph.nA * Ppad;
+          t.trig_off = (int)(pl.trig.size() / 2);
+          t.out_off = (int)pl.off_elems;
+          pl.off_elems += (size_t)ph.nA * Ppad;
           t.px = s.pose[0]; t.py = s.pose[1];
-          // Transform(sensorPose): m_InverseRotation = FromAxisAngle(0,0,1, 0 - heading)
-          if (s.pose[0] == 0.0 && s.pose[1] == 0.0 && s.pose[2] == 0.0) {
-            t.r00 = 1.0; t.r01 = 0.0; t.r10 = 0.0; t.r11 = 1.0;
-          } else {
-            const double radians = 0.0 - s.pose[2];
-            const double c = cos(radians), sn = sin(radians);
-            const double omc = 1.0 - c;
-            t.r00 = 0.0 * omc + c;
-            t.r01 = (0.0 * 0.0 * omc) - (1.0 * sn);
-            t.r10 = (0.0 * 0.0 * omc) + (1.0 * sn);
-            t.r11 = 0.0 * omc + c;
-          }
+          fill_inverse_rotation(t, s.pose);
           t.gox = s.gox; t.goy = s.goy;
           const double start_angle = ph.ch - ph.angle_offset;
           for (int a = 0; a < ph.nA; a++) {
             const double angle = start_angle + (double)(uint32_t)a * ph.angle_res;
-            htrig.push_back(cos(angle));
-            htrig.push_back(sin(angle));
+            pl.trig.push_back(cos(angle));
+            pl.trig.push_back(sin(angle));
           }
-          tid = (int)htab.size();
-          htab.push_back(t);
-          tab_index.emplace(key, tid);
+          tid = (int)pl.tab.size();
+          pl.tab.push_back(t);
+          pl.tab_index.emplace(key, tid);
         } else {
           tid = it->second;
         }
         PassDev pd;
+        memset(&pd, 0, sizeof(pd));
         pd.slot = s.slot; pd.table = tid; pd.nA = ph.nA; pd.nX = ph.nX; pd.nY = ph.nY;
         pd.P = s.P; pd.Ppad = Ppad; pd.fine = ph.fine ? 1 : 0; pd.penalize = b->do_penalize ? 1 : 0;
-        pd.sums_off = (int)sums_elems;
-        sums_elems += (size_t)ph.nX * ph.nY * ph.nA;
-        // cos/sin of the normalised headings (tie average). Identical to the table's when
-        // normalisation is a no-op; evaluated separately otherwise.
-        pd.htrig_off = (int)(htrig.size() / 2);
+        pd.sums_off = (int)pl.sums_elems;
+        pl.sums_elems += (size_t)ph.nX * ph.nY * ph.nA;
+        // cos/sin of the normalised headings (tie average); the table's own entries when
+        // normalisation leaves every angle unchanged
         {
           const double start_angle = ph.ch - ph.angle_offset;
-          for (int a = 0; a < ph.nA; a++) {
+          bool same = true;
+          for (int a = 0; a < ph.nA && same; a++) {
             const double angle = start_angle + (double)(uint32_t)a * ph.angle_res;
-            const double hn = h_normalize_angle(angle);
-            htrig.push_back(cos(hn));
-            htrig.push_back(sin(hn));
+            same = dbits(h_normalize_angle(angle)) == dbits(angle);
+          }
+          if (same) {
+            pd.htrig_off = pl.tab[tid].trig_off;
+          } else {
+            pd.htrig_off = (int)(pl.trig.size() / 2);
+            for (int a = 0; a < ph.nA; a++) {
+              const double hn = h_normalize_angle(start_angle + (double)(uint32_t)a * ph.angle_res);
+              pl.trig.push_back(cos(hn));
+              pl.trig.push_back(sin(hn));
+            }
           }
         }
-        pd.ang_off = ang_elems;
-        ph.ang_off = ang_elems;
-        if (ph.fine) ang_elems += ph.nA;
+        pd.ang_off = pl.ang_elems;
+        ph.ang_off = pl.ang_elems;
+        if (ph.fine) pl.ang_elems += ph.nA;
+        pd.spec = -1;
         pd.cx = ph.cx; pd.cy = ph.cy; pd.ch = ph.ch;
         pd.offx = ph.offx; pd.offy = ph.offy; pd.resx = ph.resx; pd.resy = ph.resy;
         pd.angle_offset = ph.angle_offset; pd.angle_res = ph.angle_res;
         pd.gox = s.gox; pd.goy = s.goy;
-        const int pid = (int)hpass.size();
+        const int pid = (int)pl.pass.size();
         s.pass_id = pid;
-        hpass.push_back(pd);
-        hph.push_back(ph);
+        pl.pass.push_back(pd);
+        pl.ph.push_back(ph);
+        pl.spec_of.push_back(-1);
+        pl.spec_h.push_back(-1);
         if (!ph.fine) {
-          for (int a = 0; a < ph.nA; a++) hpa.push_back(PassAngle{pid, a});
+          for (int a = 0; a < ph.nA; a++) pl.pa.push_back(PassAngle{pid, a});
           h->work[0] += (int64_t)ph.nX * ph.nY * ph.nA * s.P;
-          max_lat_P = std::max(max_lat_P, s.P);
-          max_lat_nx = std::max(max_lat_nx, ph.nX);
-          max_lat_ny = std::max(max_lat_ny, ph.nY);
-          max_lat_tasks = std::max(max_lat_tasks, ph.nY * ((ph.nX + 31) / 32));
+          pl.max_lat_P = std::max(pl.max_lat_P, s.P);
+          pl.max_lat_nx = std::max(pl.max_lat_nx, ph.nX);
+          pl.max_lat_ny = std::max(pl.max_lat_ny, ph.nY);
+          pl.max_lat_tasks = std::max(pl.max_lat_tasks, ph.nY * ((ph.nX + 31) / 32));
           if (s.stage == 0) {
-            h->last_coarse_table_off[s.idx] = htab[tid].out_off;
+            h->last_coarse_table_off[s.idx] = pl.tab[tid].out_off;
             h->last_coarse_nA[s.idx] = ph.nA;
             h->last_coarse_P[s.idx] = s.P;
             h->last_coarse_Ppad[s.idx] = Ppad;
           }
         } else {
-          hfine.push_back(pid);
+          pl.fine.push_back(pid);
           h->work[4] += (int64_t)(ph.nX * ph.nY + 1) * ph.nA * s.P;
-          max_fine_poses = std::max(max_fine_poses, ph.nX * ph.nY * ph.nA);
+          pl.max_fine_poses = std::max(pl.max_fine_poses, ph.nX * ph.nY * ph.nA);
         }
       }
-      const int npass = (int)hpass.size();
+      if (spec) {
+        // speculative fine passes, one per coarse pass: everything but the search centre is known;
+        // for each possible winning coarse angle the host tabulates the heading atan2 would return
+        // and the fine search angles around it (cos/sin of the angle and of its normalisation).
+        const int ncoarse = (int)pl.pass.size();
+        pl.first_spec_table = (int)pl.tab.size();
+        for (int pid = 0; pid < ncoarse; pid++) {
+          if (pl.ph[pid].fine) continue;
+          const PassHost cph = pl.ph[pid];
+          MatchState& s = states[cph.match];
+          PassDev& cpd = pl.pass[pid];
+          const int nA = cph.nA;
+          const double fo = 0.5 * h->prm.coarse_angle_resolution, fr = h->prm.fine_search_angle_resolution;
+          const int h_off = (int)pl.trig.size();
+          pl.trig.resize(pl.trig.size() + (size_t)((nA + 1) & ~1));
+          const int t_off = (int)(pl.trig.size() / 2);
+          pl.trig.resize(pl.trig.size() + (size_t)2 * nA * nAf);
+          const int ht_off = (int)(pl.trig.size() / 2);
+          pl.trig.resize(pl.trig.size() + (size_t)2 * nA * nAf);
+          const double* ctrig = pl.trig.data() + 2 * (size_t)cpd.htrig_off;
+          for (int a = 0; a < nA; a++) {
+            const double heading = atan2(ctrig[2 * a + 1] / 1.0, ctrig[2 * a] / 1.0);
+            pl.trig[h_off + a] = heading;
+            const double start_angle = heading - fo;
+            for (int f = 0; f < nAf; f++) {
+              const double angle = start_angle + (double)(uint32_t)f * fr;
+              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f)] = cos(angle);
+              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f) + 1] = sin(angle);
+              const double hn = h_normalize_angle(angle);
+              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f)] = cos(hn);
+              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f) + 1] = sin(hn);
+            }
+          }
+          const int Ppad = align_up(s.P, 4);
+          TableDev t;
+          t.q_start = b->scan_start[s.q];
+          t.P = s.P; t.Ppad = Ppad; t.nA = nAf;
+          t.trig_off = t_off;  // set by k_reduce to the winner's block
+          t.out_off = (int)pl.off_elems;
+          pl.off_elems += (size_t)nAf * Ppad;
+          t.px = s.pose[0]; t.py = s.pose[1];
+          fill_inverse_rotation(t, s.pose);
+          t.gox = s.gox; t.goy = s.goy;
+          const int tid = (int)pl.tab.size();
+          pl.tab.push_back(t);
+          PassDev fd;
+          memset(&fd, 0, sizeof(fd));
+          fd.slot = s.slot; fd.table = tid; fd.nA = nAf;
+          fd.offx = crx * 0.5; fd.offy = crx * 0.5; fd.resx = h->res_eff; fd.resy = h->res_eff;
+          fd.nX = n_steps(fd.offx, fd.resx); fd.nY = n_steps(fd.offy, fd.resy);
+          fd.P = s.P; fd.Ppad = Ppad; fd.fine = 1; fd.penalize = b->do_penalize ? 1 : 0;
+          fd.sums_off = (int)pl.sums_elems;
+          pl.sums_elems += (size_t)fd.nX * fd.nY * nAf;
+          fd.htrig_off = ht_off;
+          fd.ang_off = pl.ang_elems;
+          pl.ang_elems += nAf;
+          fd.spec = -1;
+          fd.angle_offset = fo; fd.angle_res = fr;
+          fd.gox = s.gox; fd.goy = s.goy;
+          const int fid = (int)pl.pass.size();
+          PassHost fph;
+          fph.match = cph.match; fph.fine = true; fph.spec = true;
+          fph.cx = fph.cy = fph.ch = 0.0;  // known after the coarse pass
+          fph.offx = fd.offx; fph.offy = fd.offy; fph.resx = fd.resx; fph.resy = fd.resy;
+          fph.angle_offset = fo; fph.angle_res = fr;
+          fph.nA = nAf; fph.nX = fd.nX; fph.nY = fd.nY; fph.ang_off = fd.ang_off;
+          pl.pass.push_back(fd);
+          pl.ph.push_back(fph);
+          pl.spec_of.push_back(-1);
+          pl.spec_h.push_back(-1);
+          pl.spec_fine.push_back(fid);
+          pl.spec_of[pid] = fid;
+          pl.spec_h[pid] = h_off;
+          PassDev& c2 = pl.pass[pid];
+          c2.spec = fid; c2.spec_nAf = nAf; c2.spec_h_off = h_off; c2.spec_trig_off = t_off; c2.spec_htrig_off = ht_off;
+          pl.max_fine_poses = std::max(pl.max_fine_poses, fd.nX * fd.nY * nAf);
+        }
+      }
+      return YSM_OK;
+    };
+
+    // ---- staging + upload --------------------------------------------------------------------
+    // wave_static: also carry the pool / scan directory / match descriptors (latency path)
+    BlobLayout L;
+    auto stage_blob = [&](bool wave_static, bool with_passes, PinBuf& hb, DevBuf& db) -> int {
+      size_t o = 0;
+      if (wave_static) {
+        if (small) {
+          if (!b->pool_on_device) { L.pool = o; o = a16(o + (size_t)b->n_points * 16); }
+          L.scan_start = o; o = a16(o + (size_t)b->n_scans * 4);
+          L.scan_count = o; o = a16(o + (size_t)b->n_scans * 4);
+        }
+        L.matches = o; o = a16(o + sizeof(MatchDev) * (size_t)nw);
+        L.base = o; o = a16(o + hbase.size() * 4);
+        L.workcount = o; o = a16(o + 16);
+      }
+      if (with_passes) {
+        L.tab = o; o = a16(o + sizeof(TableDev) * pl.tab.size());
+        L.pass = o; o = a16(o + sizeof(PassDev) * pl.pass.size());
+        L.pa = o; o = a16(o + sizeof(PassAngle) * pl.pa.size());
+        L.fine = o; o = a16(o + sizeof(int) * (pl.fine.size() + pl.spec_fine.size()));
+        L.trig = o; o = a16(o + sizeof(double) * pl.trig.size());
+        L.pmax = o; o = a16(o + sizeof(double) * pl.pass.size());
+      }
+      L.total = std::max<size_t>(o, 16);
+      CK(hb.ensure(L.total));
+      CK(db.ensure(L.total));
+      char* p = (char*)hb.p;
+      if (wave_static) {
+        if (small) {
+          if (!b->pool_on_device && b->n_points > 0) memcpy(p + L.pool, b->pool_xy, (size_t)b->n_points * 16);
+          if (b->n_scans > 0) {
+            memcpy(p + L.scan_start, b->scan_start, (size_t)b->n_scans * 4);
+            memcpy(p + L.scan_count, b->scan_count, (size_t)b->n_scans * 4);
+          }
+        }
+        memcpy(p + L.matches, hm.data(), sizeof(MatchDev) * (size_t)nw);
+        if (!hbase.empty()) memcpy(p + L.base, hbase.data(), hbase.size() * 4);
+        memset(p + L.workcount, 0, 16);
+      }
+      if (with_passes) {
+        memcpy(p + L.tab, pl.tab.data(), sizeof(TableDev) * pl.tab.size());
+        memcpy(p + L.pass, pl.pass.data(), sizeof(PassDev) * pl.pass.size());
+        if (!pl.pa.empty()) memcpy(p + L.pa, pl.pa.data(), sizeof(PassAngle) * pl.pa.size());
+        if (!pl.fine.empty()) memcpy(p + L.fine, pl.fine.data(), sizeof(int) * pl.fine.size());
+        if (!pl.spec_fine.empty())
+          memcpy(p + L.fine + sizeof(int) * pl.fine.size(), pl.spec_fine.data(), sizeof(int) * pl.spec_fine.size());
+        memcpy(p + L.trig, pl.trig.data(), sizeof(double) * pl.trig.size());
+        memset(p + L.pmax, 0, sizeof(double) * pl.pass.size());  // per-pass best response, max-accumulated on the GPU
+      }
+      CK(cudaMemcpyAsync(db.p, hb.p, L.total, cudaMemcpyHostToDevice, st));
+      h->work[6] += (int64_t)L.total;
+      if (wave_static) {
+        const char* d = (const char*)db.p;
+        if (small) {
+          if (!b->pool_on_device) d_pool = (const double*)(d + L.pool);
+          d_scan_start = (const int*)(d + L.scan_start);
+          d_scan_count = (const int*)(d + L.scan_count);
+        }
+        d_matches = (const MatchDev*)(d + L.matches);
+        d_base_idx = (const int*)(d + L.base);
+        d_workcount = (int*)((char*)db.p + L.workcount);
+        h->cur_matches = d_matches;
+        h->cur_workcount = d_workcount;
+      }
+      return YSM_OK;
+    };
+
+    // ---- K1: grid build ------------------------------------------------------------------------
+    auto launch_build = [&]() -> int {
+      if (timing) CK(cudaEventRecord(h->ev[0], st));
+      const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
+      const size_t fixed = 4 * (size_t)nbase_max + bits_bytes;
+      // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
+      int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
+      while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
+      size_t smem = (size_t)nwarps * 4 * pmax + fixed;
+      int stage = 0;
+      if (nw < 2 * h->num_sms) {  // latency mode: stage scan points in shared memory if they fit
+        const size_t with_pts = ((smem + 15) & ~(size_t)15) + (size_t)nwarps * 16 * pmax;
+        if (with_pts <= 200 * 1024) {
+          smem = with_pts;
+          stage = 1;
+        }
+      }
+      if (smem > 220 * 1024) return fail(h, YSM_EUNSUP, "too many base scans / points / tiles for the filter kernel");
+      if (smem > 48 * 1024 && smem > h->find_smem_attr) {
+        CK(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->find_smem_attr = smem;
+      }
+      k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, d_matches, d_base_idx, d_scan_start, d_scan_count, d_pool,
+                                                   (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
+                                                   (int*)h->d_cellcount.p, (uint2*)h->d_gbox.p, (int2*)h->d_work.p,
+                                                   d_workcount, pmax, nbase_max, stage);
+      h->launches++;
+      kt.mark("k_find_valid");
+      if (h->ordered_stamps) {
+        int log2cap = 6;
+        while ((1ll << log2cap) < 2 * max_match_cells) log2cap++;
+        const size_t osmem = (size_t)4 << log2cap;
+        if (osmem > 200 * 1024)
+          return fail(h, YSM_EUNSUP, "too many base points per match for the ordered-stamp filter (wide smear)");
+        if (osmem > 48 * 1024 && osmem > h->order_smem_attr) {
+          CK(cudaFuncSetAttribute(k_stamp_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+          h->order_smem_attr = osmem;
+        }
+        k_stamp_order<<<nw, 32, osmem, st>>>(d_matches, (uint32_t*)h->d_cells.p, (const int*)h->d_cellcount.p, log2cap);
+        h->launches++;
+        kt.mark("k_stamp_order");
+      }
+      const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
+      const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
+      k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p,
+                                                       (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
+                                                       (const int2*)h->d_work.p, d_workcount, h->d_kernel, h->d_grids,
+                                                       h->d_rowmask, h->rm_words);
+      h->launches++;
+      kt.mark("k_tile_stamp");
+      if (timing) CK(cudaEventRecord(h->ev[1], st));
+      CK(cudaGetLastError());
+      return YSM_OK;
+    };
+
+    // ---- pass iterations ------------------------------------------------------------------------
+    int iter = 0;
+    bool built = false;
+    while (true) {
+      const bool spec = speculate && iter == 0;
+      if (!small && !built) {
+        // throughput path: descriptors + build first, so the build overlaps the host's pass planning
+        int rc = stage_blob(true, false, h->h_wblob, h->d_wblob);
+        if (rc != YSM_OK) return rc;
+        rc = launch_build();
+        if (rc != YSM_OK) return rc;
+        built = true;
+      }
+      {
+        const int rc = plan_passes(spec);
+        if (rc != YSM_OK) return rc;
+      }
+      const int npass = (int)pl.pass.size();
       if (npass == 0) break;
-      if (off_elems > 0x7fffff00ull || sums_elems > 0x7fffff00ull)
+      if (pl.off_elems > 0x7fffff00ull || pl.sums_elems > 0x7fffff00ull)
         return fail(h, YSM_ENOMEM, "wave workspace exceeds 2^31 elements; lower max_slots");
+      tr.mark("pass plan (host libm)");
+      const char* db = nullptr;
+      if (!built) {
+        // latency path: ONE copy carries the wave-static data and the first iteration's pass tables
+        int rc = stage_blob(true, true, h->h_wblob, h->d_wblob);
+        if (rc != YSM_OK) return rc;
+        db = (const char*)h->d_wblob.p;
+        rc = launch_build();
+        if (rc != YSM_OK) return rc;
+        built = true;
+      } else {
+        const int rc = stage_blob(false, true, h->h_blob, h->d_blob);
+        if (rc != YSM_OK) return rc;
+        db = (const char*)h->d_blob.p;
+      }
+      const int nhostfine = (int)pl.fine.size(), nspec = (int)pl.spec_fine.size();
+      const int ncoarse_total = npass - nspec;  // passes scheduled by the host (coarse + host fine)
+      h->work[7] += (int64_t)(sizeof(PassOut) * (size_t)npass + (size_t)pl.ang_elems * 4);
+      h->work[2] += (int64_t)pl.off_elems;
+      h->work[3] += (int64_t)pl.sums_elems;
+      TableDev* d_tab = (TableDev*)(db + L.tab);
+      PassDev* d_pass = (PassDev*)(db + L.pass);
+      const PassAngle* d_pa = (const PassAngle*)(db + L.pa);
+      const int* d_fine = (const int*)(db + L.fine);
+      const double* d_trig = (const double*)(db + L.trig);
+      double* d_pmax = (double*)(db + L.pmax);
 
-      // one staging blob: tables | passes | pa_list | fine ids | trig
-      size_t o_tab = 0;
-      size_t o_pass = o_tab + sizeof(TableDev) * htab.size();
-      size_t o_pa = o_pass + sizeof(PassDev) * hpass.size();
-      size_t o_fine = o_pa + sizeof(PassAngle) * hpa.size();
-      size_t o_trig = (o_fine + sizeof(int) * hfine.size() + 15) / 16 * 16;
-      size_t o_pmax = o_trig + sizeof(double) * htrig.size();
-      size_t blob = o_pmax + sizeof(double) * hpass.size();
-      CK(h->h_blob.ensure(blob));
-      CK(h->d_blob.ensure(blob));
-      char* hb = (char*)h->h_blob.p;
-      memcpy(hb + o_tab, htab.data(), sizeof(TableDev) * htab.size());
-      memcpy(hb + o_pass, hpass.data(), sizeof(PassDev) * hpass.size());
-      if (!hpa.empty()) memcpy(hb + o_pa, hpa.data(), sizeof(PassAngle) * hpa.size());
-      if (!hfine.empty()) memcpy(hb + o_fine, hfine.data(), sizeof(int) * hfine.size());
-      memcpy(hb + o_trig, htrig.data(), sizeof(double) * htrig.size());
-      memset(hb + o_pmax, 0, sizeof(double) * hpass.size());  // per-pass best response, max-accumulated on the GPU
-      CK(cudaMemcpyAsync(h->d_blob.p, hb, blob, cudaMemcpyHostToDevice, st));
-      h->work[6] += (int64_t)blob;
-      h->work[7] += (int64_t)(sizeof(PassOut) * (size_t)npass + (size_t)ang_elems * 4);
-      h->work[2] += (int64_t)off_elems;
-      h->work[3] += (int64_t)sums_elems;
-      const char* db = (const char*)h->d_blob.p;
-      const TableDev* d_tab = (const TableDev*)(db + o_tab);
-      const PassDev* d_pass = (const PassDev*)(db + o_pass);
-      const PassAngle* d_pa = (const PassAngle*)(db + o_pa);
-      const int* d_fine = (const int*)(db + o_fine);
-      const double* d_trig = (const double*)(db + o_trig);
-      double* d_pmax = (double*)((char*)h->d_blob.p + o_pmax);
-
-      CK(h->d_offsets.ensure(std::max<size_t>(16, off_elems * 4)));
-      CK(h->d_sums.ensure(std::max<size_t>(16, sums_elems * 8)));  // penalised responses, f64 [iy][ix][a]
+      CK(h->d_offsets.ensure(std::max<size_t>(16, pl.off_elems * 4)));
+      CK(h->d_sums.ensure(std::max<size_t>(16, pl.sums_elems * 8)));  // penalised responses, f64 [iy][ix][a]
       CK(h->d_outs.ensure(sizeof(PassOut) * (size_t)npass));
-      CK(h->d_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
+      CK(h->d_angsums.ensure(std::max<size_t>(16, (size_t)pl.ang_elems * 4)));
       CK(h->h_outs.ensure(sizeof(PassOut) * (size_t)npass));
-      CK(h->h_angsums.ensure(std::max<size_t>(16, (size_t)ang_elems * 4)));
+      CK(h->h_angsums.ensure(std::max<size_t>(16, (size_t)pl.ang_elems * 4)));
+      tr.mark("blob H2D");
 
-      tr.mark("pass prep (host libm) + blob");
-      // ---- K2 offsets ---------------------------------------------------------------------------
+      // ---- K2 offsets (tables of the passes the host scheduled) ------------------------------------
+      const int ntab_host = spec ? pl.first_spec_table : (int)pl.tab.size();
       {
         int maxwork = 1;
-        for (const TableDev& t : htab) maxwork = std::max(maxwork, t.nA * (t.Ppad / 4));
-        dim3 grid((maxwork + 255) / 256, (unsigned)htab.size());
-        k_offsets<<<grid, 256, 0, st>>>(g, d_tab, d_trig, d_pool, (int*)h->d_offsets.p);
+        for (int t = 0; t < ntab_host; t++) maxwork = std::max(maxwork, pl.tab[t].nA * (pl.tab[t].Ppad / 4));
+        dim3 grid((maxwork + 255) / 256, (unsigned)ntab_host);
+        k_offsets<<<grid, 256, 0, st>>>(g, d_tab, d_trig, d_pool, (int*)h->d_offsets.p, 0);
         h->launches++;
         kt.mark("k_offsets");
       }
       // ---- K3 sweeps ----------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[2], st));
-      if (!hpa.empty()) {
-        // one warp per lattice row-task; CTAs of up to 32 warps. Small batches: split the rows
-        // over more CTAs until the machine is full.
-        const int npa = (int)hpa.size();
+      if (!pl.pa.empty()) {
+        const int npa = (int)pl.pa.size();
         const int target = h->num_sms * 2;
-        const int nrg = (max_lat_ny + 27) / 28, rows_per_cta = (max_lat_ny + nrg - 1) / nrg;
-        const int nxc = (max_lat_nx + 31) / 32, cw = (max_lat_nx + nxc - 1) / nxc;
+        const int nrg = (pl.max_lat_ny + 27) / 28, rows_per_cta = (pl.max_lat_ny + nrg - 1) / nrg;
+        const int nxc = (pl.max_lat_nx + 31) / 32, cw = (pl.max_lat_nx + nxc - 1) / nxc;
         const bool pruned = !(h->debug & YSM_DEBUG_NO_PRUNE) && (long long)npa * nrg * nxc >= target;
         if (pruned) {
           // throughput form: zero-row pruning, offsets fused (k_sweep_pruned)
           int PB = (int)((96 * 1024 / 4 / (2 + rows_per_cta)) & ~31);
-          PB = std::max(32, std::min(PB, (max_lat_P + 31) & ~31));
+          PB = std::max(32, std::min(PB, (pl.max_lat_P + 31) & ~31));
           const size_t smem = (size_t)(2 + rows_per_cta) * PB * 4;
           if (smem > 48 * 1024 && smem > h->prune_smem_attr) {
             CK(cudaFuncSetAttribute(k_sweep_pruned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -919,23 +1155,24 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
                                                                timing ? h->d_issued : nullptr);
           h->work[8]++;
         } else {
-          int tpc = std::min(max_lat_tasks, 32);
-          int task_chunks = (max_lat_tasks + tpc - 1) / tpc;
+          // one warp per lattice row-task; small batches: fewer row-tasks per CTA and several warps
+          // per row-task (point slices) until the machine is full
+          int tpc = std::min(pl.max_lat_tasks, 32);
+          int task_chunks = (pl.max_lat_tasks + tpc - 1) / tpc;
           int psplit = 1;
           if (npa * task_chunks < target) {
-            // small batch: fewer row-tasks per CTA, and several warps per row-task (point slices)
             const int want = (target + npa - 1) / npa;            // CTAs wanted per (pass, angle)
-            tpc = std::max(2, std::min(tpc, (max_lat_tasks + want - 1) / want));
-            task_chunks = (max_lat_tasks + tpc - 1) / tpc;
-            psplit = std::max(1, std::min(std::min(8, 32 / tpc), max_lat_P / 64));
+            tpc = std::max(2, std::min(tpc, (pl.max_lat_tasks + want - 1) / want));
+            task_chunks = (pl.max_lat_tasks + tpc - 1) / tpc;
+            psplit = std::max(1, std::min(std::min(8, 32 / tpc), pl.max_lat_P / 64));
             // every CTA must see exactly one task iteration per warp group (barriers inside the loop)
             bool uniform = true;
-            for (const PassHost& q : hph)
-              if (!q.fine && q.nY * ((q.nX + 31) / 32) != max_lat_tasks) uniform = false;
-            if (!uniform || max_lat_tasks % tpc != 0) psplit = 1;
+            for (const PassHost& q : pl.ph)
+              if (!q.fine && q.nY * ((q.nX + 31) / 32) != pl.max_lat_tasks) uniform = false;
+            if (!uniform || pl.max_lat_tasks % tpc != 0) psplit = 1;
           }
           const int threads = 32 * std::min(tpc, 32) * psplit;
-          const size_t smem = (size_t)(((max_lat_P + 7) & ~7) + max_lat_nx + max_lat_ny + (psplit > 1 ? threads : 0)) * 4;
+          const size_t smem = (size_t)(((pl.max_lat_P + 7) & ~7) + pl.max_lat_nx + pl.max_lat_ny + (psplit > 1 ? threads : 0)) * 4;
           if (smem > 200 * 1024) return fail(h, YSM_EUNSUP, "search lattice too large for the sweep kernel");
           if (smem > 48 * 1024 && smem > h->sweep_smem_attr) {
             CK(cudaFuncSetAttribute(k_sweep_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -950,8 +1187,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
         kt.mark("k_sweep_lattice");
       }
       if (timing) CK(cudaEventRecord(h->ev[3], st));
-      if (!hfine.empty()) {
-        dim3 grid((max_fine_poses + 7) / 8, (unsigned)hfine.size());
+      if (nhostfine > 0) {
+        dim3 grid((pl.max_fine_poses + 7) / 8, (unsigned)nhostfine);
         k_sweep_points<<<grid, 256, 0, st>>>(g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
                                              (double*)h->d_sums.p, d_pmax);
         h->launches++;
@@ -959,14 +1196,30 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       }
       // ---- K3b/K4 reduce ------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[4], st));
-      k_reduce<<<npass, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
-                                      d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p);
+      k_reduce<<<ncoarse_total, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
+                                             d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, 0);
       h->launches++;
       kt.mark("k_reduce");
+      if (nspec > 0) {
+        // speculative fine passes: their centre / angle tables were selected by the reduce above
+        int maxwork = 1;
+        for (size_t t = (size_t)pl.first_spec_table; t < pl.tab.size(); t++)
+          maxwork = std::max(maxwork, pl.tab[t].nA * (pl.tab[t].Ppad / 4));
+        dim3 og((maxwork + 255) / 256, (unsigned)(pl.tab.size() - (size_t)pl.first_spec_table));
+        k_offsets<<<og, 256, 0, st>>>(g, d_tab, d_trig, d_pool, (int*)h->d_offsets.p, pl.first_spec_table);
+        dim3 sg((pl.max_fine_poses + 7) / 8, (unsigned)nspec);
+        k_sweep_points<<<sg, 256, 0, st>>>(g, h->pen, d_pass, d_fine + nhostfine, d_tab, (const int*)h->d_offsets.p,
+                                           h->d_grids, (double*)h->d_sums.p, d_pmax);
+        k_reduce<<<nspec, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
+                                       d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p,
+                                       ncoarse_total);
+        h->launches += 3;
+        kt.mark("speculative fine");
+      }
       if (timing) CK(cudaEventRecord(h->ev[5], st));
       CK(cudaMemcpyAsync(h->h_outs.p, h->d_outs.p, sizeof(PassOut) * (size_t)npass, cudaMemcpyDeviceToHost, st));
-      if (ang_elems > 0)
-        CK(cudaMemcpyAsync(h->h_angsums.p, h->d_angsums.p, (size_t)ang_elems * 4, cudaMemcpyDeviceToHost, st));
+      if (pl.ang_elems > 0)
+        CK(cudaMemcpyAsync(h->h_angsums.p, h->d_angsums.p, (size_t)pl.ang_elems * 4, cudaMemcpyDeviceToHost, st));
       tr.mark("pass launches");
       kt.mark("d2h");
       CK(cudaStreamSynchronize(st));
@@ -978,7 +1231,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
           cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
           h->t_build += ms;
         }
-        if (!hpa.empty()) {
+        if (!pl.pa.empty()) {
           cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
           h->t_sweep += ms;
         }
@@ -989,8 +1242,8 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       // ---- host: finish every pass exactly as CorrelateScan / MatchScan do ----------------------
       const PassOut* outs = (const PassOut*)h->h_outs.p;
       const int* angs = (const int*)h->h_angsums.p;
-      for (int pid = 0; pid < npass; pid++) {
-        const PassHost& ph = hph[pid];
+      for (int pid = 0; pid < ncoarse_total; pid++) {
+        const PassHost& ph = pl.ph[pid];
         const PassOut& po = outs[pid];
         MatchState& s = states[ph.match];
         s.n_passes++;
@@ -1025,6 +1278,27 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
           } else {
             s.stage = b->do_refine ? 4 : 5;
           }
+          // the fine pass already ran on the device behind this coarse pass?
+          const int fid = pl.spec_of[pid];
+          if (fid >= 0 && s.stage == 4 && outs[fid].n_ties > 0) {
+            const PassOut& fo = outs[fid];
+            PassHost fph = pl.ph[fid];
+            // the centre k_reduce gave the fine pass: the coarse mean (single winner)
+            const int a = po.first_idx % ph.nA;
+            fph.cx = po.avg_x; fph.cy = po.avg_y; fph.ch = pl.trig[(size_t)pl.spec_h[pid] + a];
+            if (po.n_ties == 1 && dbits(fph.ch) == dbits(heading)) {
+              s.n_passes++;
+              s.n_ties = fo.n_ties;
+              const double fheading = atan2(fo.ty, fo.tx);
+              finalize_angular(fph, fo, fheading, angs + fph.ang_off, s.P, s.cov);
+              s.mean[0] = fo.avg_x; s.mean[1] = fo.avg_y; s.mean[2] = fheading;
+              double fbest = fo.best;
+              if (fbest > 1.0) fbest = 1.0;
+              s.best = fbest;
+              s.stage = 5;
+              h->work[10]++;
+            }
+          }
         }
       }
       iter++;
@@ -1045,17 +1319,12 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
       r._pad = 0;
       r._reserved = 0.0;
     }
-    if (h->debug & YSM_DEBUG_KEEP_GRIDS) {
-      h->grids_dirty = true;
-      h->dirty_matches = hm;
-      if (w1 < b->n_matches) {
-        // more waves follow: the slots are needed again
-        clear_wave(h, (const MatchDev*)h->d_matches.p, nw, st);
-        h->grids_dirty = false;
-        h->dirty_matches.clear();
+    if (built) {
+      if ((h->debug & YSM_DEBUG_KEEP_GRIDS) && w1 >= b->n_matches) {
+        h->grids_dirty = true;  // cleared at the start of the next call (the work list stays resident)
+      } else {
+        clear_wave(h, d_matches, st);
       }
-    } else {
-      clear_wave(h, (const MatchDev*)h->d_matches.p, nw, st);
     }
     CK(cudaGetLastError());
   }
@@ -1069,9 +1338,6 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     CK(cudaMemcpy(&iss, h->d_issued, 8, cudaMemcpyDeviceToHost));
     h->work[9] = (int64_t)iss;
   }
-  // the clear kernel must not race with a caller that frees / reuses `pool_xy` on the device
-  // or with the next call's staging: d_matches/d_cells are reused by the next wave, which is
-  // ordered behind the clear on the same stream.
   for (int i = 0; i < b->n_matches; i++)
     if (out[i].status != YSM_OK) return fail(h, YSM_EMATCH, "Mapper FATAL ERROR - Unable to find best position");
   return YSM_OK;

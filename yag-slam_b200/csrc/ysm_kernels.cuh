@@ -60,6 +60,10 @@ struct PassDev {
   int sums_off;   // u32 element offset into the sums buffer, layout [iy][ix][a]
   int htrig_off;  // cos/sin of NormalizeAngle(angle_a), for the tie average
   int ang_off;    // int element offset into the angular-covariance sums buffer
+  // speculative fine pass of a coarse pass (latency path): pass id (-1: none) and where, in the
+  // trig array, the host left the per-winning-angle data: heading table [nA] (double index),
+  // cos/sin blocks [nA][nAf] of the fine search angles and of their normalised headings (pair index)
+  int spec, spec_nAf, spec_h_off, spec_trig_off, spec_htrig_off, pad1;
   double cx, cy, ch;              // search centre
   double offx, offy, resx, resy;  // search space offset / resolution
   double angle_offset, angle_res;
@@ -72,8 +76,8 @@ struct PassOut {
   double avg_x, avg_y;  // tie-averaged position
   double tx, ty;        // mean cos / mean sin of the tied headings
   double norm, axx, axy, ayy;  // ComputePositionalCovariance accumulators
-  int n_ties;
-  int pad;
+  int n_ties;     // -1: speculative pass that was not run
+  int first_idx;  // storage index (iy, ix, a) of the first tied pose
 };
 
 __device__ __forceinline__ double kt_round(double v) { return v >= 0.0 ? floor(v + 0.5) : ceil(v - 0.5); }
@@ -266,6 +270,69 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1a'  AddScan's "cell already occupied -> skip" rule for wide smears. When
+// smear_deviation >= ~9.99 * resolution the stamp is 100 not only at its centre but also at its
+// four edge neighbours, so a point whose cell an EARLIER point (or its neighbour) already set to
+// 100 is skipped by Karto and never smeared: which stamps exist depends on the processing order.
+// One warp per match replays that order over the compacted cell list: 32 cells per step, a
+// shared-memory hash set of the stamped cells for the earlier steps, an in-order resolution
+// inside the step. Skipped cells are overwritten with YSM_INVALID_CELL (k_tile_stamp ignores them).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hash_has(const uint32_t* __restrict__ tab, uint32_t mask, int shift, uint32_t key) {
+  uint32_t hsh = (key * 2654435761u) >> shift;
+  while (true) {
+    const uint32_t v = tab[hsh];
+    if (v == key) return true;
+    if (v == YSM_INVALID_CELL) return false;
+    hsh = (hsh + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells,
+              const int* __restrict__ cell_count, int log2cap) {
+  extern __shared__ uint32_t s_tab[];
+  const MatchDev m = matches[blockIdx.x];
+  const int n = cell_count[blockIdx.x];
+  const int lane = threadIdx.x;
+  const uint32_t cap = 1u << log2cap, mask = cap - 1u;
+  const int shift = 32 - log2cap;
+  for (uint32_t i = lane; i < cap; i += 32) s_tab[i] = YSM_INVALID_CELL;
+  __syncwarp();
+  uint32_t* mc = cells + m.cells_off;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < n;
+    const uint32_t c = valid ? mc[i] : YSM_INVALID_CELL;
+    const int x = (int)(c & 0xFFFFu), y = (int)(c >> 16);
+    // already 100 because of a point stamped in an earlier step? (its cell or a 4-neighbour)
+    bool blocked = !valid;
+    if (valid) {
+      blocked = hash_has(s_tab, mask, shift, c) || hash_has(s_tab, mask, shift, c - 1u) ||
+                hash_has(s_tab, mask, shift, c + 1u) || hash_has(s_tab, mask, shift, c - 0x10000u) ||
+                hash_has(s_tab, mask, shift, c + 0x10000u);
+    }
+    // in-order resolution inside the step
+    bool stamped = false;
+    for (int k = 0; k < 32; k++) {
+      const bool mine = !__shfl_sync(0xffffffffu, (int)blocked, k);  // lane k stamps iff nothing earlier blocked it
+      if (!mine) continue;                                            // warp-uniform
+      const uint32_t ck = __shfl_sync(0xffffffffu, c, k);
+      if (lane == k) stamped = true;
+      const int dx = x - (int)(ck & 0xFFFFu), dy = y - (int)(ck >> 16);
+      if (lane > k && (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) <= 1) blocked = true;
+    }
+    if (valid && !stamped) mc[i] = YSM_INVALID_CELL;
+    // insert this step's stamped cells (distinct by construction)
+    if (stamped) {
+      uint32_t hsh = (c * 2654435761u) >> shift;
+      while (atomicCAS(&s_tab[hsh], YSM_INVALID_CELL, c) != YSM_INVALID_CELL) hsh = (hsh + 1) & mask;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
 // yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so each touched
 // 32 x 32 tile of the grid is OWNED by one warp: it keeps the tile in a private 1 KB block of
@@ -453,8 +520,8 @@ __device__ __forceinline__ void offset_cell(const TableDev& t, double scale, dou
 
 __global__ void __launch_bounds__(256)
 k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict__ trig,
-          const double* __restrict__ pool, int* __restrict__ offsets) {
-  const TableDev t = tables[blockIdx.y];
+          const double* __restrict__ pool, int* __restrict__ offsets, int table_base) {
+  const TableDev t = tables[table_base + blockIdx.y];
   const int p4n = t.Ppad >> 2;
   const int work = t.nA * p4n;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < work; it += gridDim.x * blockDim.x) {
@@ -692,7 +759,7 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
 // CTA = (pass, angle) x (group of <= 28 lattice rows, chunk of <= 32 lattice columns).
 // Windows that could leave the grid (or wrap a row) disable pruning for that batch of points and
 // take Karto's flat bounds check instead.
-// smem: s_flat[PB] | s_mask[PB] | lists[nrows][PB]   (PB = points per batch, host-chosen)
+// smem: s_pm[PB] {offset, row mask} of the surviving points | lists[nrows][PB]   (PB = points per batch)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t even_bits64(unsigned long long x) {
   x &= 0x5555555555555555ull;
@@ -704,19 +771,32 @@ __device__ __forceinline__ uint32_t even_bits64(unsigned long long x) {
   return (uint32_t)x;
 }
 
-// unchecked: entries are offsets biased by data_size (non-negative), gp already holds -data_size
+// unchecked: entries are offsets biased by data_size (non-negative), gp already holds -data_size.
+// k32: the caller has checked that the low 32 bits of gp cannot carry when an entry is added, so
+// every address is one 32-bit add (the high word is shared).
+template <bool k32>
+__device__ __forceinline__ const uint8_t* sweep_addr(const uint8_t* gp, unsigned lo, unsigned hi, unsigned o) {
+  if (k32) return reinterpret_cast<const uint8_t*>(((unsigned long long)hi << 32) | (unsigned long long)(lo + o));
+  return gp + o;
+}
+
+template <bool k32>
 __device__ __forceinline__ unsigned sweep_list(const uint8_t* __restrict__ gp, const unsigned* __restrict__ s_e, int n) {
   unsigned sum0 = 0, sum1 = 0;
+  const unsigned lo = (unsigned)reinterpret_cast<unsigned long long>(gp);
+  const unsigned hi = (unsigned)(reinterpret_cast<unsigned long long>(gp) >> 32);
   int p = 0;
   for (; p + 8 <= n; p += 8) {
     const uint4 o0 = *reinterpret_cast<const uint4*>(s_e + p);
     const uint4 o1 = *reinterpret_cast<const uint4*>(s_e + p + 4);
-    const unsigned v0 = __ldg(gp + o0.x), v1 = __ldg(gp + o0.y), v2 = __ldg(gp + o0.z), v3 = __ldg(gp + o0.w);
-    const unsigned v4 = __ldg(gp + o1.x), v5 = __ldg(gp + o1.y), v6 = __ldg(gp + o1.z), v7 = __ldg(gp + o1.w);
+    const unsigned v0 = __ldg(sweep_addr<k32>(gp, lo, hi, o0.x)), v1 = __ldg(sweep_addr<k32>(gp, lo, hi, o0.y));
+    const unsigned v2 = __ldg(sweep_addr<k32>(gp, lo, hi, o0.z)), v3 = __ldg(sweep_addr<k32>(gp, lo, hi, o0.w));
+    const unsigned v4 = __ldg(sweep_addr<k32>(gp, lo, hi, o1.x)), v5 = __ldg(sweep_addr<k32>(gp, lo, hi, o1.y));
+    const unsigned v6 = __ldg(sweep_addr<k32>(gp, lo, hi, o1.z)), v7 = __ldg(sweep_addr<k32>(gp, lo, hi, o1.w));
     sum0 += v0 + v1 + v2 + v3;
     sum1 += v4 + v5 + v6 + v7;
   }
-  for (; p < n; p++) sum0 += (unsigned)__ldg(gp + s_e[p]);
+  for (; p < n; p++) sum0 += (unsigned)__ldg(sweep_addr<k32>(gp, lo, hi, s_e[p]));
   return sum0 + sum1;
 }
 
@@ -742,6 +822,7 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   __shared__ double s_wmax[32];
   __shared__ int s_col[32], s_row[32];
   __shared__ unsigned s_issued;
+  __shared__ int s_nsurv;
   if (threadIdx.x == 0) s_issued = 0u;
   const PassAngle pa = pa_list[blockIdx.x];
   const PassDev ps = passes[pa.pass];
@@ -751,8 +832,7 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   if (iy0 >= ps.nY || ix0 >= ps.nX) return;
   const int nr = min(rows_per_cta, ps.nY - iy0), nxl = min(cw, ps.nX - ix0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  int* s_flat = reinterpret_cast<int*>(s_u);
-  uint32_t* s_mask = s_u + PB;
+  uint2* s_pm = reinterpret_cast<uint2*>(s_u);
   uint32_t* s_list = s_u + 2 * PB + (size_t)warp * PB;  // warp-private
   const TableDev tb = tables[ps.table];
   const double cosine = trig[2 * (tb.trig_off + pa.a)], sine = trig[2 * (tb.trig_off + pa.a) + 1];
@@ -787,56 +867,75 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const int base = s_row[row_warp ? warp : 0] * g.stride + s_col[active ? lane : 0];
   unsigned sum = 0;
 
+  // can every lane's address be formed with a 32-bit add? (low word of gp + largest entry must not carry)
+  const uint8_t* gp = grid + (base - (long long)dsz);
+  const bool lo32 = __all_sync(0xffffffffu, (reinterpret_cast<unsigned long long>(gp) & 0xFFFFFFFFull) + 2ull * dsz <
+                                               0x100000000ull);
   for (int pb = 0; pb < ps.P; pb += PB) {
     const int nb = min(PB, ps.P - pb);
-    if (pb) __syncthreads();  // the previous batch's s_flat / s_mask are still being read
-    // ---- A: offsets + per-point row masks ----------------------------------------------------
+    __syncthreads();  // the previous batch's s_pm is still being read; s_nsurv reset below
+    if (threadIdx.x == 0) s_nsurv = 0;
+    __syncthreads();
+    // ---- A: offsets + per-point row masks; points that can see a non-zero cell survive ----------
     int ok = 1;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-      const double2 w = *reinterpret_cast<const double2*>(qpts + 2 * (size_t)(pb + i));
-      int gx, gy;
-      offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
-      s_flat[i] = gx + gy * g.stride;
-      const int xa = xa0 + gx, ya = ya0 + gy;
-      uint32_t mask = rows_all;
-      if (regular && xa >= 0 && ya >= 0 && xa + xspan < g.width && ya + yspan < g.height) {
-        const int txa = xa >> 5, txb = (xa + xspan) >> 5, tya = ya >> 5, tyb = (ya + yspan) >> 5;
-        uint32_t m[3] = {0u, 0u, 0u};
+    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      uint32_t mask = 0u;
+      int flat = 0;
+      if (i < nb) {
+        const double2 w = *reinterpret_cast<const double2*>(qpts + 2 * (size_t)(pb + i));
+        int gx, gy;
+        offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
+        flat = gx + gy * g.stride;
+        const int xa = xa0 + gx, ya = ya0 + gy;
+        mask = rows_all;
+        if (regular && xa >= 0 && ya >= 0 && xa + xspan < g.width && ya + yspan < g.height) {
+          const int txa = xa >> 5, txb = (xa + xspan) >> 5, tya = ya >> 5, tyb = (ya + yspan) >> 5;
+          uint32_t m[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          if (tya + j <= tyb) {
-            const uint32_t* r = rm + (size_t)(tya + j) * tnx;
-            uint32_t v = __ldg(r + txa);
-            if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
-            if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
-            m[j] = v;
+          for (int j = 0; j < 3; j++) {
+            if (tya + j <= tyb) {
+              const uint32_t* r = rm + (size_t)(tya + j) * tnx;
+              uint32_t v = __ldg(r + txa);
+              if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
+              if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
+              m[j] = v;
+            }
           }
+          const int sft = ya & 31;
+          const unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
+          const unsigned long long S = sft ? ((lo >> sft) | ((unsigned long long)m[2] << (64 - sft))) : lo;
+          mask = (sy == 2 ? even_bits64(S) : (uint32_t)S) & rows_all;
+        } else {
+          ok = 0;  // window may leave the grid: all rows, and Karto's flat bounds check for this batch
         }
-        const int sft = ya & 31;
-        const unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
-        const unsigned long long S = sft ? ((lo >> sft) | ((unsigned long long)m[2] << (64 - sft))) : lo;
-        mask = (sy == 2 ? even_bits64(S) : (uint32_t)S) & rows_all;
-      } else {
-        ok = 0;
       }
-      s_mask[i] = mask;
+      const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
+      int wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (mask) s_pm[wbase + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)flat, mask);
     }
     const int safe = __syncthreads_and(ok);
+    const int nsurv = s_nsurv;
     // ---- B: this warp's list, C: its sums ------------------------------------------------------
     if (row_warp) {
       int cnt = 0;
       const unsigned bias = safe ? dsz : 0u;
-      for (int i0 = 0; i0 < nb; i0 += 32) {
+      for (int i0 = 0; i0 < nsurv; i0 += 32) {
         const int i = i0 + lane;
-        const bool take = i < nb && (!safe || ((s_mask[i] >> warp) & 1u));
+        uint2 pm = make_uint2(0u, 0u);
+        if (i < nsurv) pm = s_pm[i];
+        const bool take = (pm.y >> warp) & 1u;
         const unsigned bal = __ballot_sync(0xffffffffu, take);
-        if (take) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned)s_flat[i] + bias;
+        if (take) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = pm.x + bias;
         cnt += __popc(bal);
       }
       __syncwarp();
       if (issued && lane == 0) atomicAdd(&s_issued, (unsigned)(cnt * nxl));
-      if (safe) sum += sweep_list(grid + (base - (long long)dsz), s_list, cnt);
-      else sum += sweep_list_checked(grid, base, s_list, cnt, dsz);
+      if (!safe) sum += sweep_list_checked(grid, base, s_list, cnt, dsz);
+      else if (lo32) sum += sweep_list<true>(gp, s_list, cnt);
+      else sum += sweep_list<false>(gp, s_list, cnt);
       __syncwarp();
     }
   }
@@ -937,26 +1036,36 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
 }
 
 __global__ void __launch_bounds__(512)
-k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict__ tables,
+k_reduce(GridC g, PassDev* passes, TableDev* tables,
          const int* __restrict__ offsets, const double* __restrict__ resp,
          const double* __restrict__ passmax, const double* __restrict__ trig,
-         const uint8_t* __restrict__ grids, PassOut* __restrict__ outs, int* __restrict__ angsums) {
+         const uint8_t* __restrict__ grids, PassOut* __restrict__ outs, int* __restrict__ angsums, int pass_base) {
   __shared__ double s_tmp[16];
   __shared__ int s_list[YSM_TIE_CAP];
   __shared__ int s_sorted[YSM_TIE_CAP];
   __shared__ int s_count;
   __shared__ unsigned s_bits[16];
   __shared__ double s_acc[4];
-  __shared__ int s_n;
+  __shared__ int s_n, s_first;
 
-  const PassDev ps = passes[blockIdx.x];
+  const int pid = pass_base + blockIdx.x;
+  const PassDev ps = passes[pid];
   const double* pr = resp + ps.sums_off;
   const int nposes = ps.nX * ps.nY * ps.nA;
   const int tid = threadIdx.x;
+  PassOut* po = outs + pid;
+  if (nposes == 0) {  // speculative fine pass whose coarse pass did not end in a single winner
+    if (tid == 0) {
+      po->best = 0.0; po->avg_x = 0.0; po->avg_y = 0.0; po->tx = 0.0; po->ty = 0.0;
+      po->norm = 0.0; po->axx = 0.0; po->axy = 0.0; po->ayy = 0.0;
+      po->n_ties = -1; po->first_idx = -1;
+    }
+    return;
+  }
   if (tid == 0) s_count = 0;
   // best response: accumulated by the sweep kernels (max over all poses; Karto's init of -1
   // never survives because every pass has at least one pose and responses are >= 0)
-  const double best = passmax[blockIdx.x];
+  const double best = passmax[pid];
   __syncthreads();
 
   // poses tied with the best, in storage order (loads batched 4 deep to overlap L2 latency)
@@ -1001,12 +1110,13 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
       }
       s_acc[0] = sx; s_acc[1] = sy; s_acc[2] = tx; s_acc[3] = ty;
       s_n = nt;
+      s_first = nt > 0 ? s_sorted[0] : -1;
     }
   } else {
     // degenerate case (e.g. best == 0: every pose ties): ordered chunks of blockDim poses,
     // one thread accumulates sequentially so the rounding matches the CPU loop
     double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
-    int n = 0;
+    int n = 0, first = -1;
     for (int c0 = 0; c0 < nposes; c0 += blockDim.x) {
       const int i = c0 + tid;
       bool tie = false;
@@ -1028,6 +1138,7 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
             sy += ps.cy + (startY + (double)iy * ps.resy);
             tx += htrig[2 * a];
             ty += htrig[2 * a + 1];
+            if (n == 0) first = idx;
             n++;
           }
         }
@@ -1037,6 +1148,7 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
     if (tid == 0) {
       s_acc[0] = sx; s_acc[1] = sy; s_acc[2] = tx; s_acc[3] = ty;
       s_n = n;
+      s_first = first;
     }
   }
   __syncthreads();
@@ -1044,7 +1156,6 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
   const double cnt = (double)n;
   const double avg_x = n > 0 ? s_acc[0] / cnt : 0.0;
   const double avg_y = n > 0 ? s_acc[1] / cnt : 0.0;
-  PassOut* po = outs + blockIdx.x;
   if (tid == 0) {
     po->best = best;
     po->avg_x = avg_x;
@@ -1052,7 +1163,26 @@ k_reduce(GridC g, const PassDev* __restrict__ passes, const TableDev* __restrict
     po->tx = n > 0 ? s_acc[2] / cnt : 0.0;
     po->ty = n > 0 ? s_acc[3] / cnt : 0.0;
     po->n_ties = n;
-    po->pad = 0;
+    po->first_idx = s_first;
+    if (ps.spec >= 0) {
+      // latency path: point the speculative fine pass at this pass's winner. Valid only for a
+      // single winning pose with a non-zero response (then MatchScan goes straight to the fine
+      // pass, its centre is that lattice pose and the heading atan2(sin, cos) the host tabulated);
+      // otherwise the host reschedules the match through the general path.
+      PassDev* f = passes + ps.spec;
+      TableDev* ft = tables + f->table;
+      if (n == 1 && best > YSM_KT_TOLERANCE) {
+        const int a = s_first % ps.nA;
+        f->cx = avg_x;
+        f->cy = avg_y;
+        f->ch = trig[ps.spec_h_off + a];
+        f->htrig_off = ps.spec_htrig_off + a * ps.spec_nAf;
+        ft->trig_off = ps.spec_trig_off + a * ps.spec_nAf;
+      } else {
+        f->nA = 0;
+        ft->nA = 0;
+      }
+    }
   }
   if (!ps.fine) {
     // ComputePositionalCovariance accumulators over the (y, x) lattice; probs(x, y) is the

@@ -80,7 +80,8 @@ class ScanMatcherB200(object):
         v = (C.c_int64 * 16)()
         self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
-                         "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued"),
+                         "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
+                         "speculative_fine_passes"),
                         (int(x) for x in v)))
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
