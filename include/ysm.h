@@ -48,6 +48,9 @@ typedef struct ysm_params {
   int32_t use_response_expansion;
   int32_t max_slots;       /* correlation grids kept resident in HBM at once; 0 = auto */
   int64_t max_grid_bytes;  /* HBM budget for those grids; 0 = 16 GiB */
+  int32_t lanes;           /* 0/1: single; 2..4: large batches are split over that many internal matcher
+                              instances (own slots, stream, host thread) so host work overlaps kernels */
+  int32_t _pad;
 } ysm_params;
 
 /* Derived sizes (ScanMatcher::Create / CorrelationGrid::CreateGrid). */
@@ -146,7 +149,8 @@ int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, 
  * out[4] grid lookups of the fine / angular-covariance passes, out[5] base points stamped (upper bound),
  * out[6] host->device bytes, out[7] device->host bytes, out[8] sweep launches that used zero-row pruning,
  * out[9] lattice lookups actually issued after pruning (counted only with YSM_DEBUG_TIME_KERNELS),
- * out[10] fine passes that ran chained on the device behind their coarse pass (latency path);
+ * out[10] fine passes that ran chained on the device behind their coarse pass (latency path),
+ * out[11] lanes used by the call;
  * fills out[0..n), n <= 16 */
 int ysm_last_work(const ysm_handle *h, int64_t *out, int32_t n);
 

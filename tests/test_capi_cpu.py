@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_capi.YsmParams) == 11 * 8 + 4 + 4 + 8
+    assert C.sizeof(_capi.YsmParams) == 11 * 8 + 4 + 4 + 8 + 4 + 4
     assert C.sizeof(_capi.YsmDims) == 10 * 4 + 8
     assert C.sizeof(_capi.YsmBatch) == 4 + 4 + 8 + 7 * 8 + 4 * 4
     assert _capi.RESULT_DTYPE.itemsize == 128

@@ -196,6 +196,29 @@ def test_latency_path_device_chained_fine_pass(world):
     m.close()
 
 
+def test_lanes_split_large_batches(world):
+    """Large batches are split over internal lanes (own slots / stream / host thread); results are
+    those of the single-lane path and of the oracle, with a host pool and with a device pool."""
+    import torch
+    import scenarios
+    b = scenarios.make_batch(world, 300, 360, 3, 61, perturb=(0.1, 0.05), degenerate_frac=0.05)
+    ref = scenarios.oracle_results(None, b, True, True)
+    m1 = _matcher(None, max_slots=128, lanes=1)
+    a = _run(m1, b, True, True).copy()
+    assert m1.last_work()["lanes"] == 0
+    m1.close()
+    m3 = _matcher(None, max_slots=192, lanes=3)
+    c = _run(m3, b, True, True).copy()
+    assert m3.last_work()["lanes"] == 3 and m3.dims()["slots"] == 192
+    dpool = torch.from_numpy(b["pool"]).cuda()
+    d = m3.match_pool(dpool, b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"], b["base_idx"],
+                      True, True).copy()
+    m3.close()
+    _assert_parity(a, ref, "one lane")
+    _assert_parity(c, ref, "three lanes")
+    assert a.tobytes() == c.tobytes() == d.tobytes()
+
+
 def test_shared_query_and_multiwave(world):
     import scenarios
     b = scenarios.make_batch(world, 32, 720, 10, 5, perturb=(1.0, 0.2), shared_query=True)

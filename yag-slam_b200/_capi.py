@@ -20,7 +20,8 @@ DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS, DEBUG_NO_PRUNE, DEBUG_NO_SPECULATE = 1, 2,
 
 class YsmParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in PARAM_FIELDS] + [
-        ("use_response_expansion", C.c_int32), ("max_slots", C.c_int32), ("max_grid_bytes", C.c_int64)]
+        ("use_response_expansion", C.c_int32), ("max_slots", C.c_int32), ("max_grid_bytes", C.c_int64),
+        ("lanes", C.c_int32), ("_pad", C.c_int32)]
 
 
 class YsmDims(C.Structure):

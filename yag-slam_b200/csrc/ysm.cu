@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -267,6 +268,13 @@ struct ysm_handle {
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
   size_t sweep_smem_attr = 0, find_smem_attr = 0, prune_smem_attr = 0;
+  // lanes: extra matcher instances (own grid slots, workspaces and stream) that take contiguous
+  // shares of a large batch on their own host threads, so one lane's host-side pass planning and
+  // result handling overlap the other lanes' kernels
+  std::vector<ysm_handle*> lanes;
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t lane_event = nullptr;
+  DevBuf d_pool_shared;
   bool ordered_stamps = false;  // wide smear: AddScan's skip rule is order dependent
   size_t order_smem_attr = 0;
   int64_t work[16] = {0};
@@ -310,7 +318,7 @@ static int calculate_kernel(double res_eff, double smear, std::vector<uint8_t>& 
   return 0;
 }
 
-extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
+static int create_one(const ysm_params* p, int device, ysm_handle** out) {
   if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
   *out = nullptr;
   if (!(p->resolution > 0) || !(p->search_size > 0) || p->smear_deviation < 0 || !(p->range_threshold > 0))
@@ -424,10 +432,53 @@ extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
   return YSM_OK;
 }
 
+extern "C" void ysm_destroy(ysm_handle* h);
+
+extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
+  if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
+  *out = nullptr;
+  int lanes = std::max(1, std::min(4, (int)p->lanes));
+  if (p->max_slots > 0 && p->max_slots < 64 * lanes) lanes = 1;  // small handles (tests, latency use) stay single
+  ysm_params q = *p;
+  if (lanes > 1) {
+    q.max_grid_bytes = (p->max_grid_bytes > 0 ? p->max_grid_bytes : (16LL << 30)) / lanes;
+    if (p->max_slots > 0) q.max_slots = p->max_slots / lanes;
+  }
+  ysm_handle* h = nullptr;
+  int rc = create_one(&q, device, &h);
+  if (rc != YSM_OK) return rc;
+  for (int l = 1; l < lanes; l++) {
+    ysm_handle* sub = nullptr;
+    rc = create_one(&q, device, &sub);
+    if (rc != YSM_OK) {
+      ysm_destroy(h);
+      return rc;
+    }
+    h->lanes.push_back(sub);
+  }
+  if (lanes > 1) {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->lane_event, cudaEventDisableTiming);
+    for (ysm_handle* sub : h->lanes)
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sub->lane_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      ysm_destroy(h);
+      return fail(nullptr, YSM_ECUDA, std::string("lane stream creation failed: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = h;
+  return YSM_OK;
+}
+
 extern "C" void ysm_destroy(ysm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  for (ysm_handle* sub : h->lanes) ysm_destroy(sub);
+  h->lanes.clear();
+  if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
+  if (h->lane_event) cudaEventDestroy(h->lane_event);
+  h->d_pool_shared.release();
   if (h->d_grids) cudaFree(h->d_grids);
   if (h->d_rowmask) cudaFree(h->d_rowmask);
   if (h->d_issued) cudaFree(h->d_issued);
@@ -453,16 +504,23 @@ extern "C" int ysm_get_dims(const ysm_handle* h, ysm_dims* out) {
   out->half_kernel = h->g.half_kernel; out->kernel_size = h->g.K; out->border = h->g.border;
   out->width = h->g.width; out->height = h->g.height; out->stride = h->g.stride;
   out->slots = h->slots; out->grid_bytes = h->g.data_size;
+  for (const ysm_handle* sub : h->lanes) out->slots += sub->slots;
   return YSM_OK;
 }
 
 extern "C" int ysm_set_debug(ysm_handle* h, int32_t flags) {
   if (!h) return YSM_EINVAL;
   h->debug = flags;
+  for (ysm_handle* sub : h->lanes) sub->debug = flags;
   return YSM_OK;
 }
 
-extern "C" int64_t ysm_launch_count(const ysm_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t ysm_launch_count(const ysm_handle* h) {
+  if (!h) return 0;
+  int64_t n = h->launches;
+  for (const ysm_handle* sub : h->lanes) n += sub->launches;
+  return n;
+}
 
 extern "C" int ysm_last_work(const ysm_handle* h, int64_t* out, int32_t n) {
   if (!h || !out || n < 0) return YSM_EINVAL;
@@ -581,10 +639,9 @@ static void fill_inverse_rotation(TableDev& t, const double* pose) {
 }
 
 // --------------------------------------------------------------------------------------------
-extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
+static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, cudaStream_t st) {
   if (!h || !b || !out) return YSM_EINVAL;
   if (b->n_matches < 0 || b->n_scans < 0) return fail(h, YSM_EINVAL, "negative sizes");
-  cudaStream_t st = (cudaStream_t)stream;
   PhaseTrace tr;
   KernelTrace kt;
   kt.init(getenv("YSM_TRACE_GPU") != nullptr, st);
@@ -1340,6 +1397,67 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   }
   for (int i = 0; i < b->n_matches; i++)
     if (out[i].status != YSM_OK) return fail(h, YSM_EMATCH, "Mapper FATAL ERROR - Unable to find best position");
+  return YSM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
+  if (!h || !b || !out) return YSM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nl = 1 + (int)h->lanes.size();
+  // (kernel timing / grid introspection are per-stream: those debug modes stay on the main lane)
+  if (nl == 1 || b->n_matches < 64 * nl || (h->debug & (YSM_DEBUG_KEEP_GRIDS | YSM_DEBUG_TIME_KERNELS)))
+    return match_batch_impl(h, b, out, st);
+  if (b->n_matches < 0 || b->n_scans < 0 || b->n_points < 0) return fail(h, YSM_EINVAL, "negative sizes");
+  // lanes: the point pool is made resident once, then every lane matches a contiguous share of the
+  // batch on its own stream and host thread
+  CK(cudaSetDevice(h->device));
+  ysm_batch sb = *b;
+  int64_t h2d = 0;
+  if (!b->pool_on_device) {
+    CK(h->d_pool_shared.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
+    if (b->n_points > 0)
+      CK(cudaMemcpyAsync(h->d_pool_shared.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
+    h2d = (int64_t)b->n_points * 16;
+    sb.pool_xy = (const double*)h->d_pool_shared.p;
+    sb.pool_on_device = 1;
+  }
+  CK(cudaEventRecord(h->lane_event, st));
+  std::vector<ysm_handle*> hs;
+  hs.push_back(h);
+  for (ysm_handle* sub : h->lanes) hs.push_back(sub);
+  std::vector<int> rcs(nl, YSM_OK);
+  std::vector<ysm_batch> subs(nl, sb);
+  std::vector<std::thread> threads;
+  for (int l = 0; l < nl; l++) {
+    const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
+    ysm_batch& q = subs[l];
+    q.n_matches = hi - lo;
+    q.query_scan = b->query_scan + lo;
+    q.query_pose = b->query_pose + 3 * (size_t)lo;
+    q.base_ptr = b->base_ptr + lo;  // absolute offsets into the shared base_idx
+    CK(cudaStreamWaitEvent(hs[l]->lane_stream, h->lane_event, 0));
+  }
+  auto run = [&](int l) {
+    const int lo = (int)((long long)b->n_matches * l / nl);
+    rcs[l] = match_batch_impl(hs[l], &subs[l], out + lo, hs[l]->lane_stream);
+  };
+  for (int l = 1; l < nl; l++) threads.emplace_back(run, l);
+  run(0);
+  for (std::thread& t : threads) t.join();
+  // merge the lanes' accounting into the main handle
+  for (int l = 1; l < nl; l++) {
+    for (int i = 0; i < 16; i++) h->work[i] += hs[l]->work[i];
+    h->t_sweep += hs[l]->t_sweep; h->t_build += hs[l]->t_build; h->t_reduce += hs[l]->t_reduce;
+    h->t_total = std::max(h->t_total, hs[l]->t_total);
+  }
+  h->work[6] += h2d;
+  h->work[11] = nl;
+  for (int l = 0; l < nl; l++)
+    if (rcs[l] != YSM_OK) {
+      if (l) h->err = hs[l]->err;
+      return rcs[l];
+    }
   return YSM_OK;
 }
 

@@ -29,7 +29,7 @@ def _is_cuda_tensor(x):
 
 
 class ScanMatcherB200(object):
-    def __init__(self, cfg=None, device=0, max_slots=0, max_grid_bytes=0):
+    def __init__(self, cfg=None, device=0, max_slots=0, max_grid_bytes=0, lanes=2):
         d = dict(DEFAULTS)
         if cfg:
             d.update({k: v for k, v in dict(cfg).items() if k in d})
@@ -40,6 +40,7 @@ class ScanMatcherB200(object):
         p.use_response_expansion = int(bool(d["use_response_expansion"]))
         p.max_slots = int(max_slots)
         p.max_grid_bytes = int(max_grid_bytes)
+        p.lanes = int(lanes)
         self._lib = _capi.lib()
         self._h = C.c_void_p()
         rc = self._lib.ysm_create(C.byref(p), int(device), C.byref(self._h))
@@ -81,7 +82,7 @@ class ScanMatcherB200(object):
         self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
                          "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
-                         "speculative_fine_passes"),
+                         "speculative_fine_passes", "lanes"),
                         (int(x) for x in v)))
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
