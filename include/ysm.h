@@ -140,6 +140,7 @@ int64_t ysm_launch_count(const ysm_handle *h);
 #define YSM_DEBUG_TIME_KERNELS 2
 #define YSM_DEBUG_NO_PRUNE 4 /* always use the unpruned lattice sweep (A/B checks of the zero-row pruning) */
 #define YSM_DEBUG_NO_SPECULATE 8 /* latency path: do not chain the fine pass on the device (A/B checks) */
+#define YSM_DEBUG_NO_MEGA 16     /* latency path: separate kernels instead of the single cooperative kernel */
 int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, double *reduce_ms,
                        double *total_ms);
 
@@ -150,7 +151,7 @@ int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, 
  * out[6] host->device bytes, out[7] device->host bytes, out[8] sweep launches that used zero-row pruning,
  * out[9] lattice lookups actually issued after pruning (counted only with YSM_DEBUG_TIME_KERNELS),
  * out[10] fine passes that ran chained on the device behind their coarse pass (latency path),
- * out[11] lanes used by the call;
+ * out[11] lanes used by the call, out[12] launches of the single-kernel latency path;
  * fills out[0..n), n <= 16 */
 int ysm_last_work(const ysm_handle *h, int64_t *out, int32_t n);
 

@@ -171,14 +171,24 @@ def test_latency_path_device_chained_fine_pass(world):
         ref = scenarios.oracle_results(cfg, b, True, True)
         m = _matcher(cfg, max_slots=8)
         a = _run(m, b, True, True).copy()
-        spec = m.last_work()["speculative_fine_passes"]
-        m.set_debug(_capi.DEBUG_NO_SPECULATE)
+        w = m.last_work()
+        spec = w["speculative_fine_passes"]
+        assert w["latency_kernel_launches"] == 1, "the single-kernel latency path did not run"
+        m.set_debug(_capi.DEBUG_NO_MEGA)
+        a2 = _run(m, b, True, True).copy()
+        w2 = m.last_work()
+        assert w2["latency_kernel_launches"] == 0 and w2["speculative_fine_passes"] == spec
+        m.set_debug(_capi.DEBUG_NO_MEGA | _capi.DEBUG_NO_SPECULATE)
         c = _run(m, b, True, True).copy()
         assert m.last_work()["speculative_fine_passes"] == 0
+        m.set_debug(_capi.DEBUG_NO_SPECULATE)
+        c2 = _run(m, b, True, True).copy()
+        coarse_only = _run(m, b, True, False).copy()
         m.close()
-        _assert_parity(a, ref, "latency path")
+        _assert_parity(a, ref, "latency kernel")
         _assert_parity(c, ref, "general path")
-        assert a.tobytes() == c.tobytes()
+        assert a.tobytes() == a2.tobytes() == c.tobytes() == c2.tobytes()
+        _assert_parity(coarse_only, scenarios.oracle_results(cfg, b, True, False), "latency kernel, coarse only")
         if degen == 0.0:
             assert spec >= 1, "the device-chained fine pass never ran"
     # a featureless wall: every pose along it ties, so the coarse pass has many winners

@@ -122,6 +122,7 @@ struct DevBuf {
 // growable pinned host buffer
 struct PinBuf {
   void* p = nullptr;
+  void* dptr = nullptr;  // device view of the mapped allocation
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
@@ -129,8 +130,13 @@ struct PinBuf {
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = want;
+    // mapped: the latency kernel reads its inputs from / writes its results to this memory directly
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      cap = want;
+      void* d = nullptr;
+      dptr = (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess) ? d : nullptr;
+    }
     return e;
   }
   void release() {
@@ -206,14 +212,14 @@ struct PassPlan {
   std::vector<int> spec_of;    // coarse pass id -> its speculative fine pass id (-1)
   std::vector<int> spec_h;     // coarse pass id -> index of its heading table in trig (doubles)
   std::unordered_map<TableKey, int, TableKeyHash> tab_index;
-  size_t off_elems = 0, sums_elems = 0;
+  size_t off_elems = 0, sums_elems = 0, cmax_elems = 0;
   int ang_elems = 0;
   int max_lat_P = 0, max_lat_nx = 0, max_lat_ny = 0, max_lat_tasks = 0, max_fine_poses = 0;
   int first_spec_table = -1;
   void clear() {
     tab.clear(); pass.clear(); ph.clear(); pa.clear(); fine.clear(); spec_fine.clear(); trig.clear();
     spec_of.clear(); spec_h.clear(); tab_index.clear();
-    off_elems = sums_elems = 0;
+    off_elems = sums_elems = cmax_elems = 0;
     ang_elems = 0;
     max_lat_P = max_lat_nx = max_lat_ny = max_lat_tasks = max_fine_poses = 0;
     first_spec_table = -1;
@@ -252,8 +258,11 @@ struct ysm_handle {
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
   DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
-  DevBuf d_wblob;
-  PinBuf h_blob, h_wblob, h_outs, h_angsums;
+  DevBuf d_wblob, d_cellmax;
+  PinBuf h_blob, h_wblob, h_outs, h_angsums, h_flags;
+  int epoch = 0;           // completion-flag value of the current latency-kernel launch
+  size_t mega_smem_attr = 0;
+  int mega_ctas_per_sm = 0;
   PassPlan plan;
   const MatchDev* cur_matches = nullptr;  // device views of the last wave (deferred clear)
   int* cur_workcount = nullptr;
@@ -487,10 +496,11 @@ extern "C" void ysm_destroy(ysm_handle* h) {
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
                     &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
-                    &h->d_angsums, &h->d_blob, &h->d_wblob};
+                    &h->d_angsums, &h->d_blob, &h->d_wblob, &h->d_cellmax};
   for (DevBuf* b : bufs) b->release();
   h->h_blob.release();
   h->h_wblob.release();
+  h->h_flags.release();
   h->h_outs.release();
   h->h_angsums.release();
   if (h->ev_ok)
@@ -890,6 +900,11 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         ph.ang_off = pl.ang_elems;
         if (ph.fine) pl.ang_elems += ph.nA;
         pd.spec = -1;
+        pd.cmax_off = -1;
+        if (!ph.fine) {
+          pd.cmax_off = (int)pl.cmax_elems;
+          pl.cmax_elems += (size_t)ph.nX * ph.nY;
+        }
         pd.cx = ph.cx; pd.cy = ph.cy; pd.ch = ph.ch;
         pd.offx = ph.offx; pd.offy = ph.offy; pd.resx = ph.resx; pd.resy = ph.resy;
         pd.angle_offset = ph.angle_offset; pd.angle_res = ph.angle_res;
@@ -976,6 +991,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
           fd.ang_off = pl.ang_elems;
           pl.ang_elems += nAf;
           fd.spec = -1;
+          fd.cmax_off = -1;
           fd.angle_offset = fo; fd.angle_res = fr;
           fd.gox = s.gox; fd.goy = s.goy;
           const int fid = (int)pl.pass.size();
@@ -1003,7 +1019,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     // ---- staging + upload --------------------------------------------------------------------
     // wave_static: also carry the pool / scan directory / match descriptors (latency path)
     BlobLayout L;
-    auto stage_blob = [&](bool wave_static, bool with_passes, PinBuf& hb, DevBuf& db) -> int {
+    auto stage_blob = [&](bool wave_static, bool with_passes, PinBuf& hb, DevBuf& db, bool upload = true) -> int {
       size_t o = 0;
       if (wave_static) {
         if (small) {
@@ -1049,7 +1065,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         memcpy(p + L.trig, pl.trig.data(), sizeof(double) * pl.trig.size());
         memset(p + L.pmax, 0, sizeof(double) * pl.pass.size());  // per-pass best response, max-accumulated on the GPU
       }
-      CK(cudaMemcpyAsync(db.p, hb.p, L.total, cudaMemcpyHostToDevice, st));
+      if (upload) CK(cudaMemcpyAsync(db.p, hb.p, L.total, cudaMemcpyHostToDevice, st));
       h->work[6] += (int64_t)L.total;
       if (wave_static) {
         const char* d = (const char*)db.p;
@@ -1071,7 +1087,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     auto launch_build = [&]() -> int {
       if (timing) CK(cudaEventRecord(h->ev[0], st));
       const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
-      const size_t fixed = 4 * (size_t)nbase_max + bits_bytes;
+      const size_t fixed = 16 * (size_t)nbase_max + bits_bytes;
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
       int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
       while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
@@ -1109,7 +1125,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         h->launches++;
         kt.mark("k_stamp_order");
       }
-      const size_t ksmem = (size_t)4 * g.K * g.Wk * 4;
+      const size_t ksmem = tile_stamp_smem(g.K, g.Wk, 8);
       const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
@@ -1145,7 +1161,63 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         return fail(h, YSM_ENOMEM, "wave workspace exceeds 2^31 elements; lower max_slots");
       tr.mark("pass plan (host libm)");
       const char* db = nullptr;
-      if (!built) {
+      // latency path, first iteration: everything in ONE cooperative kernel (k_match_small)
+      bool mega = !built && small && !timing && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
+                  !pl.pa.empty() && pl.fine.empty();
+      int mega_tpc = 0, mega_psplit = 1, mega_chunks = 0, mega_stage = 0, mega_fvw = 0, mega_log2cap = 6;
+      size_t mega_smem = 0;
+      if (mega) {
+        // phase shapes for a 512-thread CTA (16 warps)
+        mega_fvw = std::min(16, std::max(1, nbase_max));
+        const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
+        size_t fv = (size_t)mega_fvw * 4 * pmax + 16 * (size_t)nbase_max + bits_bytes;
+        const size_t fv_pts = ((fv + 15) & ~(size_t)15) + (size_t)mega_fvw * 16 * pmax;
+        if (fv_pts <= 100 * 1024) {
+          fv = fv_pts;
+          mega_stage = 1;
+        }
+        size_t so = 0;
+        if (h->ordered_stamps) {
+          while ((1ll << mega_log2cap) < 2 * max_match_cells) mega_log2cap++;
+          so = (size_t)4 << mega_log2cap;
+        }
+        // sweep: tpc row-tasks x psplit point slices = 16 warps; every CTA sees whole task groups
+        bool uniform = true;
+        for (const PassHost& q : pl.ph)
+          if (!q.fine && q.nY * ((q.nX + 31) / 32) != pl.max_lat_tasks) uniform = false;
+        mega_tpc = 16;
+        if (uniform) {
+          for (int t : {2, 4, 8, 1})
+            if (pl.max_lat_tasks % t == 0 && pl.max_lat_P / 24 >= 16 / t) {
+              mega_tpc = t;
+              break;
+            }
+        }
+        mega_psplit = 16 / mega_tpc;
+        if (mega_psplit > 1 && (!uniform || pl.max_lat_tasks % mega_tpc != 0)) { mega_tpc = 16; mega_psplit = 1; }
+        mega_chunks = (pl.max_lat_tasks + mega_tpc - 1) / mega_tpc;
+        const size_t sw = (size_t)(((pl.max_lat_P + 7) & ~7) + pl.max_lat_nx + pl.max_lat_ny + (mega_psplit > 1 ? 512 : 0)) * 4;
+        mega_smem = std::max(std::max(fv, so), std::max(tile_stamp_smem(g.K, g.Wk, 16), sw));
+        mega_smem = std::max(mega_smem, (size_t)(pmax + 8) * 4);
+        mega_smem = (mega_smem + 1023) & ~(size_t)1023;
+        if (mega_smem > 110 * 1024) mega = false;
+      }
+      if (mega) {
+        if (mega_smem > h->mega_smem_attr) {
+          CK(cudaFuncSetAttribute(k_match_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem));
+          h->mega_smem_attr = mega_smem;
+          int occ = 0;
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match_small, 512, mega_smem));
+          h->mega_ctas_per_sm = std::min(occ, 2);
+        }
+        if (h->mega_ctas_per_sm < 1) mega = false;
+      }
+      if (mega) {
+        int rc = stage_blob(true, true, h->h_wblob, h->d_wblob, /*upload=*/false);
+        if (rc != YSM_OK) return rc;
+        db = (const char*)h->d_wblob.p;
+        built = true;
+      } else if (!built) {
         // latency path: ONE copy carries the wave-static data and the first iteration's pass tables
         int rc = stage_blob(true, true, h->h_wblob, h->d_wblob);
         if (rc != YSM_OK) return rc;
@@ -1174,11 +1246,83 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       CK(h->d_sums.ensure(std::max<size_t>(16, pl.sums_elems * 8)));  // penalised responses, f64 [iy][ix][a]
       CK(h->d_outs.ensure(sizeof(PassOut) * (size_t)npass));
       CK(h->d_angsums.ensure(std::max<size_t>(16, (size_t)pl.ang_elems * 4)));
+      CK(h->d_cellmax.ensure(std::max<size_t>(16, pl.cmax_elems * 8)));
       CK(h->h_outs.ensure(sizeof(PassOut) * (size_t)npass));
       CK(h->h_angsums.ensure(std::max<size_t>(16, (size_t)pl.ang_elems * 4)));
       tr.mark("blob H2D");
 
+      if (mega) {
+        CK(h->h_flags.ensure((size_t)npass * 4 + 256));
+        if (!h->h_wblob.dptr || !h->h_outs.dptr || !h->h_angsums.dptr || !h->h_flags.dptr)
+          return fail(h, YSM_ECUDA, "mapped host memory is not available");
+        h->epoch++;
+        for (int pid = 0; pid < npass; pid++) ((volatile int*)h->h_flags.p)[pid] = 0;
+        SmallArgs A;
+        memset(&A, 0, sizeof(A));
+        A.blob_src = (const uint4*)h->h_wblob.dptr;
+        A.blob_dst = (uint4*)h->d_wblob.p;
+        A.blob_vec = (int)((L.total + 15) / 16);
+        A.pool_in_blob = b->pool_on_device ? 0 : 1;
+        A.pool_dev = b->pool_on_device ? b->pool_xy : nullptr;
+        A.o_pool = (unsigned)L.pool; A.o_scan_start = (unsigned)L.scan_start; A.o_scan_count = (unsigned)L.scan_count;
+        A.o_matches = (unsigned)L.matches; A.o_base = (unsigned)L.base; A.o_workcount = (unsigned)L.workcount;
+        A.o_tab = (unsigned)L.tab; A.o_pass = (unsigned)L.pass; A.o_pa = (unsigned)L.pa; A.o_trig = (unsigned)L.trig;
+        A.o_pmax = (unsigned)L.pmax;
+        A.nw = nw; A.npa = (int)pl.pa.size(); A.ncoarse = ncoarse_total; A.nspec = nspec; A.nAf = std::max(1, nAf);
+        A.pmax = pmax; A.nbase_max = nbase_max; A.stage = mega_stage; A.fv_warps = mega_fvw;
+        A.ordered = h->ordered_stamps ? 1 : 0; A.log2cap = mega_log2cap;
+        A.tpc = mega_tpc; A.psplit = mega_psplit; A.task_chunks = mega_chunks;
+        A.ptcell = (uint32_t*)h->d_ptcell.p; A.cells = (uint32_t*)h->d_cells.p; A.cellcount = (int*)h->d_cellcount.p;
+        A.gbox = (uint2*)h->d_gbox.p; A.work = (int2*)h->d_work.p;
+        A.kernel = h->d_kernel; A.grids = h->d_grids; A.rowmask = h->d_rowmask; A.rm_words = h->rm_words;
+        A.epoch = h->epoch;
+        A.offsets = (int*)h->d_offsets.p; A.resp = (double*)h->d_sums.p;
+        A.cellmax = (unsigned long long*)h->d_cellmax.p; A.cellmax_n = (int)pl.cmax_elems;
+        A.outs_host = (PassOut*)h->h_outs.dptr; A.angs_host = (int*)h->h_angsums.dptr;
+        A.flags_host = (volatile int*)h->h_flags.dptr;
+        unsigned long long* ts_host = nullptr;
+        if (tr.on) {
+          ts_host = (unsigned long long*)((char*)h->h_flags.p + (((size_t)npass * 4 + 15) & ~(size_t)15));
+          A.tstamps = (unsigned long long*)((char*)h->h_flags.dptr + (((size_t)npass * 4 + 15) & ~(size_t)15));
+        }
+        GridC gg = g;
+        PenaltyC pp = h->pen;
+        void* kargs[] = {&gg, &pp, &A};
+        const int ctas = h->num_sms * h->mega_ctas_per_sm;
+        CK(cudaLaunchCooperativeKernel((const void*)k_match_small, dim3(ctas), dim3(512), kargs, mega_smem, st));
+        h->launches++;
+        h->work[12]++;
+        tr.mark("latency kernel launch");
+        // wait for the per-pass completion flags the kernel writes after its results
+        volatile int* flags = (volatile int*)h->h_flags.p;
+        const auto t_start = std::chrono::steady_clock::now();
+        long spins = 0;
+        for (int cp = 0; cp < ncoarse_total; cp++) {
+          const int pid = pl.spec_of[cp] >= 0 ? pl.spec_of[cp] : cp;  // the pass that publishes last for this match
+          while (flags[pid] != h->epoch) {
+            if ((++spins & 0xFFFF) == 0) {
+              if (cudaStreamQuery(st) != cudaErrorNotReady) break;  // finished (or failed) without the flag
+              if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 30.0) break;
+            }
+          }
+          if (flags[pid] != h->epoch) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) return fail(h, YSM_ECUDA, std::string("latency kernel: ") + cudaGetErrorString(e));
+            if (flags[pid] != h->epoch) return fail(h, YSM_ECUDA, "latency kernel finished without publishing its results");
+          }
+        }
+        tr.mark("poll");
+        if (ts_host) {
+          cudaStreamSynchronize(st);
+          static const char* names[] = {"P0 blob copy", "P1 find_valid", "sync", "P2 stamp", "sync", "P3 sweep", "sync",
+                                        "P4a reduce", "sync", "P4b fine sweep", "sync", "P4c fine reduce"};
+          for (int k = 0; k < 12; k++)
+            fprintf(stderr, "[ysm-kernel] %-14s %8.1f us\n", names[k], (double)(ts_host[k + 1] - ts_host[k]) * 1e-3);
+        }
+      } else {
       // ---- K2 offsets (tables of the passes the host scheduled) ------------------------------------
+      if (pl.cmax_elems > 0) CK(cudaMemsetAsync(h->d_cellmax.p, 0, pl.cmax_elems * 8, st));
       const int ntab_host = spec ? pl.first_spec_table : (int)pl.tab.size();
       {
         int maxwork = 1;
@@ -1208,7 +1352,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
           dim3 grid(npa, nrg * nxc, 1);
           k_sweep_pruned<<<grid, 32 * rows_per_cta, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, d_trig, d_pool, h->d_grids,
                                                                h->d_rowmask, h->rm_words, h->tnx, (double*)h->d_sums.p,
-                                                               d_pmax, rows_per_cta, cw, PB,
+                                                               d_pmax, (unsigned long long*)h->d_cellmax.p, rows_per_cta, cw, PB,
                                                                timing ? h->d_issued : nullptr);
           h->work[8]++;
         } else {
@@ -1237,7 +1381,8 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
           }
           dim3 grid(npa, task_chunks, 1);
           k_sweep_lattice<<<grid, threads, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, (const int*)h->d_offsets.p,
-                                                       h->d_grids, (double*)h->d_sums.p, d_pmax, tpc, psplit);
+                                                       h->d_grids, (double*)h->d_sums.p, d_pmax,
+                                                       (unsigned long long*)h->d_cellmax.p, tpc, psplit);
         }
         h->launches++;
         h->work[1]++;
@@ -1254,7 +1399,8 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       // ---- K3b/K4 reduce ------------------------------------------------------------------------
       if (timing) CK(cudaEventRecord(h->ev[4], st));
       k_reduce<<<ncoarse_total, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
-                                             d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, 0);
+                                             d_pmax, (const unsigned long long*)h->d_cellmax.p, d_trig, h->d_grids,
+                                             (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, 0);
       h->launches++;
       kt.mark("k_reduce");
       if (nspec > 0) {
@@ -1268,8 +1414,8 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         k_sweep_points<<<sg, 256, 0, st>>>(g, h->pen, d_pass, d_fine + nhostfine, d_tab, (const int*)h->d_offsets.p,
                                            h->d_grids, (double*)h->d_sums.p, d_pmax);
         k_reduce<<<nspec, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
-                                       d_pmax, d_trig, h->d_grids, (PassOut*)h->d_outs.p, (int*)h->d_angsums.p,
-                                       ncoarse_total);
+                                       d_pmax, (const unsigned long long*)h->d_cellmax.p, d_trig, h->d_grids,
+                                       (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, ncoarse_total);
         h->launches += 3;
         kt.mark("speculative fine");
       }
@@ -1282,6 +1428,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       CK(cudaStreamSynchronize(st));
       tr.mark("sync");
       CK(cudaGetLastError());
+      }  // !mega
       if (timing) {
         float ms = 0;
         if (iter == 0) {

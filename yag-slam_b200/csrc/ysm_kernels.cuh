@@ -10,6 +10,7 @@
 // No device sin/cos/atan2 anywhere: every transcendental is evaluated by the host runtime with
 // libm and handed in as a table, so results are bit-identical to the CPU reference.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,7 +64,8 @@ struct PassDev {
   // speculative fine pass of a coarse pass (latency path): pass id (-1: none) and where, in the
   // trig array, the host left the per-winning-angle data: heading table [nA] (double index),
   // cos/sin blocks [nA][nAf] of the fine search angles and of their normalised headings (pair index)
-  int spec, spec_nAf, spec_h_off, spec_trig_off, spec_htrig_off, pad1;
+  int spec, spec_nAf, spec_h_off, spec_trig_off, spec_htrig_off;
+  int cmax_off;   // element offset of this (coarse) pass's per-cell maxima [nY][nX]; -1: none
   double cx, cy, ch;              // search centre
   double offx, offy, resx, resy;  // search space offset / resolution
   double angle_offset, angle_res;
@@ -101,25 +103,25 @@ __device__ __forceinline__ uint32_t vmax4_lt128(uint32_t a, uint32_t b) {
 // memory pointer chase), then every segment [t_k, t_k+1) is kept iff the side test ss >= 0
 // (parallel). Output: the match's occupied cells in Karto's processing order.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restrict__ base_idx,
-             const int* __restrict__ scan_start, const int* __restrict__ scan_count,
-             const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
-             uint32_t* __restrict__ cells, int* __restrict__ cell_count, uint2* __restrict__ gbox,
-             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max, int stage) {
-  extern __shared__ unsigned char smem_raw[];
+__device__ __forceinline__ void
+find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, const int* scan_start,
+                const int* scan_count, const double* pool, uint32_t* pt_cell, uint32_t* cells, int* cell_count,
+                uint2* gbox, int2* work, int* work_count, int pmax, int nbase_max, int stage, int vbx,
+                unsigned char* smem_raw, int fv_warps = 0) {
   __shared__ int s_tile_total, s_tile_base;
-  const int nwarps = blockDim.x >> 5;
+  // fv_warps > 0: only that many warps take scans (the shared arrays are sized for them)
+  const int nwarps = fv_warps > 0 ? min(fv_warps, (int)(blockDim.x >> 5)) : (int)(blockDim.x >> 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned short* s_next = reinterpret_cast<unsigned short*>(smem_raw) + (size_t)warp * 2 * pmax;
   unsigned short* s_trig = s_next + pmax;
   int* s_scan_emit = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * 4 * pmax);  // [nbase_max]
-  unsigned* s_bits = reinterpret_cast<unsigned*>(s_scan_emit + nbase_max);         // touched-tile bitmap
+  int* s_dir = s_scan_emit + nbase_max;  // [3][nbase_max]: point count, pool start, prefix of counts of the base scans
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_dir + 3 * nbase_max);           // touched-tile bitmap
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int nbitw = (tnx * tnx + 31) >> 5;
   // small waves: each warp stages its scan's points in shared memory (SoA) so the filter's
   // dependent loads are LDS instead of L2 round trips
-  double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 4 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
+  double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 16 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
   double* s_py = s_px + pmax;
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) s_bits[i] = 0u;
   if (threadIdx.x == 0) s_tile_total = 0;
@@ -127,18 +129,29 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
 #define YSM_PX(i) (stage ? s_px[i] : pts[2 * (i)])
 #define YSM_PY(i) (stage ? s_py[i] : pts[2 * (i) + 1])
 
-  const MatchDev m = matches[blockIdx.x];
+  const MatchDev m = matches[vbx];
   const int nbase = m.base_end - m.base_begin;
   const double msd = 0.1 * 0.1;  // math::Square(0.1)
 
-  // scan-local offsets inside the match's scratch: prefix of scan counts
-  // (recomputed per warp; nbase is small)
-  for (int b = warp; b < nbase; b += nwarps) {
-    int off = 0;
-    for (int bb = 0; bb < b; bb++) off += scan_count[base_idx[m.base_begin + bb]];
+  // directory of the match's base scans (one round of loads), scan-local offsets = prefix of counts
+  for (int b = threadIdx.x; b < nbase; b += blockDim.x) {
     const int s = base_idx[m.base_begin + b];
-    const int n = scan_count[s];
-    const double* pts = pool + 2 * (size_t)scan_start[s];
+    s_dir[b] = scan_count[s];
+    s_dir[nbase_max + b] = scan_start[s];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int b = 0; b < nbase; b++) {
+      s_dir[2 * nbase_max + b] = off;
+      off += s_dir[b];
+    }
+  }
+  __syncthreads();
+  for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
+    const int off = s_dir[2 * nbase_max + b];
+    const int n = s_dir[b];
+    const double* pts = pool + 2 * (size_t)s_dir[nbase_max + b];
     uint32_t* out = pt_cell + m.cells_off + off;
     for (int i = lane; i < n; i += 32) out[i] = YSM_INVALID_CELL;
     int emitted = 0;
@@ -209,13 +222,11 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
   }
   __syncthreads();
   // ordered compaction (scan order, then point order)
-  for (int b = warp; b < nbase; b += nwarps) {
-    int off = 0, dst = 0;
-    for (int bb = 0; bb < b; bb++) {
-      off += scan_count[base_idx[m.base_begin + bb]];
-      dst += s_scan_emit[bb];
-    }
-    const int n = scan_count[base_idx[m.base_begin + b]];
+  for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
+    int dst = 0;
+    for (int bb = 0; bb < b; bb++) dst += s_scan_emit[bb];
+    const int off = s_dir[2 * nbase_max + b];
+    const int n = s_dir[b];
     const uint32_t* in = pt_cell + m.cells_off + off;
     uint32_t* outc = cells + m.cells_off;
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -228,7 +239,7 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
   }
   int tot = 0;
   for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
-  if (threadIdx.x == 0) cell_count[blockIdx.x] = tot;
+  if (threadIdx.x == 0) cell_count[vbx] = tot;
   // touched tiles -> the wave's (match, tile) work list
   int cnt = 0;
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) cnt += __popc(s_bits[i]);
@@ -245,13 +256,13 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
     while (b) {
       const int bit = __ffs(b) - 1;
       b &= b - 1;
-      work[pos++] = make_int2((int)blockIdx.x, i * 32 + bit);
+      work[pos++] = make_int2(vbx, i * 32 + bit);
     }
   }
   // bounding box of every group of 32 consecutive cells (scan order keeps them spatially close)
   __threadfence_block();
   const uint32_t* mcells = cells + m.cells_off;
-  for (int g0 = warp * 32; g0 < tot; g0 += nwarps * 32) {
+  for (int g0 = warp * 32; g0 < tot && warp < nwarps; g0 += nwarps * 32) {
     const int i = g0 + lane;
     int xlo = 0xFFFF, xhi = 0, ylo = 0xFFFF, yhi = 0;
     if (i < tot) {
@@ -267,6 +278,17 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
     }
     if (lane == 0) gbox[m.gbox_off + (g0 >> 5)] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   }
+}
+
+__global__ void __launch_bounds__(1024)
+k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restrict__ base_idx,
+             const int* __restrict__ scan_start, const int* __restrict__ scan_count,
+             const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
+             uint32_t* __restrict__ cells, int* __restrict__ cell_count, uint2* __restrict__ gbox,
+             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max, int stage) {
+  extern __shared__ __align__(16) unsigned char dsm_fv[];
+  find_valid_body(g, matches, base_idx, scan_start, scan_count, pool, pt_cell, cells, cell_count, gbox, work,
+                  work_count, pmax, nbase_max, stage, (int)blockIdx.x, dsm_fv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,13 +310,12 @@ __device__ __forceinline__ bool hash_has(const uint32_t* __restrict__ tab, uint3
   }
 }
 
-__global__ void __launch_bounds__(32)
-k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells,
-              const int* __restrict__ cell_count, int log2cap) {
-  extern __shared__ uint32_t s_tab[];
-  const MatchDev m = matches[blockIdx.x];
-  const int n = cell_count[blockIdx.x];
-  const int lane = threadIdx.x;
+// (one warp; `lane` = lane id)
+__device__ __forceinline__ void
+stamp_order_body(const MatchDev* matches, uint32_t* cells, const int* cell_count, int log2cap, int vbx, int lane,
+                 uint32_t* s_tab) {
+  const MatchDev m = matches[vbx];
+  const int n = cell_count[vbx];
   const uint32_t cap = 1u << log2cap, mask = cap - 1u;
   const int shift = 32 - log2cap;
   for (uint32_t i = lane; i < cap; i += 32) s_tab[i] = YSM_INVALID_CELL;
@@ -332,6 +353,13 @@ k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells
   }
 }
 
+__global__ void __launch_bounds__(32)
+k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells,
+              const int* __restrict__ cell_count, int log2cap) {
+  extern __shared__ uint32_t dsm_so[];
+  stamp_order_body(matches, cells, cell_count, log2cap, (int)blockIdx.x, (int)threadIdx.x, dsm_so);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
 // yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so each touched
@@ -345,8 +373,8 @@ k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells
 // ---------------------------------------------------------------------------------------------
 #define YSM_TILE_LIST 224   // candidate cells staged per warp between flushes
 
-__device__ __forceinline__ void tile_scatter(uint32_t* __restrict__ tile, const uint32_t* __restrict__ list,
-                                             int n, const uint32_t* __restrict__ s_k, int K, int Wk, int h,
+__device__ __forceinline__ void tile_scatter(uint2* __restrict__ tile, const uint32_t* __restrict__ list,
+                                             int n, const uint2* __restrict__ s_k, int K, int Wk, int h,
                                              int x0t, int y0t, int lane) {
   const int wt0 = x0t >> 2;
   for (int e0 = 0; e0 < n; e0 += 32) {
@@ -372,48 +400,56 @@ __device__ __forceinline__ void tile_scatter(uint32_t* __restrict__ tile, const 
       const uint32_t q0 = __shfl_sync(0xffffffffu, p0, k), q1 = __shfl_sync(0xffffffffu, p1, k);
       const int nwd = (int)((q0 >> 8) & 15u), items = (int)(q0 >> 12);
       const unsigned rcp = q1 >> 11;
-      const uint32_t* ks = s_k + (q1 & 2047u);
-      uint32_t* t0 = tile + (q0 & 255u);
+      const uint2* ks = s_k + (q1 & 2047u);
+      uint2* t0 = tile + (q0 & 255u);
       for (int it = lane; it < items; it += 32) {
         const int jr = (int)(((unsigned)it * rcp) >> 16);
         const int ww = it - jr * nwd;
-        const uint32_t kw = ks[jr * Wk + ww];
-        uint32_t* tp = t0 + jr * 8 + ww;
-        *tp = vmax4_lt128(*tp, kw);
+        const uint2 kw = ks[jr * Wk + ww];
+        uint2* tp = t0 + jr * 8 + ww;
+        uint2 tv = *tp;
+        tv.x = __vmaxu2(tv.x, kw.x);  // VIMNMX.U16x2: two cells per instruction
+        tv.y = __vmaxu2(tv.y, kw.y);
+        *tp = tv;
       }
       __syncwarp();
     }
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
-             const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
-             const int2* __restrict__ work, const int* __restrict__ work_count,
-             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
-             int rm_words) {
-  extern __shared__ uint32_t s_k[];  // [4][K][Wk] pre-shifted stamp rows
-  __shared__ uint32_t s_tile[8][YSM_TILE * YSM_TILE / 4];
-  __shared__ uint32_t s_list[8][YSM_TILE_LIST + 32];
+// dynamic smem: s_k [4][K][Wk] uint2 (pre-shifted stamp rows, 4 cells per entry widened to u16) |
+// per warp: tile [256] uint2 | candidate list [YSM_TILE_LIST + 32] u32
+__host__ __device__ __forceinline__ size_t tile_stamp_smem(int K, int Wk, int nwarps) {
+  return (size_t)4 * K * Wk * 8 + (size_t)nwarps * (YSM_TILE * YSM_TILE / 4 * 8 + (YSM_TILE_LIST + 32) * 4);
+}
+
+__device__ __forceinline__ void
+tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, const int* cell_count,
+                const uint2* gbox, const int2* work, const int* work_count, const uint8_t* kernel, uint8_t* grids,
+                uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm) {
   const int K = g.K, Wk = g.Wk, h = g.half_kernel;
   const int nks = 4 * K * Wk;
+  const int wpb = blockDim.x >> 5;  // warps per block
+  uint2* s_k = reinterpret_cast<uint2*>(dsm);
+  uint2* s_tile = s_k + nks;
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_tile + (size_t)wpb * (YSM_TILE * YSM_TILE / 4));
   for (int t = threadIdx.x; t < nks; t += blockDim.x) {
     const int w = t % Wk, j = (t / Wk) % K, s = t / (Wk * K);
-    uint32_t word = 0;
+    uint32_t v[4];
     for (int b = 0; b < 4; b++) {
       const int i = w * 4 + b - s;  // stamp column
-      if (i >= 0 && i < K) word |= (uint32_t)kernel[i + K * j] << (8 * b);
+      v[b] = (i >= 0 && i < K) ? (uint32_t)kernel[i + K * j] : 0u;
     }
-    s_k[t] = word;
+    s_k[t] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
   }
   __syncthreads();
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* tile = s_tile[warp];
-  uint32_t* list = s_list[warp];
+  uint2* tile = s_tile + (size_t)warp * (YSM_TILE * YSM_TILE / 4);
+  uint32_t* list = s_list + (size_t)warp * (YSM_TILE_LIST + 32);
   const int nwork = *work_count;
-  const int nwarps_total = gridDim.x * 8;
-  for (int wi = blockIdx.x * 8 + warp; wi < nwork; wi += nwarps_total) {
+  const int nwarps_total = vgx * wpb;
+  for (int wi = vbx * wpb + warp; wi < nwork; wi += nwarps_total) {
     const int2 wk = work[wi];
     const MatchDev m = matches[wk.x];
     const int ncells = cell_count[wk.x];
@@ -423,7 +459,7 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
     const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
     const int ngroups = (ncells + 31) >> 5;
 #pragma unroll
-    for (int k = 0; k < 8; k++) tile[k * 32 + lane] = 0u;
+    for (int k = 0; k < 8; k++) tile[k * 32 + lane] = make_uint2(0u, 0u);
     __syncwarp();
     int n = 0;
     for (int g0 = 0; g0 < ngroups; g0 += 32) {
@@ -467,7 +503,8 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int row = y0t + k * 4 + dr;
-      const uint32_t v = tile[(k * 4 + dr) * 8 + wd];
+      const uint2 tv = tile[(k * 4 + dr) * 8 + wd];
+      const uint32_t v = __byte_perm(tv.x, tv.y, 0x6420);  // u16 lanes -> bytes
       if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
       const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
 #pragma unroll
@@ -479,32 +516,41 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
   }
 }
 
-// zero the tiles a wave touched (the slot grids are kept all-zero between matches)
+__global__ void __launch_bounds__(256)
+k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
+             const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
+             const int2* __restrict__ work, const int* __restrict__ work_count,
+             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
+             int rm_words) {
+  extern __shared__ __align__(16) unsigned char dsm_ts[];
+  tile_stamp_body(g, matches, cells, cell_count, gbox, work, work_count, kernel, grids, rowmask, rm_words,
+                  (int)blockIdx.x, (int)gridDim.x, dsm_ts);
+}
+
+// zero the tiles a wave touched (the slot grids are kept all-zero between matches): warp per tile
 __global__ void __launch_bounds__(256)
 k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
              const int* __restrict__ work_count, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
              int rm_words) {
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int r = threadIdx.x >> 3, wd = threadIdx.x & 7;
+  const int lane = threadIdx.x & 31, dr = lane >> 3, wd = lane & 7;
   const int nwork = *work_count;
-  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+  const int nwarps_total = gridDim.x * (blockDim.x >> 5);
+  for (int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nwork; wi += nwarps_total) {
     const int2 wk = work[wi];
     const int slot = matches[wk.x].slot;
     const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
-    const int row = ty * YSM_TILE + r, gw = ((tx * YSM_TILE) >> 2) + wd;
-    if (row < g.height && gw < g.stride4)
-      reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes)[(size_t)row * g.stride4 + gw] = 0u;
-    if (threadIdx.x == 0) rowmask[(size_t)slot * rm_words + wk.y] = 0u;
+    uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes);
+    const int gw = ((tx * YSM_TILE) >> 2) + wd;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int row = ty * YSM_TILE + k * 4 + dr;
+      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = 0u;
+    }
+    if (lane == 0) rowmask[(size_t)slot * rm_words + wk.y] = 0u;
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2  GridIndexLookup::ComputeOffsets (python analogue _rotate_points,
-// yag_slam/helpers.py:76-78). One thread per (angle, 4 points): inverse-transform the query's
-// world readings into the sensor frame, rotate by the search angle (cos/sin from the host),
-// round to cells exactly as Karto (including the add-then-subtract of the grid offset) and
-// store int4-vectorised, point index fastest. grid = (ceil(nA*Ppad/4 / 256), n_tables)
-// ---------------------------------------------------------------------------------------------
 // cell offset (gx, gy) of query point (wx, wy) rotated by the search angle (cosine, sine):
 // the arithmetic of GridIndexLookup::ComputeOffsets, shared by k_offsets and the fused sweep
 __device__ __forceinline__ void offset_cell(const TableDev& t, double scale, double wx, double wy, double cosine,
@@ -518,13 +564,12 @@ __device__ __forceinline__ void offset_cell(const TableDev& t, double scale, dou
   gy = world_to_grid1(oy + t.goy, t.goy, scale);
 }
 
-__global__ void __launch_bounds__(256)
-k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict__ trig,
-          const double* __restrict__ pool, int* __restrict__ offsets, int table_base) {
-  const TableDev t = tables[table_base + blockIdx.y];
+// (thread `tid0` of `nthreads` cooperating on table t)
+__device__ __forceinline__ void offsets_body(const GridC& g, const TableDev& t, const double* trig, const double* pool,
+                                             int* offsets, int tid0, int nthreads) {
   const int p4n = t.Ppad >> 2;
   const int work = t.nA * p4n;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < work; it += gridDim.x * blockDim.x) {
+  for (int it = tid0; it < work; it += nthreads) {
     const int a = it / p4n, p0 = (it - a * p4n) << 2;
     const double cosine = trig[2 * (t.trig_off + a)], sine = trig[2 * (t.trig_off + a) + 1];
     int o[4];
@@ -542,6 +587,13 @@ k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict
     }
     *reinterpret_cast<int4*>(offsets + t.out_off + (size_t)a * t.Ppad + p0) = make_int4(o[0], o[1], o[2], o[3]);
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict__ trig,
+          const double* __restrict__ pool, int* __restrict__ offsets, int table_base) {
+  const TableDev t = tables[table_base + blockIdx.y];
+  offsets_body(g, t, trig, pool, offsets, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -576,6 +628,13 @@ __device__ __forceinline__ double response_of(const PassDev& ps, const PenaltyC&
     r *= (dp * ap);
   }
   return r;
+}
+
+// m_pSearchSpaceProbs of CorrelateScan: per lattice cell the maximum response over the
+// angles, accumulated by the sweep epilogues (responses are >= 0: bit patterns order like integers)
+__device__ __forceinline__ void cell_max_update(unsigned long long* cellmax, const PassDev& ps, int ix, int iy, double v) {
+  if (ps.cmax_off >= 0)
+    atomicMax(cellmax + ps.cmax_off + (size_t)iy * ps.nX + ix, (unsigned long long)__double_as_longlong(v));
 }
 
 // responses are >= 0, so their IEEE bit patterns order like unsigned integers
@@ -618,20 +677,21 @@ __device__ __forceinline__ unsigned sweep_row(const uint8_t* __restrict__ gp, co
   return sum0 + sum1;
 }
 
-__global__ void __launch_bounds__(1024, 2)
-k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
-                const PassAngle* __restrict__ pa_list, const TableDev* __restrict__ tables,
-                const int* __restrict__ offsets, const uint8_t* __restrict__ grids,
-                double* __restrict__ resp, double* __restrict__ passmax, int tasks_per_cta, int psplit) {
-  extern __shared__ __align__(16) int s_i[];
+// offsets == nullptr: the lookup offsets of the angle are computed here from the query points
+// (ComputeOffsets fused; trig / pool must be given), else read from the k_offsets table.
+__device__ __forceinline__ void
+sweep_lattice_body(const GridC& g, const PenaltyC& pen, const PassDev* passes, const PassAngle* pa_list,
+                   const TableDev* tables, const int* offsets, const double* trig, const double* pool,
+                   const uint8_t* grids, double* resp, double* passmax, unsigned long long* cellmax,
+                   int tasks_per_cta, int psplit, int vbx, int vby, int* s_i) {
   __shared__ int s_minmax[4];  // min off, max off, min base, max base
   __shared__ double s_wmax[32];
-  const int p_chunk = (passes[pa_list[blockIdx.x].pass].P + 7) & ~7;
-  const PassAngle pa = pa_list[blockIdx.x];
+  const int p_chunk = (passes[pa_list[vbx].pass].P + 7) & ~7;
+  const PassAngle pa = pa_list[vbx];
   const PassDev ps = passes[pa.pass];
   const int nxc = (ps.nX + 31) >> 5;
   const int ntasks = ps.nY * nxc;
-  const int task0 = blockIdx.y * tasks_per_cta;
+  const int task0 = vby * tasks_per_cta;
   if (task0 >= ntasks) return;
   const int task1 = min(ntasks, task0 + tasks_per_cta);
   const int pbeg = 0;
@@ -646,10 +706,23 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
   }
   __syncthreads();
   const TableDev tb = tables[ps.table];
-  const int* goff = offsets + tb.out_off + (size_t)pa.a * tb.Ppad;
+  const int* goff = offsets ? offsets + tb.out_off + (size_t)pa.a * tb.Ppad : nullptr;
+  double cosine = 0.0, sine = 0.0;
+  if (!goff) {
+    cosine = trig[2 * (tb.trig_off + pa.a)];
+    sine = trig[2 * (tb.trig_off + pa.a) + 1];
+  }
   int mn = 0x7fffffff, mx = (int)0x80000000;
   for (int p = pbeg + threadIdx.x; p < pend; p += blockDim.x) {
-    const int o = goff[p];
+    int o;
+    if (goff) {
+      o = goff[p];
+    } else {
+      const double2 w = *reinterpret_cast<const double2*>(pool + 2 * (size_t)(tb.q_start + p));
+      int gx, gy;
+      offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
+      o = gx + gy * g.stride;
+    }
     s_off[p - pbeg] = o;
     mn = min(mn, o);
     mx = max(mx, o);
@@ -728,6 +801,7 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
     if (active) {
       const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
       resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
+      cell_max_update(cellmax, ps, ix, iy, rr);
       wmax = rr > wmax ? rr : wmax;
     }
   }
@@ -743,6 +817,17 @@ k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
     for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
     pass_max_update(passmax, pa.pass, m);
   }
+}
+
+__global__ void __launch_bounds__(1024, 2)
+k_sweep_lattice(GridC g, PenaltyC pen, const PassDev* __restrict__ passes,
+                const PassAngle* __restrict__ pa_list, const TableDev* __restrict__ tables,
+                const int* __restrict__ offsets, const uint8_t* __restrict__ grids,
+                double* __restrict__ resp, double* __restrict__ passmax, unsigned long long* __restrict__ cellmax,
+                int tasks_per_cta, int psplit) {
+  extern __shared__ __align__(16) int dsm_sl[];
+  sweep_lattice_body(g, pen, passes, pa_list, tables, offsets, nullptr, nullptr, grids, resp, passmax, cellmax,
+                     tasks_per_cta, psplit, (int)blockIdx.x, (int)blockIdx.y, dsm_sl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -816,8 +901,8 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
                const TableDev* __restrict__ tables, const double* __restrict__ trig,
                const double* __restrict__ pool, const uint8_t* __restrict__ grids,
                const uint32_t* __restrict__ rowmask, int rm_words, int tnx, double* __restrict__ resp,
-               double* __restrict__ passmax, int rows_per_cta, int cw, int PB,
-               unsigned long long* __restrict__ issued) {
+               double* __restrict__ passmax, unsigned long long* __restrict__ cellmax, int rows_per_cta, int cw,
+               int PB, unsigned long long* __restrict__ issued) {
   extern __shared__ __align__(16) uint32_t s_u[];
   __shared__ double s_wmax[32];
   __shared__ int s_col[32], s_row[32];
@@ -944,6 +1029,7 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
     const int ix = ix0 + lane, iy = iy0 + warp;
     const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
     resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
+    cell_max_update(cellmax, ps, ix, iy, rr);
     wmax = rr;
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -965,15 +1051,12 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
 // 3 x 3 x nA poses): one warp per pose, lanes stride the query points, integer partial sums
 // combined with warp shuffles. grid = (ceil(nposes / warps_per_cta), n_fine_passes)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
-               const TableDev* __restrict__ tables, const int* __restrict__ offsets,
-               const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax) {
-  const int pid = pass_ids[blockIdx.y];
-  const PassDev ps = passes[pid];
+// (one warp evaluates pose `pose` of pass `pid`)
+__device__ __forceinline__ void
+sweep_points_body(const GridC& g, const PenaltyC& pen, const PassDev& ps, const TableDev& tb, int pid, int pose,
+                  const int* offsets, const uint8_t* grids, double* resp, double* passmax) {
   const int nposes = ps.nX * ps.nY * ps.nA;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int pose = blockIdx.x * nwarps + warp;
+  const int lane = threadIdx.x & 31;
   if (pose >= nposes) return;
   const int iy = pose / (ps.nX * ps.nA);
   const int rem = pose - iy * ps.nX * ps.nA;
@@ -983,7 +1066,6 @@ k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const int gx = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
   const int gy = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
   const int base = gx + gy * g.stride;
-  const TableDev tb = tables[ps.table];
   const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
   const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
   const unsigned dsz = (unsigned)g.data_size;
@@ -1001,6 +1083,17 @@ k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
     resp[ps.sums_off + pose] = rr;
     pass_max_update(passmax, pid, rr);
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
+               const TableDev* __restrict__ tables, const int* __restrict__ offsets,
+               const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax) {
+  const int pid = pass_ids[blockIdx.y];
+  const PassDev ps = passes[pid];
+  const TableDev tb = tables[ps.table];
+  sweep_points_body(g, pen, ps, tb, pid, (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)), offsets, grids,
+                    resp, passmax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1035,11 +1128,10 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
   return r;
 }
 
-__global__ void __launch_bounds__(512)
-k_reduce(GridC g, PassDev* passes, TableDev* tables,
-         const int* __restrict__ offsets, const double* __restrict__ resp,
-         const double* __restrict__ passmax, const double* __restrict__ trig,
-         const uint8_t* __restrict__ grids, PassOut* __restrict__ outs, int* __restrict__ angsums, int pass_base) {
+// (one CTA of <= 512 threads reduces pass `ps`; *po may live in shared memory)
+__device__ __forceinline__ void
+reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* offsets, const double* resp, double best,
+            const unsigned long long* cellmax, const double* trig, const uint8_t* grids, PassOut* po, int* angsums) {
   __shared__ double s_tmp[16];
   __shared__ int s_list[YSM_TIE_CAP];
   __shared__ int s_sorted[YSM_TIE_CAP];
@@ -1048,12 +1140,9 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
   __shared__ double s_acc[4];
   __shared__ int s_n, s_first;
 
-  const int pid = pass_base + blockIdx.x;
-  const PassDev ps = passes[pid];
   const double* pr = resp + ps.sums_off;
   const int nposes = ps.nX * ps.nY * ps.nA;
   const int tid = threadIdx.x;
-  PassOut* po = outs + pid;
   if (nposes == 0) {  // speculative fine pass whose coarse pass did not end in a single winner
     if (tid == 0) {
       po->best = 0.0; po->avg_x = 0.0; po->avg_y = 0.0; po->tx = 0.0; po->ty = 0.0;
@@ -1065,11 +1154,28 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
   if (tid == 0) s_count = 0;
   // best response: accumulated by the sweep kernels (max over all poses; Karto's init of -1
   // never survives because every pass has at least one pose and responses are >= 0)
-  const double best = passmax[pid];
   __syncthreads();
 
+  // per-cell maxima of a coarse pass (accumulated by the sweep): only cells whose maximum is within
+  // the tie tolerance of the best can hold a tied pose, and the maxima ARE the search-space probs
+  const unsigned long long* cm = (!ps.fine && cellmax && ps.cmax_off >= 0) ? cellmax + ps.cmax_off : nullptr;
+  if (cm) {
+    const int ncell = ps.nX * ps.nY;
+    for (int c = tid; c < ncell; c += blockDim.x) {
+      const double m = __longlong_as_double((long long)__ldcg(cm + c));
+      if (m >= best - YSM_KT_TOLERANCE) {
+        const double* pc = pr + (size_t)c * ps.nA;
+        for (int a = 0; a < ps.nA; a++) {
+          if (kt_double_equal(pc[a], best)) {
+            const int pos = atomicAdd(&s_count, 1);
+            if (pos < YSM_TIE_CAP) s_list[pos] = c * ps.nA + a;
+          }
+        }
+      }
+    }
+  }
   // poses tied with the best, in storage order (loads batched 4 deep to overlap L2 latency)
-  for (int i0 = tid; i0 < nposes; i0 += 4 * blockDim.x) {
+  for (int i0 = tid; i0 < (cm ? 0 : nposes); i0 += 4 * blockDim.x) {
     double r[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -1164,25 +1270,6 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
     po->ty = n > 0 ? s_acc[3] / cnt : 0.0;
     po->n_ties = n;
     po->first_idx = s_first;
-    if (ps.spec >= 0) {
-      // latency path: point the speculative fine pass at this pass's winner. Valid only for a
-      // single winning pose with a non-zero response (then MatchScan goes straight to the fine
-      // pass, its centre is that lattice pose and the heading atan2(sin, cos) the host tabulated);
-      // otherwise the host reschedules the match through the general path.
-      PassDev* f = passes + ps.spec;
-      TableDev* ft = tables + f->table;
-      if (n == 1 && best > YSM_KT_TOLERANCE) {
-        const int a = s_first % ps.nA;
-        f->cx = avg_x;
-        f->cy = avg_y;
-        f->ch = trig[ps.spec_h_off + a];
-        f->htrig_off = ps.spec_htrig_off + a * ps.spec_nAf;
-        ft->trig_off = ps.spec_trig_off + a * ps.spec_nAf;
-      } else {
-        f->nA = 0;
-        ft->nA = 0;
-      }
-    }
   }
   if (!ps.fine) {
     // ComputePositionalCovariance accumulators over the (y, x) lattice; probs(x, y) is the
@@ -1194,17 +1281,21 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
       for (int c = tid; c < ncell; c += blockDim.x) {
         const int iy = c / ps.nX, ix = c - iy * ps.nX;
         double pm = 0.0;  // probs grid is cleared to 0 and max'ed with every response
-        const double* pc = pr + (size_t)c * ps.nA;
-        int a = 0;
-        for (; a + 4 <= ps.nA; a += 4) {
-          const double r0 = pc[a], r1 = pc[a + 1], r2 = pc[a + 2], r3 = pc[a + 3];
-          const double m01 = r0 > r1 ? r0 : r1, m23 = r2 > r3 ? r2 : r3;
-          const double m = m01 > m23 ? m01 : m23;
-          pm = m > pm ? m : pm;
-        }
-        for (; a < ps.nA; a++) {
-          const double r = pc[a];
-          pm = r > pm ? r : pm;
+        if (cm) {
+          pm = __longlong_as_double((long long)__ldcg(cm + c));
+        } else {
+          const double* pc = pr + (size_t)c * ps.nA;
+          int a = 0;
+          for (; a + 4 <= ps.nA; a += 4) {
+            const double r0 = pc[a], r1 = pc[a + 1], r2 = pc[a + 2], r3 = pc[a + 3];
+            const double m01 = r0 > r1 ? r0 : r1, m23 = r2 > r3 ? r2 : r3;
+            const double m = m01 > m23 ? m01 : m23;
+            pm = m > pm ? m : pm;
+          }
+          for (; a < ps.nA; a++) {
+            const double r = pc[a];
+            pm = r > pm ? r : pm;
+          }
         }
         if (pm >= (best - 0.1)) {
           const double x = startX + (double)ix * ps.resx;
@@ -1230,7 +1321,6 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
       const int gx = world_to_grid1(avg_x, ps.gox, g.scale) + g.border;
       const int gy = world_to_grid1(avg_y, ps.goy, g.scale) + g.border;
       const int base = gx + gy * g.stride;
-      const TableDev tb = tables[ps.table];
       const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
       const unsigned dsz = (unsigned)g.data_size;
       const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -1249,6 +1339,266 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
       }
     }
   }
+}
+
+// latency path: point the speculative fine pass of coarse pass `ps` at its winner (result *po).
+// Valid only for a single winning pose with a non-zero response (then MatchScan goes straight to
+// the fine pass, its centre is that lattice pose and the heading the atan2(sin, cos) the host
+// tabulated); otherwise nA = 0 and the host reschedules the match through the general path.
+__device__ __forceinline__ void spec_resolve(const PassDev& ps, const PassOut& po, const double* trig, PassDev* f,
+                                             TableDev* ft) {
+  if (po.n_ties == 1 && po.best > YSM_KT_TOLERANCE) {
+    const int a = po.first_idx % ps.nA;
+    f->cx = po.avg_x;
+    f->cy = po.avg_y;
+    f->ch = trig[ps.spec_h_off + a];
+    f->htrig_off = ps.spec_htrig_off + a * ps.spec_nAf;
+    ft->trig_off = ps.spec_trig_off + a * ps.spec_nAf;
+  } else {
+    f->nA = 0;
+    ft->nA = 0;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+k_reduce(GridC g, PassDev* passes, TableDev* tables,
+         const int* __restrict__ offsets, const double* __restrict__ resp,
+         const double* __restrict__ passmax, const unsigned long long* __restrict__ cellmax,
+         const double* __restrict__ trig, const uint8_t* __restrict__ grids, PassOut* __restrict__ outs,
+         int* __restrict__ angsums, int pass_base) {
+  const int pid = pass_base + blockIdx.x;
+  const PassDev ps = passes[pid];
+  const TableDev tb = tables[ps.table];
+  reduce_body(g, ps, tb, offsets, resp, passmax[pid], cellmax, trig, grids, outs + pid, angsums);
+  if (ps.spec >= 0 && threadIdx.x == 0) {
+    PassDev* f = passes + ps.spec;
+    spec_resolve(ps, outs[pid], trig, f, tables + f->table);  // thread 0 wrote outs[pid] itself
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KL  latency path: ONE cooperative kernel runs a whole MatchScan for a handful of matches --
+// P0 pull the staging blob (points, descriptors, pass tables) from mapped host memory,
+// P1 FindValidPoints (+ the ordered-stamp filter), P2 tile stamping, P3 the coarse lattice sweep
+// with ComputeOffsets fused, P4 per match: reduce -> resolve the fine pass at the winner ->
+// fine offsets -> fine sweep -> reduce, results and a completion flag written straight to
+// mapped host memory (the host polls the flag: no copy engine, no stream synchronisation).
+// Phases are separated by grid-wide barriers; every phase is the body of the stand-alone kernel.
+// ---------------------------------------------------------------------------------------------
+// cooperative copy of a descriptor another CTA of the same kernel just rewrote (L2 reads: the L1 of
+// this SM may still hold the line from an earlier phase)
+template <typename T>
+__device__ __forceinline__ void load_struct_cg(T* dst_smem, const T* src, int tid) {
+  static_assert(sizeof(T) % 8 == 0, "descriptor size");
+  if (tid < (int)(sizeof(T) / 8))
+    reinterpret_cast<unsigned long long*>(dst_smem)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(src) + tid);
+}
+
+// fine CorrelateScan sweep of ONE angle of pass f by one CTA: the angle's lookup offsets go to shared
+// memory (and to the table row the angular covariance reads later), then one warp per (x, y) pose
+__device__ __forceinline__ void
+fine_angle_body(const GridC& g, const PenaltyC& pen, const PassDev& f, const TableDev& ft, int fid, int a,
+                const double* trig, const double* pool, int* offsets_tab, const uint8_t* grids, double* resp,
+                double* passmax, int* s_off) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const double cosine = trig[2 * (ft.trig_off + a)], sine = trig[2 * (ft.trig_off + a) + 1];
+  int* row = offsets_tab + ft.out_off + (size_t)a * ft.Ppad;
+  for (int p = tid; p < ft.P; p += blockDim.x) {
+    const double2 w = *reinterpret_cast<const double2*>(pool + 2 * (size_t)(ft.q_start + p));
+    int gx, gy;
+    offset_cell(ft, g.scale, w.x, w.y, cosine, sine, gx, gy);
+    const int o = gx + gy * g.stride;
+    s_off[p] = o;
+    row[p] = o;
+  }
+  __syncthreads();
+  const uint8_t* grid = grids + (size_t)f.slot * g.grid_bytes;
+  const unsigned dsz = (unsigned)g.data_size;
+  const int nxy = f.nX * f.nY;
+  for (int c = warp; c < nxy; c += nwarps) {
+    const int iy = c / f.nX, ix = c - iy * f.nX;
+    const double x = -f.offx + (double)ix * f.resx;
+    const double y = -f.offy + (double)iy * f.resy;
+    const int gx = world_to_grid1(f.cx + x, f.gox, g.scale) + g.border;
+    const int gy = world_to_grid1(f.cy + y, f.goy, g.scale) + g.border;
+    const int base = gx + gy * g.stride;
+    unsigned sum = 0;
+    for (int p0 = lane; p0 < f.P; p0 += 256) {
+      unsigned idx[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) idx[u] = (p0 + 32 * u < f.P) ? (unsigned)(base + s_off[p0 + 32 * u]) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (idx[u] < dsz) sum += (unsigned)__ldg(grid + idx[u]);
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+      const double rr = response_of(f, pen, sum, ix, iy, a);
+      resp[f.sums_off + (size_t)c * f.nA + a] = rr;
+      pass_max_update(passmax, fid, rr);
+    }
+  }
+}
+
+struct SmallArgs {
+  const uint4* blob_src;  // mapped host memory
+  uint4* blob_dst;        // device copy
+  int blob_vec;           // 16-byte units
+  int pool_in_blob;
+  const double* pool_dev; // caller's device pool when not in the blob
+  unsigned o_pool, o_scan_start, o_scan_count, o_matches, o_base, o_workcount, o_tab, o_pass, o_pa, o_trig, o_pmax;
+  int nw, npa, ncoarse, nspec, nAf;
+  int pmax, nbase_max, stage, fv_warps, ordered, log2cap;
+  int tpc, psplit, task_chunks;
+  uint32_t* ptcell;
+  uint32_t* cells;
+  int* cellcount;
+  uint2* gbox;
+  int2* work;
+  const uint8_t* kernel;
+  uint8_t* grids;
+  uint32_t* rowmask;
+  int rm_words;
+  int epoch;
+  int* offsets;
+  double* resp;
+  unsigned long long* cellmax;
+  int cellmax_n;          // elements to zero
+  PassOut* outs_host;     // mapped host memory
+  int* angs_host;         // mapped host memory
+  volatile int* flags_host;  // mapped host memory: flags_host[pid] = epoch when pass pid's results are visible
+  unsigned long long* tstamps;  // optional (tracing): %globaltimer at the phase boundaries, CTA 0
+};
+
+__global__ void __launch_bounds__(512, 2)
+k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ PassOut s_po[2];
+  __shared__ PassDev s_f;
+  __shared__ TableDev s_ft;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#define YSM_TSTAMP(k)                                                                  \
+  if (A.tstamps && blockIdx.x == 0 && tid == 0) {                                      \
+    unsigned long long t_;                                                             \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    A.tstamps[k] = t_;                                                                 \
+  }
+  YSM_TSTAMP(0)
+  // ---- P0: staging blob, host -> device ---------------------------------------------------------
+  for (int i = blockIdx.x * blockDim.x + tid; i < A.blob_vec; i += gridDim.x * blockDim.x) A.blob_dst[i] = A.blob_src[i];
+  for (int i = blockIdx.x * blockDim.x + tid; i < A.cellmax_n; i += gridDim.x * blockDim.x) A.cellmax[i] = 0ull;
+  grid.sync();
+  YSM_TSTAMP(1)
+  unsigned char* db = reinterpret_cast<unsigned char*>(A.blob_dst);
+  const double* pool = A.pool_in_blob ? reinterpret_cast<const double*>(db + A.o_pool) : A.pool_dev;
+  const int* scan_start = reinterpret_cast<const int*>(db + A.o_scan_start);
+  const int* scan_count = reinterpret_cast<const int*>(db + A.o_scan_count);
+  const MatchDev* matches = reinterpret_cast<const MatchDev*>(db + A.o_matches);
+  const int* base_idx = reinterpret_cast<const int*>(db + A.o_base);
+  int* work_count = reinterpret_cast<int*>(db + A.o_workcount);
+  TableDev* tables = reinterpret_cast<TableDev*>(db + A.o_tab);
+  PassDev* passes = reinterpret_cast<PassDev*>(db + A.o_pass);
+  const PassAngle* pa_list = reinterpret_cast<const PassAngle*>(db + A.o_pa);
+  const double* trig = reinterpret_cast<const double*>(db + A.o_trig);
+  double* passmax = reinterpret_cast<double*>(db + A.o_pmax);
+  // ---- P1: FindValidPoints ------------------------------------------------------------------------
+  for (int vb = blockIdx.x; vb < A.nw; vb += gridDim.x) {
+    find_valid_body(g, matches, base_idx, scan_start, scan_count, pool, A.ptcell, A.cells, A.cellcount, A.gbox, A.work,
+                    work_count, A.pmax, A.nbase_max, A.stage, vb, dsm, A.fv_warps);
+    __syncthreads();
+    if (A.ordered) {
+      if (warp == 0) stamp_order_body(matches, A.cells, A.cellcount, A.log2cap, vb, lane, reinterpret_cast<uint32_t*>(dsm));
+      __syncthreads();
+    }
+  }
+  YSM_TSTAMP(2)
+  grid.sync();
+  YSM_TSTAMP(3)
+  // ---- P2: SmearPoint ---------------------------------------------------------------------------------
+  tile_stamp_body(g, matches, A.cells, A.cellcount, A.gbox, A.work, work_count, A.kernel, A.grids, A.rowmask,
+                  A.rm_words, (int)blockIdx.x, (int)gridDim.x, dsm);
+  YSM_TSTAMP(4)
+  grid.sync();
+  YSM_TSTAMP(5)
+  // ---- P3: coarse CorrelateScan sweep -----------------------------------------------------------------
+  const int nv = A.npa * A.task_chunks;
+  for (int v = blockIdx.x; v < nv; v += gridDim.x) {
+    sweep_lattice_body(g, pen, passes, pa_list, tables, nullptr, trig, pool, A.grids, A.resp, passmax, A.cellmax,
+                       A.tpc, A.psplit, v % A.npa, v / A.npa, reinterpret_cast<int*>(dsm));
+    __syncthreads();
+  }
+  YSM_TSTAMP(6)
+  grid.sync();
+  YSM_TSTAMP(7)
+  // ---- P4a: per coarse pass: reduce, resolve its fine pass at the winner ------------------------------
+  const int nw8 = (int)(sizeof(PassOut) / 8);
+  for (int pid = blockIdx.x; pid < A.ncoarse; pid += gridDim.x) {
+    const PassDev ps = passes[pid];
+    const TableDev tb = tables[ps.table];
+    reduce_body(g, ps, tb, A.offsets, A.resp, __ldcg(passmax + pid), A.cellmax, trig, A.grids, &s_po[0], A.angs_host);
+    __syncthreads();
+    if (tid < nw8) reinterpret_cast<double*>(A.outs_host + pid)[tid] = reinterpret_cast<const double*>(&s_po[0])[tid];
+    if (ps.spec >= 0) {
+      if (tid == 0) {
+        s_f = passes[ps.spec];
+        s_ft = tables[s_f.table];
+        spec_resolve(ps, s_po[0], trig, &s_f, &s_ft);
+      }
+      __syncthreads();
+      // publish the resolved descriptors for the CTAs of the next phases
+      if (tid < (int)(sizeof(PassDev) / 8))
+        reinterpret_cast<unsigned long long*>(passes + ps.spec)[tid] = reinterpret_cast<const unsigned long long*>(&s_f)[tid];
+      if (tid >= 32 && tid < 32 + (int)(sizeof(TableDev) / 8))
+        reinterpret_cast<unsigned long long*>(tables + s_f.table)[tid - 32] =
+            reinterpret_cast<const unsigned long long*>(&s_ft)[tid - 32];
+      __threadfence();
+    } else {
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence_system();
+        A.flags_host[pid] = A.epoch;
+      }
+    }
+    __syncthreads();
+  }
+  YSM_TSTAMP(8)
+  grid.sync();
+  YSM_TSTAMP(9)
+  // ---- P4b: fine sweep, CTA = (fine pass, angle) -----------------------------------------------------
+  for (int v = blockIdx.x; v < A.nspec * A.nAf; v += gridDim.x) {
+    const int fid = A.ncoarse + v / A.nAf, a = v % A.nAf;
+    load_struct_cg(&s_f, passes + fid, tid);
+    __syncthreads();
+    load_struct_cg(&s_ft, tables + s_f.table, tid);
+    __syncthreads();
+    if (a < s_f.nA)
+      fine_angle_body(g, pen, s_f, s_ft, fid, a, trig, pool, A.offsets, A.grids, A.resp, passmax, reinterpret_cast<int*>(dsm));
+    __syncthreads();
+  }
+  YSM_TSTAMP(10)
+  grid.sync();
+  YSM_TSTAMP(11)
+  // ---- P4c: per fine pass: reduce + angular covariance sums, publish --------------------------------
+  for (int fi = blockIdx.x; fi < A.nspec; fi += gridDim.x) {
+    const int fid = A.ncoarse + fi;
+    load_struct_cg(&s_f, passes + fid, tid);
+    __syncthreads();
+    load_struct_cg(&s_ft, tables + s_f.table, tid);
+    __syncthreads();
+    reduce_body(g, s_f, s_ft, A.offsets, A.resp, __ldcg(passmax + fid), A.cellmax, trig, A.grids, &s_po[1], A.angs_host);
+    __syncthreads();
+    if (tid < nw8) reinterpret_cast<double*>(A.outs_host + fid)[tid] = reinterpret_cast<const double*>(&s_po[1])[tid];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      A.flags_host[fid] = A.epoch;
+    }
+    __syncthreads();
+  }
+  YSM_TSTAMP(12)
+#undef YSM_TSTAMP
 }
 
 // ---------------------------------------------------------------------------------------------

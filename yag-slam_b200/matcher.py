@@ -82,7 +82,7 @@ class ScanMatcherB200(object):
         self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
                          "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
-                         "speculative_fine_passes", "lanes"),
+                         "speculative_fine_passes", "lanes", "latency_kernel_launches"),
                         (int(x) for x in v)))
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
