@@ -128,6 +128,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_cores():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would starve the CPU arm: the thread count is taken from the affinity mask instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(cfg, b, n_sample, n_threads):
     """Oracle timed on the first n_sample matches of the workload (checker used as the CPU arm)."""
     from oracle import oracle
@@ -144,9 +153,8 @@ def run_reference(args, rank, world):
     of it on the host cores, all threads, on a bounded sample of the same workload per step."""
     if rank != 0:
         return
-    from oracle import oracle
     b = make_workload(args, 0)
-    cores = oracle.max_threads()
+    cores = host_cores()
     # calibrate the per-step sample to ~3 s of wall clock
     dt, _ = cpu_sample(None, b, min(args.matches, 2 * cores), cores)
     rate = (2 * cores) / max(dt, 1e-6)
@@ -269,13 +277,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- p50 single-match latency through the public API ----------------------------------------
     lat = {}
     if rank == 0 and not args.no_latency:
-        lat = latency_probe(local_rank)
+        lat = latency_probe(local_rank, with_cpu=(world == 1 and not args.no_cpu))
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle
-        cores = oracle.max_threads()
+        cores = host_cores()
         dt, ref = cpu_sample(None, b, min(n, 8 * cores), cores)
         n_sample = int(max(cores, min(n, (8 * cores / max(dt, 1e-6)) * 12.0)))
         dt, ref = cpu_sample(None, b, n_sample, cores)
@@ -327,9 +334,10 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(out))
 
 
-def latency_probe(device):
+def latency_probe(device, with_cpu=False):
     """p50 of single match_scan calls through the reference-facing API (Wrapper.match_scan):
-    cfg 1 (360 beams, 1 base scan) and cfg 2 shape (720 beams, 10 running scans)."""
+    cfg 1 (360 beams, 1 base scan) and cfg 2 shape (720 beams, 10 running scans). with_cpu: the
+    same single queries on the CPU oracle, one thread (the cpu_baseline leg)."""
     from yag_slam_b200 import karto_compat as kc
     from yag_slam_b200 import synth
     world = synth.make_world()
@@ -358,6 +366,21 @@ def latency_probe(device):
         ts = np.array(ts) * 1e6
         out["p50_latency_us_" + name] = float(np.percentile(ts, 50))
         out["p99_latency_us_" + name] = float(np.percentile(ts, 99))
+        if with_cpu:
+            from oracle.oracle import KartoOracle
+            o = KartoOracle(None)
+            qp, bp = q.point_readings(), [s.point_readings() for s in scans]
+            pose = q.sensor_pose()
+            cts = []
+            for _ in range(12):
+                t0 = time.perf_counter()
+                ref = o.match(qp, pose, bp, True, True)
+                cts.append(time.perf_counter() - t0)
+            r = w.match_scan(q, scans, True, True)
+            exact = (r.response == ref[0] and (r.best_pose.x, r.best_pose.y, r.best_pose.yaw) == ref[1])
+            out["cpu_p50_latency_us_" + name] = float(np.percentile(np.array(cts[2:]) * 1e6, 50))
+            out["latency_speedup_" + name] = out["cpu_p50_latency_us_" + name] / out["p50_latency_us_" + name]
+            out["latency_result_bit_exact_" + name] = bool(exact)
     return out
 
 

@@ -228,7 +228,7 @@ struct PassPlan {
 
 // byte layout of one staging blob (host pinned mirror == device copy)
 struct BlobLayout {
-  size_t pool = 0, scan_start = 0, scan_count = 0, matches = 0, base = 0, workcount = 0;  // wave-static part
+  size_t pool = 0, scan_start = 0, scan_count = 0, matches = 0, base = 0, workcount = 0, scanlist = 0;  // wave-static part
   size_t tab = 0, pass = 0, pa = 0, fine = 0, trig = 0, pmax = 0, total = 0;
 };
 
@@ -258,7 +258,7 @@ struct ysm_handle {
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
   DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
-  DevBuf d_wblob, d_cellmax;
+  DevBuf d_wblob, d_cellmax, d_scan_emit, d_tileflag;
   PinBuf h_blob, h_wblob, h_outs, h_angsums, h_flags;
   int epoch = 0;           // completion-flag value of the current latency-kernel launch
   size_t mega_smem_attr = 0;
@@ -496,7 +496,8 @@ extern "C" void ysm_destroy(ysm_handle* h) {
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
                     &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
-                    &h->d_angsums, &h->d_blob, &h->d_wblob, &h->d_cellmax};
+                    &h->d_angsums, &h->d_blob, &h->d_wblob, &h->d_cellmax, &h->d_scan_emit,
+                    &h->d_tileflag};
   for (DevBuf* b : bufs) b->release();
   h->h_blob.release();
   h->h_wblob.release();
@@ -730,6 +731,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
   std::vector<MatchState> states;
   std::vector<MatchDev> hm;
   std::vector<int> hbase;
+  std::vector<ScanRef> hscans;  // latency path: one entry per (match, base scan)
   PassPlan& pl = h->plan;
 
   h->last_slot_of_match.assign(b->n_matches, -1);
@@ -747,6 +749,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     states.assign(nw, MatchState());
     hm.assign(nw, MatchDev());
     hbase.clear();
+    hscans.clear();
     long long cells_total = 0, gbox_total = 0, work_cap = 0, max_match_cells = 1;
     int nbase_max = 1;
     for (int i = 0; i < nw; i++) {
@@ -776,6 +779,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       if (s.P > 0) {
         for (int k = b->base_ptr[mi]; k < b->base_ptr[mi + 1]; k++) {
           hbase.push_back(b->base_idx[k]);
+          if (small) hscans.push_back(ScanRef{i, k - b->base_ptr[mi], (int)mc, 0});
           mc += b->scan_count[b->base_idx[k]];
         }
       }
@@ -1030,6 +1034,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         L.matches = o; o = a16(o + sizeof(MatchDev) * (size_t)nw);
         L.base = o; o = a16(o + hbase.size() * 4);
         L.workcount = o; o = a16(o + 16);
+        if (small) { L.scanlist = o; o = a16(o + sizeof(ScanRef) * hscans.size()); }
       }
       if (with_passes) {
         L.tab = o; o = a16(o + sizeof(TableDev) * pl.tab.size());
@@ -1054,6 +1059,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         memcpy(p + L.matches, hm.data(), sizeof(MatchDev) * (size_t)nw);
         if (!hbase.empty()) memcpy(p + L.base, hbase.data(), hbase.size() * 4);
         memset(p + L.workcount, 0, 16);
+        if (small && !hscans.empty()) memcpy(p + L.scanlist, hscans.data(), sizeof(ScanRef) * hscans.size());
       }
       if (with_passes) {
         memcpy(p + L.tab, pl.tab.data(), sizeof(TableDev) * pl.tab.size());
@@ -1086,7 +1092,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     // ---- K1: grid build ------------------------------------------------------------------------
     auto launch_build = [&]() -> int {
       if (timing) CK(cudaEventRecord(h->ev[0], st));
-      const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
+      const size_t bits_bytes = (size_t)((tiles_per_grid + 3) / 4) * 4;  // one byte per tile
       const size_t fixed = 16 * (size_t)nbase_max + bits_bytes;
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
       int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
@@ -1163,19 +1169,13 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       const char* db = nullptr;
       // latency path, first iteration: everything in ONE cooperative kernel (k_match_small)
       bool mega = !built && small && !timing && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
-                  !pl.pa.empty() && pl.fine.empty();
+                  !pl.pa.empty() && pl.fine.empty() && nbase_max <= 64 && hscans.size() <= 512;
       int mega_tpc = 0, mega_psplit = 1, mega_chunks = 0, mega_stage = 0, mega_fvw = 0, mega_log2cap = 6;
       size_t mega_smem = 0;
       if (mega) {
         // phase shapes for a 512-thread CTA (16 warps)
-        mega_fvw = std::min(16, std::max(1, nbase_max));
-        const size_t bits_bytes = (size_t)((tiles_per_grid + 31) / 32) * 4;
-        size_t fv = (size_t)mega_fvw * 4 * pmax + 16 * (size_t)nbase_max + bits_bytes;
-        const size_t fv_pts = ((fv + 15) & ~(size_t)15) + (size_t)mega_fvw * 16 * pmax;
-        if (fv_pts <= 100 * 1024) {
-          fv = fv_pts;
-          mega_stage = 1;
-        }
+        const size_t fv = fv_scan_smem(pmax);
+        (void)mega_fvw; (void)mega_stage;
         size_t so = 0;
         if (h->ordered_stamps) {
           while ((1ll << mega_log2cap) < 2 * max_match_cells) mega_log2cap++;
@@ -1268,6 +1268,13 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         A.o_matches = (unsigned)L.matches; A.o_base = (unsigned)L.base; A.o_workcount = (unsigned)L.workcount;
         A.o_tab = (unsigned)L.tab; A.o_pass = (unsigned)L.pass; A.o_pa = (unsigned)L.pa; A.o_trig = (unsigned)L.trig;
         A.o_pmax = (unsigned)L.pmax;
+        A.o_scanlist = (unsigned)L.scanlist;
+        A.nscans_total = (int)hscans.size();
+        A.tiles_per_grid = (tiles_per_grid + 3) & ~3;
+        CK(h->d_scan_emit.ensure(std::max<size_t>(16, hscans.size() * 4)));
+        CK(h->d_tileflag.ensure((size_t)nw * A.tiles_per_grid + 16));
+        A.scan_emit = (int*)h->d_scan_emit.p;
+        A.tileflag = (unsigned char*)h->d_tileflag.p;
         A.nw = nw; A.npa = (int)pl.pa.size(); A.ncoarse = ncoarse_total; A.nspec = nspec; A.nAf = std::max(1, nAf);
         A.pmax = pmax; A.nbase_max = nbase_max; A.stage = mega_stage; A.fv_warps = mega_fvw;
         A.ordered = h->ordered_stamps ? 1 : 0; A.log2cap = mega_log2cap;
@@ -1315,10 +1322,12 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         tr.mark("poll");
         if (ts_host) {
           cudaStreamSynchronize(st);
-          static const char* names[] = {"P0 blob copy", "P1 find_valid", "sync", "P2 stamp", "sync", "P3 sweep", "sync",
+          static const char* names[] = {"P0 blob copy", "P1a+P1b", "sync", "P2 stamp", "sync", "P3 sweep", "sync",
                                         "P4a reduce", "sync", "P4b fine sweep", "sync", "P4c fine reduce"};
           for (int k = 0; k < 12; k++)
             fprintf(stderr, "[ysm-kernel] %-14s %8.1f us\n", names[k], (double)(ts_host[k + 1] - ts_host[k]) * 1e-3);
+          fprintf(stderr, "[ysm-kernel]   P1a scans %.1f us, sync %.1f us, P1b %.1f us\n", (double)(ts_host[13] - ts_host[1]) * 1e-3,
+                  (double)(ts_host[14] - ts_host[13]) * 1e-3, (double)(ts_host[2] - ts_host[14]) * 1e-3);
         }
       } else {
       // ---- K2 offsets (tables of the passes the host scheduled) ------------------------------------

@@ -103,6 +103,15 @@ __device__ __forceinline__ uint32_t vmax4_lt128(uint32_t a, uint32_t b) {
 // memory pointer chase), then every segment [t_k, t_k+1) is kept iff the side test ss >= 0
 // (parallel). Output: the match's occupied cells in Karto's processing order.
 // ---------------------------------------------------------------------------------------------
+__device__ unsigned long long g_fv_ts[16];  // developer tracing: %globaltimer inside find_valid (CTA 0, thread 0)
+__device__ int g_fv_trace = 0;
+#define YSM_FVTS(k)                                                        \
+  if (g_fv_trace && vbx == 0 && threadIdx.x == 0) {                        \
+    unsigned long long t_;                                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                 \
+    g_fv_ts[k] = t_;                                                       \
+  }
+
 __device__ __forceinline__ void
 find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, const int* scan_start,
                 const int* scan_count, const double* pool, uint32_t* pt_cell, uint32_t* cells, int* cell_count,
@@ -116,13 +125,15 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
   unsigned short* s_trig = s_next + pmax;
   int* s_scan_emit = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * 4 * pmax);  // [nbase_max]
   int* s_dir = s_scan_emit + nbase_max;  // [3][nbase_max]: point count, pool start, prefix of counts of the base scans
-  unsigned* s_bits = reinterpret_cast<unsigned*>(s_dir + 3 * nbase_max);           // touched-tile bitmap
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_dir + 3 * nbase_max);           // touched-tile flags, one BYTE per tile
+  unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_bits);                // (plain stores: no atomics)
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int nbitw = (tnx * tnx + 31) >> 5;
+  const int nbitw = (tnx * tnx + 3) >> 2;  // words of 4 flags
   // small waves: each warp stages its scan's points in shared memory (SoA) so the filter's
   // dependent loads are LDS instead of L2 round trips
   double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 16 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
   double* s_py = s_px + pmax;
+  YSM_FVTS(0)
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) s_bits[i] = 0u;
   if (threadIdx.x == 0) s_tile_total = 0;
   __syncthreads();
@@ -148,6 +159,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     }
   }
   __syncthreads();
+  YSM_FVTS(1)
   for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
     const int off = s_dir[2 * nbase_max + b];
     const int n = s_dir[b];
@@ -174,6 +186,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
         s_next[i] = (unsigned short)j;
       }
       __syncwarp();
+      YSM_FVTS(2)
       int ntrig = 0;
       if (lane == 0) {
         int t = 0;
@@ -184,6 +197,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       }
       ntrig = __shfl_sync(0xffffffffu, ntrig, 0);
       __syncwarp();
+      YSM_FVTS(3)
       for (int k = lane; k < ntrig - 1; k += 32) {
         const int f = s_trig[k], c = s_trig[k + 1];
         const double fx = YSM_PX(f), fy = YSM_PY(f);
@@ -207,8 +221,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
                 const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
                 for (int ty = ty0; ty <= ty1; ty++)
                   for (int tx = tx0; tx <= tx1; tx++) {
-                    const int t = ty * tnx + tx;
-                    atomicOr(&s_bits[t >> 5], 1u << (t & 31));
+                    s_flag[ty * tnx + tx] = 1;
                   }
               }
             }
@@ -219,8 +232,10 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     for (int o = 16; o > 0; o >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
     if (lane == 0) s_scan_emit[b] = emitted;
     __syncwarp();
+    YSM_FVTS(4)
   }
   __syncthreads();
+  YSM_FVTS(5)
   // ordered compaction (scan order, then point order)
   for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
     int dst = 0;
@@ -237,6 +252,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       dst += __popc(bal);
     }
   }
+  YSM_FVTS(6)
   int tot = 0;
   for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
   if (threadIdx.x == 0) cell_count[vbx] = tot;
@@ -254,11 +270,12 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     if (!b) continue;
     int pos = s_tile_base + atomicAdd(&s_tile_total, __popc(b));
     while (b) {
-      const int bit = __ffs(b) - 1;
+      const int bit = __ffs(b) - 1;  // flags are 0 / 1: bit 8k set <=> flag k
       b &= b - 1;
-      work[pos++] = make_int2(vbx, i * 32 + bit);
+      work[pos++] = make_int2(vbx, i * 4 + (bit >> 3));
     }
   }
+  YSM_FVTS(7)
   // bounding box of every group of 32 consecutive cells (scan order keeps them spatially close)
   __threadfence_block();
   const uint32_t* mcells = cells + m.cells_off;
@@ -277,6 +294,203 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
     }
     if (lane == 0) gbox[m.gbox_off + (g0 >> 5)] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
+  }
+  YSM_FVTS(8)
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a (latency path)  FindValidPoints with a whole CTA per base scan, then a CTA per match.
+// fv_scan_body: points staged in shared memory; next[i] in parallel; the trigger chain
+// 0 -> next[0] -> ... is found by pointer doubling (log2 n rounds) instead of a serial walk; every
+// point finds its trigger by stepping back, evaluates the side test and its cell; touched tiles are
+// flagged with plain byte stores; ordered block-wide compaction into the scan's region.
+// fv_match_body: concatenates the scans' cells in scan order, bounding boxes, (match, tile) work list.
+// ---------------------------------------------------------------------------------------------
+struct ScanRef {
+  int match, b, off, pad;  // match of the wave, base-scan ordinal, prefix of the point counts inside the match
+};
+
+__host__ __device__ __forceinline__ size_t fv_scan_smem(int pmax) {
+  return ((size_t)pmax * (8 + 8 + 2 + 2 + 2 + 1 + 1) + 256 + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void
+fv_scan_body(const GridC& g, const MatchDev* matches, const int* base_idx, const int* scan_start,
+             const int* scan_count, const double* pool, const ScanRef& sr, uint32_t* pt_cell, int* scan_emit, int v,
+             unsigned char* tileflag, int tiles_per_grid, int pmax, unsigned char* dsm) {
+  __shared__ int s_wtot[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  double* s_px = reinterpret_cast<double*>(dsm);
+  double* s_py = s_px + pmax;
+  unsigned short* s_next = reinterpret_cast<unsigned short*>(s_py + pmax);
+  unsigned short* s_ja = s_next + pmax;
+  unsigned short* s_jb = s_ja + pmax;
+  unsigned char* s_mark = reinterpret_cast<unsigned char*>(s_jb + pmax);
+  const MatchDev m = matches[sr.match];
+  const int s = base_idx[m.base_begin + sr.b];
+  const int n = scan_count[s];
+  const double* pts = pool + 2 * (size_t)scan_start[s];
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const double msd = 0.1 * 0.1;  // math::Square(0.1)
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double2 w = *reinterpret_cast<const double2*>(pts + 2 * (size_t)i);
+    s_px[i] = w.x;
+    s_py[i] = w.y;
+    s_mark[i] = i == 0;
+  }
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double fx = s_px[i], fy = s_py[i];
+    int j = i + 1;
+    while (j < n) {
+      const double dx = fx - s_px[j], dy = fy - s_py[j];
+      if (dx * dx + dy * dy > msd) break;
+      j++;
+    }
+    s_next[i] = (unsigned short)j;
+    s_ja[i] = (unsigned short)j;
+  }
+  __syncthreads();
+  // reachability from point 0 by pointer doubling: after round k every point within 2^(k+1) - 1 hops is marked
+  unsigned short* ja = s_ja;
+  unsigned short* jb = s_jb;
+  for (int span = 1; span < n; span <<= 1) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int j = ja[i];
+      if (j < n) {
+        if (s_mark[i]) s_mark[j] = 1;
+        jb[i] = ja[j];
+      } else {
+        jb[i] = (unsigned short)n;
+      }
+    }
+    __syncthreads();
+    unsigned short* t = ja; ja = jb; jb = t;
+  }
+  // per point: its trigger, the side test of the trigger's segment, its cell; ordered compaction
+  uint32_t* out = pt_cell + m.cells_off + sr.off;
+  for (int j0 = 0; j0 < n; j0 += blockDim.x) {
+    const int j = j0 + tid;
+    uint32_t cell = YSM_INVALID_CELL;
+    if (j < n) {
+      int f = j;
+      while (!s_mark[f]) f--;
+      const int c = s_next[f];
+      if (c < n) {  // points after the last trigger are never emitted
+        const double fx = s_px[f], fy = s_py[f];
+        const double a = m.vpy - fy;
+        const double b2 = fx - m.vpx;
+        const double cc = fy * m.vpx - fx * m.vpy;
+        const double ss = s_px[c] * a + s_py[c] * b2 + cc;
+        if (!(ss < 0.0)) {
+          const double vx = (s_px[j] - m.gox) * g.scale;
+          const double vy = (s_py[j] - m.goy) * g.scale;
+          if (vx > -1.0 && vy > -1.0 && vx < 1e9 && vy < 1e9) {
+            const int gx = (int)kt_round(vx), gy = (int)kt_round(vy);
+            if (gx >= 0 && gx < g.roi && gy >= 0 && gy < g.roi) {
+              const int ax = gx + g.border, ay = gy + g.border;
+              cell = (uint32_t)ax | ((uint32_t)ay << 16);
+              const int tx0 = (ax - g.half_kernel) / YSM_TILE, tx1 = (ax + g.half_kernel) / YSM_TILE;
+              const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
+              unsigned char* tf = tileflag + (size_t)sr.match * tiles_per_grid;
+              for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) tf[ty * tnx + tx] = 1;
+            }
+          }
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, cell != YSM_INVALID_CELL);
+    if (lane == 0) s_wtot[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; w++) before += s_wtot[w];
+    if (cell != YSM_INVALID_CELL) out[before + __popc(bal & ((1u << lane) - 1u))] = cell;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = s_base;
+      for (int w = 0; w < nwarps; w++) tot += s_wtot[w];
+      s_base = tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) scan_emit[v] = s_base;
+}
+
+// Grid-wide: every CTA rebuilds the (tiny) emit-count prefix of match vbx, then its warps take
+// tasks -- a group of 32 final cells (gathered from the scans' regions, bounding box) or a slice of
+// the tile flags (work-list entries). vblock / nblocks: this CTA's rank among those working on the match.
+__device__ __forceinline__ void
+fv_match_body(const GridC& g, const MatchDev* matches, const ScanRef* scanlist, int nscans_total, const int* scan_emit,
+              const uint32_t* pt_cell, uint32_t* cells, int* cell_count, uint2* gbox, int2* work, int* work_count,
+              const unsigned char* tileflag, int tiles_per_grid, int vbx, int vblock, int nblocks) {
+  __shared__ int s_src[64], s_dst[65], s_first;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const MatchDev m = matches[vbx];
+  if (tid == 0) s_first = nscans_total;
+  __syncthreads();
+  // scans of this match are consecutive in the scan list, in base order
+  if (tid < nscans_total && scanlist[tid].match == vbx) atomicMin(&s_first, tid);
+  __syncthreads();
+  const int v0 = s_first;
+  const int nb = min(64, m.base_end - m.base_begin);
+  if (tid < nb) {
+    s_src[tid] = scanlist[v0 + tid].off;
+    s_dst[tid + 1] = __ldcg(scan_emit + v0 + tid);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s_dst[0] = 0;
+    for (int b = 0; b < nb; b++) s_dst[b + 1] += s_dst[b];
+  }
+  __syncthreads();
+  const int tot = nb > 0 ? s_dst[nb] : 0;
+  if (vblock == 0 && tid == 0) cell_count[vbx] = tot;
+  const int ngroups = (tot + 31) >> 5;
+  const unsigned* tf = reinterpret_cast<const unsigned*>(tileflag + (size_t)vbx * tiles_per_grid);
+  const int nw4 = (tiles_per_grid + 3) >> 2, nflag = (nw4 + 31) >> 5;
+  for (int t = vblock * nwarps + warp; t < ngroups + nflag; t += nblocks * nwarps) {
+    if (t < ngroups) {
+      // 32 consecutive cells of the match (scan order, then point order) + their bounding box
+      const int i = t * 32 + lane;
+      int xlo = 0xFFFF, xhi = 0, ylo = 0xFFFF, yhi = 0;
+      if (i < tot) {
+        int b = 0;
+        while (s_dst[b + 1] <= i) b++;
+        const uint32_t c = __ldcg(pt_cell + m.cells_off + s_src[b] + (i - s_dst[b]));
+        cells[m.cells_off + i] = c;
+        xlo = xhi = (int)(c & 0xFFFFu);
+        ylo = yhi = (int)(c >> 16);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+        yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+      }
+      if (lane == 0) gbox[m.gbox_off + t] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
+    } else {
+      // 32 words of tile flags -> (match, tile) work-list entries
+      const int i = (t - ngroups) * 32 + lane;
+      unsigned b = i < nw4 ? __ldcg(tf + i) : 0u;
+      int cnt = __popc(b), pre = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+      }
+      const int wtot = __shfl_sync(0xffffffffu, pre, 31);
+      int base = 0;
+      if (lane == 0 && wtot) base = atomicAdd(work_count, wtot);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      int pos = base + pre - cnt;
+      while (b) {
+        const int bit = __ffs(b) - 1;  // flags are 0 / 1: bit 8k set <=> flag k
+        b &= b - 1;
+        work[pos++] = make_int2(vbx, i * 4 + (bit >> 3));
+      }
+    }
   }
 }
 
@@ -426,7 +640,11 @@ __host__ __device__ __forceinline__ size_t tile_stamp_smem(int K, int Wk, int nw
 __device__ __forceinline__ void
 tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, const int* cell_count,
                 const uint2* gbox, const int2* work, const int* work_count, const uint8_t* kernel, uint8_t* grids,
-                uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm) {
+                uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm, int S = 1) {
+  // S > 1 (latency path): S warps share one tile -- each scans its share of the cell groups into a
+  // private copy of the tile, the copies are max-combined at write-out (named barrier per group)
+  __shared__ unsigned s_rows[16];
+  if (threadIdx.x < 16) s_rows[threadIdx.x] = 0u;
   const int K = g.K, Wk = g.Wk, h = g.half_kernel;
   const int nks = 4 * K * Wk;
   const int wpb = blockDim.x >> 5;  // warps per block
@@ -448,8 +666,9 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
   uint2* tile = s_tile + (size_t)warp * (YSM_TILE * YSM_TILE / 4);
   uint32_t* list = s_list + (size_t)warp * (YSM_TILE_LIST + 32);
   const int nwork = *work_count;
-  const int nwarps_total = vgx * wpb;
-  for (int wi = vbx * wpb + warp; wi < nwork; wi += nwarps_total) {
+  const int gpc = wpb / S, group = warp / S, sub = warp - group * S;  // tile groups per CTA
+  const int ngroups_total = vgx * gpc;
+  for (int wi = vbx * gpc + group; wi < nwork; wi += ngroups_total) {
     const int2 wk = work[wi];
     const MatchDev m = matches[wk.x];
     const int ncells = cell_count[wk.x];
@@ -462,8 +681,9 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
     for (int k = 0; k < 8; k++) tile[k * 32 + lane] = make_uint2(0u, 0u);
     __syncwarp();
     int n = 0;
-    for (int g0 = 0; g0 < ngroups; g0 += 32) {
+    for (int gs = 0; gs < ngroups; gs += 32 * S) {
       // groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
+      const int g0 = gs + sub * 32;
       bool ghit = false;
       if (g0 + lane < ngroups) {
         const uint2 bb = mb[g0 + lane];
@@ -500,10 +720,16 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
     const int dr = lane >> 3, wd = lane & 7;
     const int gw = (x0t >> 2) + wd;
     uint32_t rows = 0;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
+    if (S > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * S) : "memory");
+    const uint2* copies = s_tile + (size_t)(group * S) * (YSM_TILE * YSM_TILE / 4);
+    for (int k = sub; k < 8; k += S) {
       const int row = y0t + k * 4 + dr;
-      const uint2 tv = tile[(k * 4 + dr) * 8 + wd];
+      uint2 tv = copies[(k * 4 + dr) * 8 + wd];
+      for (int c = 1; c < S; c++) {
+        const uint2 o = copies[(size_t)c * (YSM_TILE * YSM_TILE / 4) + (k * 4 + dr) * 8 + wd];
+        tv.x = __vmaxu2(tv.x, o.x);
+        tv.y = __vmaxu2(tv.y, o.y);
+      }
       const uint32_t v = __byte_perm(tv.x, tv.y, 0x6420);  // u16 lanes -> bytes
       if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
       const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
@@ -511,7 +737,16 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
       for (int d = 0; d < 4; d++)
         if (nz & (0xFFu << (8 * d))) rows |= 1u << (k * 4 + d);
     }
-    if (lane == 0) rowmask[(size_t)m.slot * rm_words + wk.y] = rows;
+    if (S > 1) {
+      if (lane == 0 && rows) atomicOr(&s_rows[group], rows);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * S) : "memory");
+      if (sub == 0 && lane == 0) {
+        rowmask[(size_t)m.slot * rm_words + wk.y] = s_rows[group];
+        s_rows[group] = 0u;
+      }
+    } else if (lane == 0) {
+      rowmask[(size_t)m.slot * rm_words + wk.y] = rows;
+    }
     __syncwarp();
   }
 }
@@ -1165,10 +1400,16 @@ reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* of
       const double m = __longlong_as_double((long long)__ldcg(cm + c));
       if (m >= best - YSM_KT_TOLERANCE) {
         const double* pc = pr + (size_t)c * ps.nA;
-        for (int a = 0; a < ps.nA; a++) {
-          if (kt_double_equal(pc[a], best)) {
-            const int pos = atomicAdd(&s_count, 1);
-            if (pos < YSM_TIE_CAP) s_list[pos] = c * ps.nA + a;
+        for (int a0 = 0; a0 < ps.nA; a0 += 8) {
+          double r[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) r[u] = a0 + u < ps.nA ? pc[a0 + u] : -1.0;  // independent loads
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (r[u] >= 0.0 && kt_double_equal(r[u], best)) {
+              const int pos = atomicAdd(&s_count, 1);
+              if (pos < YSM_TIE_CAP) s_list[pos] = c * ps.nA + a0 + u;
+            }
           }
         }
       }
@@ -1327,12 +1568,12 @@ reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* of
       for (int a = warp; a < ps.nA; a += nwarps) {
         const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
         unsigned sum = 0;
-        for (int p0 = lane; p0 < ps.P; p0 += 128) {
-          unsigned idx[4];
+        for (int p0 = lane; p0 < ps.P; p0 += 384) {
+          unsigned idx[12];
 #pragma unroll
-          for (int u = 0; u < 4; u++) idx[u] = (p0 + 32 * u < ps.P) ? (unsigned)(base + goff[p0 + 32 * u]) : 0xFFFFFFFFu;
+          for (int u = 0; u < 12; u++) idx[u] = (p0 + 32 * u < ps.P) ? (unsigned)(base + goff[p0 + 32 * u]) : 0xFFFFFFFFu;
 #pragma unroll
-          for (int u = 0; u < 4; u++) if (idx[u] < dsz) sum += (unsigned)__ldg(grid + idx[u]);
+          for (int u = 0; u < 12; u++) if (idx[u] < dsz) sum += (unsigned)__ldg(grid + idx[u]);
         }
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) angsums[ps.ang_off + a] = (int)sum;
@@ -1446,6 +1687,10 @@ struct SmallArgs {
   int pool_in_blob;
   const double* pool_dev; // caller's device pool when not in the blob
   unsigned o_pool, o_scan_start, o_scan_count, o_matches, o_base, o_workcount, o_tab, o_pass, o_pa, o_trig, o_pmax;
+  unsigned o_scanlist;
+  int nscans_total, tiles_per_grid;
+  int* scan_emit;
+  unsigned char* tileflag;  // [nw][tiles_per_grid] bytes
   int nw, npa, ncoarse, nspec, nAf;
   int pmax, nbase_max, stage, fv_warps, ordered, log2cap;
   int tpc, psplit, task_chunks;
@@ -1487,6 +1732,8 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   // ---- P0: staging blob, host -> device ---------------------------------------------------------
   for (int i = blockIdx.x * blockDim.x + tid; i < A.blob_vec; i += gridDim.x * blockDim.x) A.blob_dst[i] = A.blob_src[i];
   for (int i = blockIdx.x * blockDim.x + tid; i < A.cellmax_n; i += gridDim.x * blockDim.x) A.cellmax[i] = 0ull;
+  for (int i = blockIdx.x * blockDim.x + tid; i < (A.nw * A.tiles_per_grid + 3) / 4; i += gridDim.x * blockDim.x)
+    reinterpret_cast<unsigned*>(A.tileflag)[i] = 0u;
   grid.sync();
   YSM_TSTAMP(1)
   unsigned char* db = reinterpret_cast<unsigned char*>(A.blob_dst);
@@ -1501,12 +1748,34 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   const PassAngle* pa_list = reinterpret_cast<const PassAngle*>(db + A.o_pa);
   const double* trig = reinterpret_cast<const double*>(db + A.o_trig);
   double* passmax = reinterpret_cast<double*>(db + A.o_pmax);
-  // ---- P1: FindValidPoints ------------------------------------------------------------------------
-  for (int vb = blockIdx.x; vb < A.nw; vb += gridDim.x) {
-    find_valid_body(g, matches, base_idx, scan_start, scan_count, pool, A.ptcell, A.cells, A.cellcount, A.gbox, A.work,
-                    work_count, A.pmax, A.nbase_max, A.stage, vb, dsm, A.fv_warps);
+  // ---- P1a: FindValidPoints, CTA per base scan ------------------------------------------------------
+  const ScanRef* scanlist = reinterpret_cast<const ScanRef*>(db + A.o_scanlist);
+  for (int v = blockIdx.x; v < A.nscans_total; v += gridDim.x) {
+    const ScanRef sr = scanlist[v];
+    fv_scan_body(g, matches, base_idx, scan_start, scan_count, pool, sr, A.ptcell, A.scan_emit, v, A.tileflag,
+                 A.tiles_per_grid, A.pmax, dsm);
     __syncthreads();
-    if (A.ordered) {
+  }
+  __threadfence();
+  YSM_TSTAMP(13)
+  grid.sync();
+  YSM_TSTAMP(14)
+  // ---- P1b: per match: cells in scan order, bounding boxes, tile work list (all CTAs) --------------
+  {
+    // the CTAs are dealt to the matches round-robin
+    const int per = max(1, (int)gridDim.x / A.nw);
+    for (int vb = 0; vb < A.nw; vb++) {
+      const int lo = vb * per, hi = vb == A.nw - 1 ? (int)gridDim.x : lo + per;
+      if ((int)blockIdx.x >= lo && (int)blockIdx.x < hi)
+        fv_match_body(g, matches, scanlist, A.nscans_total, A.scan_emit, A.ptcell, A.cells, A.cellcount, A.gbox, A.work,
+                      work_count, A.tileflag, A.tiles_per_grid, vb, (int)blockIdx.x - lo, hi - lo);
+    }
+  }
+  if (A.ordered) {
+    // the ordered-stamp filter needs the whole cell list of a match: one more barrier
+    __threadfence();
+    grid.sync();
+    for (int vb = blockIdx.x; vb < A.nw; vb += gridDim.x) {
       if (warp == 0) stamp_order_body(matches, A.cells, A.cellcount, A.log2cap, vb, lane, reinterpret_cast<uint32_t*>(dsm));
       __syncthreads();
     }
@@ -1515,8 +1784,14 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   grid.sync();
   YSM_TSTAMP(3)
   // ---- P2: SmearPoint ---------------------------------------------------------------------------------
-  tile_stamp_body(g, matches, A.cells, A.cellcount, A.gbox, A.work, work_count, A.kernel, A.grids, A.rowmask,
-                  A.rm_words, (int)blockIdx.x, (int)gridDim.x, dsm);
+  {
+    // as many warps per tile as the machine has to spare (<= 8: named barriers 1..8)
+    const int nwork = *work_count, wtot = (int)gridDim.x * (int)(blockDim.x >> 5);
+    int S = 8;
+    while (S > 1 && (long long)nwork * S > wtot) S >>= 1;
+    tile_stamp_body(g, matches, A.cells, A.cellcount, A.gbox, A.work, work_count, A.kernel, A.grids, A.rowmask,
+                    A.rm_words, (int)blockIdx.x, (int)gridDim.x, dsm, S);
+  }
   YSM_TSTAMP(4)
   grid.sync();
   YSM_TSTAMP(5)

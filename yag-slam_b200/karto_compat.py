@@ -14,7 +14,7 @@ import sys
 import numpy as np
 
 from . import _capi
-from .matcher import DEFAULTS, ScanMatcherB200, pack_pool
+from .matcher import _ERRORS, DEFAULTS, ScanMatcherB200, pack_pool
 
 
 class Pose2(object):
@@ -121,13 +121,51 @@ class Wrapper(object):
         self.config = config
         cfg = config._as_dict() if hasattr(config, "_as_dict") else dict(config)
         self._m = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
+        self._one = {}  # single-query descriptors, keyed by base-set size
 
     @property
     def matcher(self):
         return self._m
 
     def match_scan(self, query, base_scans, penalty=True, do_fine=False):
-        return self.match_scan_batch([query], [base_scans], penalty, do_fine)[0]
+        """Wrapper.match_scan(query, base_scans, penalty, do_fine) (reference scan_matching.py:41).
+        Single-query fast path: the descriptor arrays are cached per base-set size, only the
+        point readings are packed per call."""
+        import ctypes as C
+        nb = len(base_scans)
+        c = self._one.get(nb)
+        if c is None:
+            b = _capi.YsmBatch()
+            arr = dict(counts=np.zeros(nb + 1, np.int32), starts=np.zeros(nb + 1, np.int32),
+                       qidx=np.zeros(1, np.int32), pose=np.zeros((1, 3), np.float64),
+                       bptr=np.array([0, nb], np.int32), bidx=np.arange(1, nb + 1, dtype=np.int32),
+                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE))
+            b.n_matches, b.n_scans = 1, nb + 1
+            b.scan_start, b.scan_count = arr["starts"].ctypes.data, arr["counts"].ctypes.data
+            b.query_scan, b.query_pose = arr["qidx"].ctypes.data, arr["pose"].ctypes.data
+            b.base_ptr, b.base_idx = arr["bptr"].ctypes.data, (arr["bidx"].ctypes.data if nb else None)
+            b.pool_on_device = 0
+            c = self._one[nb] = (b, arr, C.byref(b), arr["res"].ctypes.data)
+        b, arr, bref, resp = c
+        pts = [query.point_readings()]
+        pts.extend(s.point_readings() for s in base_scans)
+        counts, starts = arr["counts"], arr["starts"]
+        tot = 0
+        for i, p in enumerate(pts):
+            starts[i] = tot
+            counts[i] = len(p)
+            tot += len(p)
+        pool = np.concatenate(pts) if tot else np.zeros((1, 2))
+        arr["pose"][0] = query.sensor_pose()
+        b.pool_xy, b.n_points = pool.ctypes.data, tot
+        b.do_penalize, b.do_refine = int(bool(penalty)), int(bool(do_fine))
+        m = self._m
+        rc = m._lib.ysm_match_batch(m._h, bref, resp, None)
+        if rc != _capi.YSM_OK:
+            raise _ERRORS.get(rc, RuntimeError)(_capi.last_error(m._h))
+        r = arr["res"][0]
+        return MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
+                           Pose2(float(r["x"]), float(r["y"]), float(r["heading"])))
 
     def match_scan_batch(self, queries, base_sets, penalty=True, do_fine=False):
         """Independent (query, base set) matches in one launch sequence. Scans shared between
