@@ -123,6 +123,50 @@ int ysm_raytrace(const uint8_t *img, int32_t h, int32_t w, int32_t img_on_device
                  const double *angles_deg, int32_t n_angles, const double *starts_xy,
                  int32_t n_starts, float *out, int device, void *stream);
 
+/* ---- occupancy grid: replaces karto_scanmatcher.create_occupancy_grid(scans, resolution,
+ * range_threshold) (reference yag_slam/graph_slam.py:341-342, ros1/slam_node_ros1:188-209;
+ * Karto OccupancyGrid::CreateFromScans). Scans cross as raw range readings +
+ * sensor pose + laser parameters (what the wheel's LocalizedRangeScan holds, models.py:37-39).
+ * range_threshold replaces the lasers' own threshold for the whole construction. ---- */
+typedef struct ysm_occ_scans {
+  int32_t n_scans;
+  int32_t _pad;
+  const double *pose;      /* [n_scans][3] sensor pose x, y, heading; host */
+  const double *laser;     /* [n_scans][4] min_angle, angular_resolution, min_range, max_range; host */
+  const double *ranges;    /* raw range readings of all scans, concatenated; host */
+  const int32_t *beam_ptr; /* [n_scans+1] first reading of each scan; host */
+  double resolution;
+  double range_threshold;
+} ysm_occ_scans;
+
+typedef struct ysm_occ_info {
+  int32_t width, height;     /* cells (OccupancyGrid::ComputeDimensions) */
+  double offset_x, offset_y; /* world position of cell (0,0) = bounding-box minimum */
+  double resolution;
+  int64_t rays;              /* raw beams examined */
+  int64_t cells_visited;     /* Bresenham steps taken (pass-count increments incl. out-of-bounds steps) */
+  int32_t box_candidates;    /* beams re-evaluated with host libm for the bounding box */
+  int32_t cell_fixups;       /* beams whose end cell was re-evaluated with host libm */
+  int32_t launches;          /* kernels launched */
+  int32_t _pad;
+} ysm_occ_info;
+
+typedef struct ysm_occ ysm_occ;
+
+/* Builds the grid on `device`; counts and image stay resident in HBM until ysm_occ_destroy.
+ * Synchronous w.r.t. the host. EINVAL for an empty scan list (Karto returns NULL). */
+int ysm_occ_create(const ysm_occ_scans *scans, int device, void *stream, ysm_occ **out);
+void ysm_occ_destroy(ysm_occ *o);
+int ysm_occ_get_info(const ysm_occ *o, ysm_occ_info *out);
+/* image [height][width] uint8, row 0 = minimum y: 0 occupied, 200 unknown, 255 free
+ * (the values ros1/slam_node_ros1:199-202 decodes) */
+int ysm_occ_copy_image(const ysm_occ *o, uint8_t *out_host);
+/* pass / hit counters [height][width] uint32 (parity tests) */
+int ysm_occ_copy_counts(const ysm_occ *o, uint32_t *pass_host, uint32_t *hit_host);
+/* device pointer of the image, for ysm_raytrace(img_on_device=1) without a host round trip */
+const uint8_t *ysm_occ_device_image(const ysm_occ *o);
+const char *ysm_occ_last_error(void); /* thread-local text of the last failing ysm_occ_* call */
+
 /* ---- introspection for parity tests (not part of the reference surface) ---- */
 #define YSM_DEBUG_KEEP_GRIDS 1 /* do not clear the slot grids after a batch */
 int ysm_set_debug(ysm_handle *h, int32_t flags);

@@ -26,8 +26,12 @@ class KoParams(C.Structure):
         ("use_response_expansion", C.c_int), ("_pad", C.c_int)]
 
 
+class OcDims(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("offset_x", C.c_double), ("offset_y", C.c_double)]
+
+
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "raywalk_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "raywalk_oracle.c", "occgrid_oracle.c", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -75,6 +79,13 @@ def lib():
                                C.c_double, C.POINTER(C.c_float)]
         L.rw_sweep_many.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, dp, C.c_int, dp, C.c_int,
                                     C.POINTER(C.c_float)]
+        L.oc_compute_dims.restype = C.c_int
+        L.oc_compute_dims.argtypes = [C.c_int, dp, dp, dp, C.POINTER(C.c_int32), C.c_double, C.c_double,
+                                      C.POINTER(OcDims)]
+        L.oc_render.restype = C.c_int
+        L.oc_render.argtypes = [C.c_int, dp, dp, dp, C.POINTER(C.c_int32), C.c_double, C.c_double,
+                                C.POINTER(OcDims), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_uint8)]
         _lib = L
     return _lib
 
@@ -241,3 +252,27 @@ def raywalk_sweep_many(img, angles_deg, starts_xy):
     lib().rw_sweep_many(img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[0], img.shape[1], _dp(a),
                         len(a), _dp(s), len(s), out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+def occupancy_grid(poses, lasers, ranges, beam_ptr, resolution, range_threshold):
+    """Restatement of karto_scanmatcher.create_occupancy_grid (occgrid_oracle.c): returns
+    dict(image, passes, hits, width, height, offset_x, offset_y)."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+    lasers = np.ascontiguousarray(lasers, dtype=np.float64).reshape(-1, 4)
+    ranges = np.ascontiguousarray(ranges, dtype=np.float64).reshape(-1)
+    beam_ptr = np.ascontiguousarray(beam_ptr, dtype=np.int32).reshape(-1)
+    n = len(poses)
+    d = OcDims()
+    bp = beam_ptr.ctypes.data_as(C.POINTER(C.c_int32))
+    if lib().oc_compute_dims(n, _dp(poses), _dp(lasers), _dp(ranges), bp, float(resolution),
+                             float(range_threshold), C.byref(d)) != 0:
+        return None
+    w, h = int(d.width), int(d.height)
+    passes = np.zeros((h, w), np.uint32)
+    hits = np.zeros((h, w), np.uint32)
+    image = np.zeros((h, w), np.uint8)
+    lib().oc_render(n, _dp(poses), _dp(lasers), _dp(ranges), bp, float(resolution), float(range_threshold),
+                    C.byref(d), passes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                    hits.ctypes.data_as(C.POINTER(C.c_uint32)), image.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return dict(image=image, passes=passes, hits=hits, width=w, height=h, offset_x=float(d.offset_x),
+                offset_y=float(d.offset_y))

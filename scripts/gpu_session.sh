@@ -12,4 +12,7 @@ timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-latency --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:${KREG} -s 4 -c 2 -o gpurun_out/${TAG}_sweep -f python bench.py --steps 2 --warmup 3 --no-latency --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_stamp -s 4 -c 2 -o gpurun_out/${TAG}_stamp -f python bench.py --steps 2 --warmup 3 --no-latency --no-cpu > gpurun_out/${TAG}_ncu_full2.log 2>&1; echo "ncu full stamp rc=$?"
+timeout 300 python scripts/occ_probe.py 2000 --cpu > gpurun_out/${TAG}_occ.log 2>&1; cat gpurun_out/${TAG}_occ.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_occ_trace -c 1 -o gpurun_out/${TAG}_occtrace -f python scripts/occ_probe.py 2000 > gpurun_out/${TAG}_ncu_full3.log 2>&1; echo "ncu full occ rc=$?"
 ls -la gpurun_out

@@ -38,6 +38,19 @@ class YsmBatch(C.Structure):
         ("pool_on_device", C.c_int32), ("_pad", C.c_int32)]
 
 
+class YsmOccScans(C.Structure):
+    _fields_ = [("n_scans", C.c_int32), ("_pad", C.c_int32), ("pose", C.c_void_p), ("laser", C.c_void_p),
+                ("ranges", C.c_void_p), ("beam_ptr", C.c_void_p), ("resolution", C.c_double),
+                ("range_threshold", C.c_double)]
+
+
+class YsmOccInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("offset_x", C.c_double), ("offset_y", C.c_double),
+                ("resolution", C.c_double), ("rays", C.c_int64), ("cells_visited", C.c_int64),
+                ("box_candidates", C.c_int32), ("cell_fixups", C.c_int32), ("launches", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
 RESULT_DTYPE = np.dtype([("response", "<f8"), ("x", "<f8"), ("y", "<f8"), ("heading", "<f8"),
                          ("cov", "<f8", (9,)), ("n_passes", "<i4"), ("n_ties", "<i4"),
                          ("status", "<i4"), ("_pad", "<i4"), ("_reserved", "<f8")])
@@ -47,6 +60,8 @@ EXPORTS = [
     "ysm_create", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
     "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
     "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
+    "ysm_occ_create", "ysm_occ_destroy", "ysm_occ_get_info", "ysm_occ_copy_image", "ysm_occ_copy_counts",
+    "ysm_occ_device_image", "ysm_occ_last_error",
 ]
 
 _lib = None
@@ -91,6 +106,20 @@ def lib():
     L.ysm_last_kernel_ms.argtypes = [vp] + [C.POINTER(f64)] * 4
     L.ysm_last_work.restype = C.c_int
     L.ysm_last_work.argtypes = [vp, C.POINTER(C.c_int64), i32]
+    L.ysm_occ_create.restype = C.c_int
+    L.ysm_occ_create.argtypes = [C.POINTER(YsmOccScans), C.c_int, vp, C.POINTER(vp)]
+    L.ysm_occ_destroy.restype = None
+    L.ysm_occ_destroy.argtypes = [vp]
+    L.ysm_occ_get_info.restype = C.c_int
+    L.ysm_occ_get_info.argtypes = [vp, C.POINTER(YsmOccInfo)]
+    L.ysm_occ_copy_image.restype = C.c_int
+    L.ysm_occ_copy_image.argtypes = [vp, vp]
+    L.ysm_occ_copy_counts.restype = C.c_int
+    L.ysm_occ_copy_counts.argtypes = [vp, vp, vp]
+    L.ysm_occ_device_image.restype = vp
+    L.ysm_occ_device_image.argtypes = [vp]
+    L.ysm_occ_last_error.restype = C.c_char_p
+    L.ysm_occ_last_error.argtypes = []
     _lib = L
     return L
 

@@ -192,9 +192,11 @@ class Wrapper(object):
 
 
 def create_occupancy_grid(scans, resolution, range_threshold):
-    """karto_scanmatcher.create_occupancy_grid (reference graph_slam.py:341-342). SURVEY.md 8f-1
-    ranks it as the first "next" row; it is not part of the hot path built so far."""
-    raise NotImplementedError("create_occupancy_grid: SURVEY.md 8(f)-1, not built yet")
+    """karto_scanmatcher.create_occupancy_grid (reference graph_slam.py:341-342,
+    ros1/slam_node_ros1:188): Karto's OccupancyGrid::CreateFromScans on the B200
+    (csrc/ysm_occ.cu). Returns an object with .image / .offset / .width / .height."""
+    from .occupancy import create_occupancy_grid as _create
+    return _create(scans, resolution, range_threshold)
 
 
 def install(name="karto_scanmatcher"):

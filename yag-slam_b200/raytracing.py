@@ -32,7 +32,10 @@ def raytrace_many(img, angles_deg, starts_xy, device=0, stream=0):
     starts = np.ascontiguousarray(starts_xy, dtype=np.float64).reshape(-1, 2)
     out = np.zeros((len(starts), len(angles), 5), dtype=np.float32)
     on_dev = hasattr(img, "is_cuda") and bool(img.is_cuda)
-    if on_dev:
+    if hasattr(img, "device_image"):  # occupancy.OccupancyGrid: the image is already resident in HBM
+        on_dev, h, w, ptr, keep = True, img.height, img.width, img.device_image, img
+        device = img.device
+    elif on_dev:
         h, w = int(img.shape[0]), int(img.shape[1])
         ptr, keep = int(img.data_ptr()), img
     else:

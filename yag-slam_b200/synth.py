@@ -187,3 +187,25 @@ def make_match_batch(world, n_matches, n_beams, n_base, seed, perturb=(0.2, 0.15
                 base_idx=np.array(base_idx, np.int32), points=pts)
 
 
+
+
+# ---- raw scan logs for the occupancy grid --------------------------------
+def make_scan_log(world, n_scans, n_beams, seed, step=0.25, defects=0.0):
+    """n_scans raw scans along the loop path: dict(poses [n][3], lasers [n][4] = min_angle,
+    angular_resolution, min_range, max_range, ranges (concatenated), beam_ptr [n+1]).
+    `defects` = fraction of readings replaced by NaN / inf / below-min / at-max values."""
+    rng = np.random.default_rng(seed)
+    path = loop_path(n_scans, step=step)
+    lp = laser_params(n_beams)
+    ranges = np.empty((n_scans, n_beams))
+    for i in range(n_scans):
+        ranges[i] = cast_scan(world, path[i], n_beams, rng)
+    if defects > 0:
+        m = rng.random(ranges.shape)
+        ranges[m < defects * 0.25] = np.nan
+        ranges[(m >= defects * 0.25) & (m < defects * 0.5)] = np.inf
+        ranges[(m >= defects * 0.5) & (m < defects * 0.75)] = 0.01
+        ranges[(m >= defects * 0.75) & (m < defects)] = lp[4]
+    lasers = np.tile(np.array([lp[0], lp[2], lp[3], lp[4]]), (n_scans, 1))
+    beam_ptr = (np.arange(n_scans + 1) * n_beams).astype(np.int32)
+    return dict(poses=np.ascontiguousarray(path), lasers=lasers, ranges=ranges.reshape(-1), beam_ptr=beam_ptr)
