@@ -249,6 +249,7 @@ struct ysm_handle {
   uint32_t* d_rowmask = nullptr;  // [slots][tny*tnx]: which rows of every 32x32 tile hold a non-zero cell
   int tnx = 0, rm_words = 0;
   uint8_t* d_kernel = nullptr;
+  uint16_t* d_stamp_tab = nullptr;  // pre-shifted stamp rows of k_tile_stamp: u16 [8][K][Wt]
   std::vector<uint8_t> h_kernel;
   std::string err;
   int debug = 0;
@@ -276,7 +277,7 @@ struct ysm_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   double t_sweep = 0, t_build = 0, t_reduce = 0, t_total = 0;
-  size_t sweep_smem_attr = 0, find_smem_attr = 0, prune_smem_attr = 0;
+  size_t sweep_smem_attr = 0, find_smem_attr = 0, prune_smem_attr = 0, stamp_smem_attr = 0;
   // lanes: extra matcher instances (own grid slots, workspaces and stream) that take contiguous
   // shares of a large batch on their own host threads, so one lane's host-side pass planning and
   // result handling overlap the other lanes' kernels
@@ -325,6 +326,17 @@ static int calculate_kernel(double res_eff, double smear, std::vector<uint8_t>& 
     }
   }
   return 0;
+}
+
+// Stamp rows pre-shifted to the 8 cell alignments of a 16-byte shared-memory load (k_tile_stamp):
+// row j of alignment a holds kernel row j at cells [24 + a, 24 + a + K) of a Wt-cell row of zeros.
+static void build_stamp_table(const std::vector<uint8_t>& kern, int K, int& Wt, std::vector<uint16_t>& tab) {
+  Wt = K + 62;
+  while (Wt % 16 != 8) Wt++;  // row stride = 16 B (mod 32 B): consecutive rows on distinct banks
+  tab.assign((size_t)8 * K * Wt, 0);
+  for (int a = 0; a < 8; a++)
+    for (int j = 0; j < K; j++)
+      for (int i = 0; i < K; i++) tab[((size_t)a * K + j) * Wt + 24 + a + i] = kern[(size_t)i + (size_t)K * j];
 }
 
 static int create_one(const ysm_params* p, int device, ysm_handle** out) {
@@ -394,7 +406,8 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out) {
     }
     h->ordered_stamps = (hot == 5);
   }
-  g.Wk = (g.K + 6) / 4;
+  std::vector<uint16_t> stamp_tab;
+  build_stamp_table(h->h_kernel, g.K, g.Wt, stamp_tab);
   h->pen.distance_variance_penalty = p->distance_variance_penalty;
   h->pen.angle_variance_penalty = p->angle_variance_penalty;
   h->pen.minimum_distance_penalty = p->minimum_distance_penalty;
@@ -423,6 +436,8 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_issued, 8);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_kernel, h->h_kernel.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->d_kernel, h->h_kernel.data(), h->h_kernel.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stamp_tab, stamp_tab.size() * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_stamp_tab, stamp_tab.data(), stamp_tab.size() * 2, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     h->ev_ok = true;
     for (int i = 0; i < 8; i++)
@@ -434,6 +449,7 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out) {
     if (h->d_rowmask) cudaFree(h->d_rowmask);
     if (h->d_issued) cudaFree(h->d_issued);
     if (h->d_kernel) cudaFree(h->d_kernel);
+    if (h->d_stamp_tab) cudaFree(h->d_stamp_tab);
     delete h;
     return fail(nullptr, YSM_ECUDA, msg);
   }
@@ -492,6 +508,7 @@ extern "C" void ysm_destroy(ysm_handle* h) {
   if (h->d_rowmask) cudaFree(h->d_rowmask);
   if (h->d_issued) cudaFree(h->d_issued);
   if (h->d_kernel) cudaFree(h->d_kernel);
+  if (h->d_stamp_tab) cudaFree(h->d_stamp_tab);
   DevBuf* bufs[] = {&h->d_pool, &h->d_scan_start, &h->d_scan_count, &h->d_base_idx, &h->d_matches,
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
                     &h->d_tables, &h->d_passes,
@@ -1131,11 +1148,15 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         h->launches++;
         kt.mark("k_stamp_order");
       }
-      const size_t ksmem = tile_stamp_smem(g.K, g.Wk, 8);
+      const size_t ksmem = tile_stamp_smem(g.K, g.Wt, 8);
+      if (ksmem > 48 * 1024 && ksmem > h->stamp_smem_attr) {
+        CK(cudaFuncSetAttribute(k_tile_stamp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem));
+        h->stamp_smem_attr = ksmem;
+      }
       const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
-                                                       (const int2*)h->d_work.p, d_workcount, h->d_kernel, h->d_grids,
+                                                       (const int2*)h->d_work.p, d_workcount, h->d_stamp_tab, h->d_grids,
                                                        h->d_rowmask, h->rm_words);
       h->launches++;
       kt.mark("k_tile_stamp");
@@ -1197,7 +1218,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         if (mega_psplit > 1 && (!uniform || pl.max_lat_tasks % mega_tpc != 0)) { mega_tpc = 16; mega_psplit = 1; }
         mega_chunks = (pl.max_lat_tasks + mega_tpc - 1) / mega_tpc;
         const size_t sw = (size_t)(((pl.max_lat_P + 7) & ~7) + pl.max_lat_nx + pl.max_lat_ny + (mega_psplit > 1 ? 512 : 0)) * 4;
-        mega_smem = std::max(std::max(fv, so), std::max(tile_stamp_smem(g.K, g.Wk, 16), sw));
+        mega_smem = std::max(std::max(fv, so), std::max(tile_stamp_smem(g.K, g.Wt, 16), sw));
         mega_smem = std::max(mega_smem, (size_t)(pmax + 8) * 4);
         mega_smem = (mega_smem + 1023) & ~(size_t)1023;
         if (mega_smem > 110 * 1024) mega = false;
@@ -1281,7 +1302,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         A.tpc = mega_tpc; A.psplit = mega_psplit; A.task_chunks = mega_chunks;
         A.ptcell = (uint32_t*)h->d_ptcell.p; A.cells = (uint32_t*)h->d_cells.p; A.cellcount = (int*)h->d_cellcount.p;
         A.gbox = (uint2*)h->d_gbox.p; A.work = (int2*)h->d_work.p;
-        A.kernel = h->d_kernel; A.grids = h->d_grids; A.rowmask = h->d_rowmask; A.rm_words = h->rm_words;
+        A.stamp_tab = h->d_stamp_tab; A.grids = h->d_grids; A.rowmask = h->d_rowmask; A.rm_words = h->rm_words;
         A.epoch = h->epoch;
         A.offsets = (int*)h->d_offsets.p; A.resp = (double*)h->d_sums.p;
         A.cellmax = (unsigned long long*)h->d_cellmax.p; A.cellmax_n = (int)pl.cmax_elems;

@@ -23,7 +23,7 @@ namespace ysm {
 // Sizes of one correlation grid (ScanMatcher::Create / CorrelationGrid).
 struct GridC {
   int roi, border, stride, width, height, data_size;
-  int half_kernel, K, Wk;  // Wk = 32-bit words a stamp row can straddle
+  int half_kernel, K, Wt;  // Wt = row width (cells) of the pre-shifted stamp table
   int stride4;             // stride / 4
   double scale;            // 1 / resolution
   long long grid_bytes;    // bytes between consecutive slots (16-B aligned)
@@ -577,93 +577,90 @@ k_stamp_order(const MatchDev* __restrict__ matches, uint32_t* __restrict__ cells
 // ---------------------------------------------------------------------------------------------
 // K1b  CorrelationGrid::SmearPoint over every occupied cell (python twin
 // yag_slam/helpers.py:105-119). The smear is a pure max of a K x K stamp, so each touched
-// 32 x 32 tile of the grid is OWNED by one warp: it keeps the tile in a private 1 KB block of
-// shared memory, collects the match's cells whose stamp reaches the tile (groups of 32
-// consecutive cells are pre-filtered by their bounding box), scatters every candidate's
-// clipped stamp into the tile -- lanes = 4 tile rows x 8 words, byte-wise max of four cells
-// per lane, stamp rows pre-shifted for the four byte alignments -- and writes the tile to the
-// grid exactly once: no atomics, no global read-modify-write. Warps stride the wave's
-// (match, tile) work list.
+// 32 x 32 tile of the grid is OWNED by one warp and lives in its REGISTERS: lane r holds tile
+// row r as 16 u16x2 words. The warp collects the match's cells whose stamp reaches the tile
+// (groups of 32 consecutive cells are pre-filtered by their bounding box; the per-candidate
+// addressing is prepared lane-parallel while the list is compacted), then every candidate is one
+// warp-uniform step: lane r reads the stamp row that crosses its tile row -- already shifted to
+// the tile's columns, from a shared-memory table holding the stamp rows at the 8 cell alignments
+// a 16-byte load allows -- and maxes it in with VIMNMX.U16x2, skipping the 8-cell groups the
+// stamp does not overlap. No shared-memory read-modify-write, no atomics; the tile is written
+// to the grid exactly once. Warps stride the wave's (match, tile) work list.
+// Stamp table (host-built, ysm.cu build_stamp_table): u16 [8][K][Wt]; row j of alignment a holds
+// the stamp's row j at cells [24 + a, 24 + a + K), zero elsewhere; Wt = 8 (mod 16) keeps the
+// lanes' 16-byte loads (consecutive rows) on distinct banks.
 // ---------------------------------------------------------------------------------------------
 #define YSM_TILE_LIST 224   // candidate cells staged per warp between flushes
 
-__device__ __forceinline__ void tile_scatter(uint2* __restrict__ tile, const uint32_t* __restrict__ list,
-                                             int n, const uint2* __restrict__ s_k, int K, int Wk, int h,
-                                             int x0t, int y0t, int lane) {
-  const int wt0 = x0t >> 2;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    // lane-parallel set-up of up to 32 candidates: the stamp clipped to the tile
-    // (rows [r0, r1], words [w0, w1]) packed into two words that are broadcast below
-    uint32_t p0 = 0, p1 = 0;
-    if (e0 + lane < n) {
-      const uint32_t c = list[e0 + lane];
-      const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
-      const int xs = ax - h, ys = ay - h;  // top-left cell of the stamp
-      const int wrel = (xs >> 2) - wt0;    // tile word of the stamp's first word
-      const int r0 = max(0, ys - y0t), r1 = min(YSM_TILE - 1, ys + K - 1 - y0t);
-      const int w0 = max(0, wrel), w1 = min(7, wrel + Wk - 1);
-      const int nwd = w1 - w0 + 1;
-      const int items = (r1 - r0 + 1) * nwd;                                   // <= 256
-      const unsigned rcp = (65536u + (unsigned)nwd - 1u) / (unsigned)nwd;      // it / nwd for it < 256
-      const int koff = ((xs & 3) * K + (y0t + r0 - ys)) * Wk + (w0 - wrel);    // < 4*K*Wk <= 2048
-      p0 = (uint32_t)(r0 * 8 + w0) | ((uint32_t)nwd << 8) | ((uint32_t)items << 12);
-      p1 = (uint32_t)koff | (rcp << 11);
-    }
-    const int cnt = min(32, n - e0);
-    for (int k = 0; k < cnt; k++) {
-      const uint32_t q0 = __shfl_sync(0xffffffffu, p0, k), q1 = __shfl_sync(0xffffffffu, p1, k);
-      const int nwd = (int)((q0 >> 8) & 15u), items = (int)(q0 >> 12);
-      const unsigned rcp = q1 >> 11;
-      const uint2* ks = s_k + (q1 & 2047u);
-      uint2* t0 = tile + (q0 & 255u);
-      for (int it = lane; it < items; it += 32) {
-        const int jr = (int)(((unsigned)it * rcp) >> 16);
-        const int ww = it - jr * nwd;
-        const uint2 kw = ks[jr * Wk + ww];
-        uint2* tp = t0 + jr * 8 + ww;
-        uint2 tv = *tp;
-        tv.x = __vmaxu2(tv.x, kw.x);  // VIMNMX.U16x2: two cells per instruction
-        tv.y = __vmaxu2(tv.y, kw.y);
-        *tp = tv;
-      }
-      __syncwarp();
-    }
+// candidate -> packed step descriptor: bits 31..12 q (signed; u16 index of tile row 0's window in
+// the table), bit 11 zero, 10..7 mask of the 8-cell groups the stamp overlaps, 6..0 dy + 31 (dy = stamp
+// row of tile row 0)
+__device__ __forceinline__ uint32_t stamp_step(uint32_t c, int h, int K, int Wt, int x0t, int y0t) {
+  const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+  const int xr = ax - h - x0t;      // tile column of the stamp's first column: [-(K-1), 31]
+  const int dy = y0t - (ay - h);    // stamp row that lands on tile row 0: [-31, K-1]
+  const int a = xr & 7;
+  const int ws = 24 + a - xr;       // multiple of 8
+  const int q = (a * K + dy) * Wt + ws;
+  const int g0 = max(0, xr) >> 3, g1 = min(31, xr + K - 1) >> 3;
+  const uint32_t mask = ((2u << g1) - 1u) & ~((1u << g0) - 1u);
+  return ((uint32_t)q << 12) | (mask << 7) | (uint32_t)(dy + 31);
+}
+
+// t[0..3] = max(t[0..3], the 8 cells at shared address saddr)   (VIMNMX.U16x2: two cells per instruction)
+__device__ __forceinline__ void max_group(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t& t3, uint32_t saddr) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr));
+  t0 = __vmaxu2(t0, a);
+  t1 = __vmaxu2(t1, b);
+  t2 = __vmaxu2(t2, c);
+  t3 = __vmaxu2(t3, d);
+}
+
+// lane_tab_s: shared-space address of this lane's row of the stamp table (tile row `lane`, stamp row 0)
+__device__ __forceinline__ void tile_scatter_rows(uint32_t (&t)[16], const uint32_t* __restrict__ list, int n,
+                                                  uint32_t lane_tab_s, int K) {
+  const int lane31 = (int)(threadIdx.x & 31) - 31;
+#pragma unroll 2
+  for (int k = 0; k < n; k++) {
+    const uint32_t w = list[k];  // warp-uniform (broadcast)
+    const uint32_t saddr = lane_tab_s + (uint32_t)((int)w >> 11);  // + 2 * q bytes
+    // group mask, cleared when this tile row does not cross the stamp
+    const uint32_t gm = (unsigned)(lane31 + (int)(w & 0x7Fu)) < (unsigned)K ? w : 0u;
+    if (gm & 0x080u) max_group(t[0], t[1], t[2], t[3], saddr);
+    if (gm & 0x100u) max_group(t[4], t[5], t[6], t[7], saddr + 16u);
+    if (gm & 0x200u) max_group(t[8], t[9], t[10], t[11], saddr + 32u);
+    if (gm & 0x400u) max_group(t[12], t[13], t[14], t[15], saddr + 48u);
   }
 }
 
-// dynamic smem: s_k [4][K][Wk] uint2 (pre-shifted stamp rows, 4 cells per entry widened to u16) |
-// per warp: tile [256] uint2 | candidate list [YSM_TILE_LIST + 32] u32
-__host__ __device__ __forceinline__ size_t tile_stamp_smem(int K, int Wk, int nwarps) {
-  return (size_t)4 * K * Wk * 8 + (size_t)nwarps * (YSM_TILE * YSM_TILE / 4 * 8 + (YSM_TILE_LIST + 32) * 4);
+__host__ __device__ __forceinline__ size_t stamp_table_bytes(int K, int Wt) { return (size_t)8 * K * Wt * 2; }
+
+// dynamic smem: stamp table | per warp: byte tile staging [256] u32 | step list [YSM_TILE_LIST + 32] u32
+__host__ __device__ __forceinline__ size_t tile_stamp_smem(int K, int Wt, int nwarps) {
+  return stamp_table_bytes(K, Wt) + (size_t)nwarps * (YSM_TILE * YSM_TILE + (YSM_TILE_LIST + 32) * 4);
 }
 
 __device__ __forceinline__ void
 tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, const int* cell_count,
-                const uint2* gbox, const int2* work, const int* work_count, const uint8_t* kernel, uint8_t* grids,
+                const uint2* gbox, const int2* work, const int* work_count, const uint16_t* stamp_tab, uint8_t* grids,
                 uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm, int S = 1) {
   // S > 1 (latency path): S warps share one tile -- each scans its share of the cell groups into a
   // private copy of the tile, the copies are max-combined at write-out (named barrier per group)
   __shared__ unsigned s_rows[16];
   if (threadIdx.x < 16) s_rows[threadIdx.x] = 0u;
-  const int K = g.K, Wk = g.Wk, h = g.half_kernel;
-  const int nks = 4 * K * Wk;
+  const int K = g.K, Wt = g.Wt, h = g.half_kernel;
   const int wpb = blockDim.x >> 5;  // warps per block
-  uint2* s_k = reinterpret_cast<uint2*>(dsm);
-  uint2* s_tile = s_k + nks;
-  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_tile + (size_t)wpb * (YSM_TILE * YSM_TILE / 4));
-  for (int t = threadIdx.x; t < nks; t += blockDim.x) {
-    const int w = t % Wk, j = (t / Wk) % K, s = t / (Wk * K);
-    uint32_t v[4];
-    for (int b = 0; b < 4; b++) {
-      const int i = w * 4 + b - s;  // stamp column
-      v[b] = (i >= 0 && i < K) ? (uint32_t)kernel[i + K * j] : 0u;
-    }
-    s_k[t] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-  }
+  const int ntab4 = (int)(stamp_table_bytes(K, Wt) / 16);
+  uint4* s_tab4 = reinterpret_cast<uint4*>(dsm);
+  for (int t = threadIdx.x; t < ntab4; t += blockDim.x) s_tab4[t] = __ldg(reinterpret_cast<const uint4*>(stamp_tab) + t);
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_tab4 + ntab4);
+  uint32_t* s_list = s_stage + (size_t)wpb * (YSM_TILE * YSM_TILE / 4);
   __syncthreads();
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint2* tile = s_tile + (size_t)warp * (YSM_TILE * YSM_TILE / 4);
+  const uint32_t lane_tab_s = (uint32_t)__cvta_generic_to_shared(dsm) + (uint32_t)(lane * Wt * 2);
+  uint32_t* stage = s_stage + (size_t)warp * (YSM_TILE * YSM_TILE / 4);
   uint32_t* list = s_list + (size_t)warp * (YSM_TILE_LIST + 32);
   const int nwork = *work_count;
   const int gpc = wpb / S, group = warp / S, sub = warp - group * S;  // tile groups per CTA
@@ -677,9 +674,9 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
     const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
     const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
     const int ngroups = (ncells + 31) >> 5;
+    uint32_t t[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) tile[k * 32 + lane] = make_uint2(0u, 0u);
-    __syncwarp();
+    for (int k = 0; k < 16; k++) t[k] = 0u;
     int n = 0;
     for (int gs = 0; gs < ngroups; gs += 32 * S) {
       // groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
@@ -701,36 +698,45 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
         if (i < ncells) {
           c = mc[i];
           const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
-          hit = ax + h >= x0t && ax - h <= x0t + YSM_TILE - 1 && ay + h >= y0t && ay - h <= y0t + YSM_TILE - 1;
+          hit = c != YSM_INVALID_CELL && ax + h >= x0t && ax - h <= x0t + YSM_TILE - 1 && ay + h >= y0t &&
+                ay - h <= y0t + YSM_TILE - 1;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[n + __popc(bal & ((1u << lane) - 1u))] = c;
+        if (hit) list[n + __popc(bal & ((1u << lane) - 1u))] = stamp_step(c, h, K, Wt, x0t, y0t);
         n += __popc(bal);
         if (n > YSM_TILE_LIST) {  // warp-uniform
           __syncwarp();
-          tile_scatter(tile, list, n, s_k, K, Wk, h, x0t, y0t, lane);
+          tile_scatter_rows(t, list, n, lane_tab_s, K);
+          __syncwarp();
           n = 0;
         }
       }
     }
     __syncwarp();
-    tile_scatter(tile, list, n, s_k, K, Wk, h, x0t, y0t, lane);
+    tile_scatter_rows(t, list, n, lane_tab_s, K);
+    // lane r's row as bytes -> this warp's staging tile (16-byte chunks swizzled: conflict-free both ways)
+    {
+      uint32_t b[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) b[k] = __byte_perm(t[2 * k], t[2 * k + 1], 0x6420);  // u16 lanes -> bytes
+      const int sw = (lane >> 2) & 1;
+      uint4* st4 = reinterpret_cast<uint4*>(stage);
+      st4[lane * 2 + (0 ^ sw)] = make_uint4(b[0], b[1], b[2], b[3]);
+      st4[lane * 2 + (1 ^ sw)] = make_uint4(b[4], b[5], b[6], b[7]);
+    }
     // the tile is written exactly once
     uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)m.slot * g.grid_bytes);
     const int dr = lane >> 3, wd = lane & 7;
     const int gw = (x0t >> 2) + wd;
     uint32_t rows = 0;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
     if (S > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * S) : "memory");
-    const uint2* copies = s_tile + (size_t)(group * S) * (YSM_TILE * YSM_TILE / 4);
+    else __syncwarp();
+    const uint32_t* copies = s_stage + (size_t)(group * S) * (YSM_TILE * YSM_TILE / 4);
     for (int k = sub; k < 8; k += S) {
-      const int row = y0t + k * 4 + dr;
-      uint2 tv = copies[(k * 4 + dr) * 8 + wd];
-      for (int c = 1; c < S; c++) {
-        const uint2 o = copies[(size_t)c * (YSM_TILE * YSM_TILE / 4) + (k * 4 + dr) * 8 + wd];
-        tv.x = __vmaxu2(tv.x, o.x);
-        tv.y = __vmaxu2(tv.y, o.y);
-      }
-      const uint32_t v = __byte_perm(tv.x, tv.y, 0x6420);  // u16 lanes -> bytes
+      const int r = k * 4 + dr, row = y0t + r;
+      const int widx = r * 8 + 4 * ((wd >> 2) ^ (k & 1)) + (wd & 3);
+      uint32_t v = copies[widx];
+      for (int c = 1; c < S; c++) v = vmax4_lt128(v, copies[(size_t)c * (YSM_TILE * YSM_TILE / 4) + widx]);
       if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
       const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
 #pragma unroll
@@ -755,10 +761,10 @@ __global__ void __launch_bounds__(256)
 k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __restrict__ cells,
              const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
              const int2* __restrict__ work, const int* __restrict__ work_count,
-             const uint8_t* __restrict__ kernel, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
+             const uint16_t* __restrict__ stamp_tab, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
              int rm_words) {
   extern __shared__ __align__(16) unsigned char dsm_ts[];
-  tile_stamp_body(g, matches, cells, cell_count, gbox, work, work_count, kernel, grids, rowmask, rm_words,
+  tile_stamp_body(g, matches, cells, cell_count, gbox, work, work_count, stamp_tab, grids, rowmask, rm_words,
                   (int)blockIdx.x, (int)gridDim.x, dsm_ts);
 }
 
@@ -1699,7 +1705,7 @@ struct SmallArgs {
   int* cellcount;
   uint2* gbox;
   int2* work;
-  const uint8_t* kernel;
+  const uint16_t* stamp_tab;
   uint8_t* grids;
   uint32_t* rowmask;
   int rm_words;
@@ -1789,7 +1795,7 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
     const int nwork = *work_count, wtot = (int)gridDim.x * (int)(blockDim.x >> 5);
     int S = 8;
     while (S > 1 && (long long)nwork * S > wtot) S >>= 1;
-    tile_stamp_body(g, matches, A.cells, A.cellcount, A.gbox, A.work, work_count, A.kernel, A.grids, A.rowmask,
+    tile_stamp_body(g, matches, A.cells, A.cellcount, A.gbox, A.work, work_count, A.stamp_tab, A.grids, A.rowmask,
                     A.rm_words, (int)blockIdx.x, (int)gridDim.x, dsm, S);
   }
   YSM_TSTAMP(4)
