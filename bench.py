@@ -128,6 +128,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from the committed ncu --set full
+    capture of this same command (profiles/sweep_traffic.json); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def host_cores():
     """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers, which
     would starve the CPU arm: the thread count is taken from the affinity mask instead)."""
@@ -300,6 +311,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    traffic, traffic_src = measured_traffic()
     sweep_bytes = snap["lookups"] * 1 + snap["offset_entries"] * 4 + snap["poses"] * 4
     sweep_s = snap["sweep_ms"] * 1e-3
     achieved = sweep_bytes / sweep_s / 1e9 if sweep_s > 0 else None
@@ -317,7 +329,8 @@ def run_ours(args, rank, world, local_rank):
             "kernel": ("k_sweep_pruned" if snap["pruned_launches"] else "k_sweep_lattice") +
                       " (CorrelateScan/GetResponse coarse sweep)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": sweep_bytes / max(snap["launches"], 1),
             "avg_launch_ms": snap["sweep_ms"] / max(snap["launches"], 1), "launches": snap["launches"],
             "lookups_per_s": snap["lookups"] / sweep_s if sweep_s > 0 else None,

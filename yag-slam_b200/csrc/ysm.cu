@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #include <algorithm>
 #include <thread>
@@ -66,7 +67,7 @@ struct PhaseTrace {
   void mark(const char* what) {
     if (!on) return;
     auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[ysm] %-28s +%8.1f us (t=%8.1f)\n", what,
+    fprintf(stderr, "[ysm %03x] %-28s +%8.1f us (t=%8.1f)\n", (unsigned)(((uintptr_t)pthread_self()) >> 12) & 0xfffu, what,
             std::chrono::duration<double, std::micro>(now - last).count(),
             std::chrono::duration<double, std::micro>(now - t0).count());
     last = now;

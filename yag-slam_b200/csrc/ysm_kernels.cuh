@@ -737,8 +737,9 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
       const int widx = r * 8 + 4 * ((wd >> 2) ^ (k & 1)) + (wd & 3);
       uint32_t v = copies[widx];
       for (int c = 1; c < S; c++) v = vmax4_lt128(v, copies[(size_t)c * (YSM_TILE * YSM_TILE / 4) + widx]);
-      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
       const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+      // all-zero rows are not written (the slot is all-zero between matches; 8 lanes = one 32-byte sector)
+      if ((nz & (0xFFu << (8 * dr))) && row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
 #pragma unroll
       for (int d = 0; d < 4; d++)
         if (nz & (0xFFu << (8 * d))) rows |= 1u << (k * 4 + d);
@@ -768,27 +769,44 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
                   (int)blockIdx.x, (int)gridDim.x, dsm_ts);
 }
 
-// zero the tiles a wave touched (the slot grids are kept all-zero between matches): warp per tile
+// zero the tiles a wave touched (the slot grids are kept all-zero between matches). A warp takes 32
+// work items at a time: the (match, tile) pairs and their slots are fetched lane-parallel (no
+// dependent-load chain per tile), then each tile is zeroed with four 8-byte stores per lane
+// (row stride is a multiple of 8 bytes).
 __global__ void __launch_bounds__(256)
 k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
              const int* __restrict__ work_count, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
              int rm_words) {
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int lane = threadIdx.x & 31, dr = lane >> 3, wd = lane & 7;
+  const int lane = threadIdx.x & 31, dr = lane >> 2, wd = lane & 3;
   const int nwork = *work_count;
   const int nwarps_total = gridDim.x * (blockDim.x >> 5);
-  for (int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nwork; wi += nwarps_total) {
-    const int2 wk = work[wi];
-    const int slot = matches[wk.x].slot;
-    const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
-    uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes);
-    const int gw = ((tx * YSM_TILE) >> 2) + wd;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int row = ty * YSM_TILE + k * 4 + dr;
-      if (row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = 0u;
+  const int stride8 = g.stride4 >> 1;
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < nwork; base += nwarps_total * 32) {
+    const int cnt = min(32, nwork - base);
+    int my_tile = 0, my_slot = 0;
+    uint32_t my_rows = 0u;  // rows of the tile that hold a non-zero cell: the only ones the stamp kernel wrote
+    if (lane < cnt) {
+      const int2 wk = work[base + lane];
+      my_tile = wk.y;
+      my_slot = matches[wk.x].slot;
+      uint32_t* rm = rowmask + (size_t)my_slot * rm_words + wk.y;
+      my_rows = *rm;
+      if (my_rows) *rm = 0u;
     }
-    if (lane == 0) rowmask[(size_t)slot * rm_words + wk.y] = 0u;
+    for (int j = 0; j < cnt; j++) {
+      const uint32_t rows = __shfl_sync(0xffffffffu, my_rows, j);
+      if (rows == 0u) continue;  // warp-uniform
+      const int tile = __shfl_sync(0xffffffffu, my_tile, j), slot = __shfl_sync(0xffffffffu, my_slot, j);
+      const int ty = tile / tnx, tx = tile - ty * tnx;
+      uint2* gout = reinterpret_cast<uint2*>(grids + (size_t)slot * g.grid_bytes);
+      const int gw = ((tx * YSM_TILE) >> 3) + wd;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int row = ty * YSM_TILE + k * 8 + dr;
+        if (((rows >> (k * 8 + dr)) & 1u) && row < g.height && gw < stride8) gout[(size_t)row * stride8 + gw] = make_uint2(0u, 0u);
+      }
+    }
   }
 }
 
