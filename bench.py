@@ -209,7 +209,8 @@ def run_ours(args, rank, world, local_rank):
     hpool = torch.from_numpy(b["pool"]).pin_memory()
     res = np.zeros(n, dtype=_capi.RESULT_DTYPE)
     acc = {"sweep_ms": 0.0, "build_ms": 0.0, "reduce_ms": 0.0, "total_ms": 0.0, "lookups": 0, "launches": 0,
-           "offset_entries": 0, "poses": 0, "h2d": 0, "d2h": 0, "issued": 0, "pruned_launches": 0, "count": False}
+           "offset_entries": 0, "poses": 0, "h2d": 0, "d2h": 0, "issued": 0, "pruned_launches": 0, "count": False,
+           "base_points": 0}
 
     def step(pool):
         out = m.match_pool(pool, b["starts"], b["counts"], b["query_scan"], b["query_pose"], b["base_ptr"],
@@ -222,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
             acc["offset_entries"] += w["offset_entries"]; acc["poses"] += w["poses"]
             acc["h2d"] += w["h2d_bytes"]; acc["d2h"] += w["d2h_bytes"]
             acc["issued"] += w["lookups_issued"]; acc["pruned_launches"] += w["pruned_sweep_launches"]
+            acc["base_points"] += w["base_points"]
         if world > 1:
             # one all-gather of best poses / responses over NVLink; weak scaling: every
             # rank contributes its own n records
@@ -315,6 +317,11 @@ def run_ours(args, rank, world, local_rank):
     sweep_bytes = snap["lookups"] * 1 + snap["offset_entries"] * 4 + snap["poses"] * 4
     sweep_s = snap["sweep_ms"] * 1e-3
     achieved = sweep_bytes / sweep_s / 1e9 if sweep_s > 0 else None
+    # the grid build (FindValidPoints + SmearPoint): SURVEY 8d counts 2 B per byte-max op, S = P_base * K^2
+    ksz = int(m.dims()["kernel_size"])
+    stamp_bytes = snap["base_points"] * ksz * ksz * 2
+    build_s = snap["build_ms"] * 1e-3
+    stamp_achieved = stamp_bytes / build_s / 1e9 if build_s > 0 else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -340,6 +347,13 @@ def run_ours(args, rank, world, local_rank):
             "share_of_step": snap["sweep_ms"] / max(snap["total_ms"], 1e-9),
             "build_share": snap["build_ms"] / max(snap["total_ms"], 1e-9),
             "reduce_share": snap["reduce_ms"] / max(snap["total_ms"], 1e-9),
+        },
+        "roofline_build": {
+            "kernel": "k_find_valid + k_tile_stamp (AddScans/FindValidPoints/SmearPoint)", "bound": "hbm",
+            "achieved": stamp_achieved, "peak": peak, "unit": "GB/s",
+            "frac": (stamp_achieved / peak) if stamp_achieved else None,
+            "algorithmic_bytes": "2 B x base points x K^2 (K = %d), base points before FindValidPoints" % ksz,
+            "avg_launch_ms": snap["build_ms"] / max(snap["launches"], 1),
         },
         "cpu_baseline": cpu,
     }
