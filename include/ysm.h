@@ -167,6 +167,41 @@ int ysm_occ_copy_counts(const ysm_occ *o, uint32_t *pass_host, uint32_t *hit_hos
 const uint8_t *ysm_occ_device_image(const ysm_occ *o);
 const char *ysm_occ_last_error(void); /* thread-local text of the last failing ysm_occ_* call */
 
+/* ---- loop-closure chain finder: replaces, for a batch of query scans, the reference's Python
+ * GraphSlam.find_possible_loop_closure_chains (yag_slam/graph_slam.py:274-304) with its
+ * breadth-first "near linked" traversal (yag_slam/graph.py:71-98, graph_slam.py:32-39) and
+ * RadiusHashSearch.crude_radius_search (yag_slam/helpers.py:395-431). Vertex ids are scan numbers
+ * (graph.vertices[scan.num], graph_slam.py:275). The result is CSR: chains of query i are
+ * query_chain_ptr[i] .. query_chain_ptr[i+1]; chain c holds vertices members[chain_ptr[c] ..
+ * chain_ptr[c+1]) -- i.e. directly the base_ptr / base_idx lists of ysm_batch. ---- */
+typedef struct ysm_chain_query {
+  int32_t n_vertices;
+  int32_t n_queries;
+  const double *pose_xy;        /* [n_vertices][2] current corrected poses; host */
+  const double *hash_xy;        /* [n_vertices][2] poses the vertices had when RadiusHashSearch hashed them
+                                   (add_vertex / last run_opt); NULL = pose_xy */
+  const int32_t *adj_ptr;       /* [n_vertices+1] CSR adjacency over graph edges, both directions; host */
+  const int32_t *adj_idx;       /* [adj_ptr[n_vertices]] */
+  const int32_t *query_vertex;  /* [n_queries] scan numbers of the query scans */
+  double loop_search_dist;      /* GraphSlam.loop_search_dist (also the hash resolution, graph_slam.py:67) */
+  double crude_r2;              /* (radius + res)**2 as the caller's language evaluates it (helpers.py:423) */
+  double near_dist_sq;          /* distance**2 of make_near_scan_visitor (graph_slam.py:33) */
+  int32_t min_chain_size;       /* GraphSlam.loop_search_min_chain_size, >= 1 */
+  int32_t _pad;
+} ysm_chain_query;
+
+typedef struct ysm_chains ysm_chains;
+
+/* Runs the search on `device` (synchronous w.r.t. the host); the CSR result is held by *out. */
+int ysm_chains_find(const ysm_chain_query *q, int device, void *stream, ysm_chains **out);
+/* sizes of the result (+ kernels launched and their device time in ms; any pointer may be NULL) */
+int ysm_chains_get_counts(const ysm_chains *c, int32_t *n_chains, int32_t *n_members, int32_t *launches,
+                          double *kernel_ms);
+/* query_chain_ptr [n_queries+1], chain_ptr [n_chains+1], members [n_members]; host, any may be NULL */
+int ysm_chains_copy(const ysm_chains *c, int32_t *query_chain_ptr, int32_t *chain_ptr, int32_t *members);
+void ysm_chains_destroy(ysm_chains *c);
+const char *ysm_chains_last_error(void); /* thread-local text of the last failing ysm_chains_* call */
+
 /* ---- introspection for parity tests (not part of the reference surface) ---- */
 #define YSM_DEBUG_KEEP_GRIDS 1 /* do not clear the slot grids after a batch */
 int ysm_set_debug(ysm_handle *h, int32_t flags);

@@ -51,6 +51,13 @@ class YsmOccInfo(C.Structure):
                 ("_pad", C.c_int32)]
 
 
+class YsmChainQuery(C.Structure):
+    _fields_ = [("n_vertices", C.c_int32), ("n_queries", C.c_int32), ("pose_xy", C.c_void_p), ("hash_xy", C.c_void_p),
+                ("adj_ptr", C.c_void_p), ("adj_idx", C.c_void_p), ("query_vertex", C.c_void_p),
+                ("loop_search_dist", C.c_double), ("crude_r2", C.c_double), ("near_dist_sq", C.c_double),
+                ("min_chain_size", C.c_int32), ("_pad", C.c_int32)]
+
+
 RESULT_DTYPE = np.dtype([("response", "<f8"), ("x", "<f8"), ("y", "<f8"), ("heading", "<f8"),
                          ("cov", "<f8", (9,)), ("n_passes", "<i4"), ("n_ties", "<i4"),
                          ("status", "<i4"), ("_pad", "<i4"), ("_reserved", "<f8")])
@@ -62,6 +69,7 @@ EXPORTS = [
     "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
     "ysm_occ_create", "ysm_occ_destroy", "ysm_occ_get_info", "ysm_occ_copy_image", "ysm_occ_copy_counts",
     "ysm_occ_device_image", "ysm_occ_last_error",
+    "ysm_chains_find", "ysm_chains_get_counts", "ysm_chains_copy", "ysm_chains_destroy", "ysm_chains_last_error",
 ]
 
 _lib = None
@@ -120,6 +128,16 @@ def lib():
     L.ysm_occ_device_image.argtypes = [vp]
     L.ysm_occ_last_error.restype = C.c_char_p
     L.ysm_occ_last_error.argtypes = []
+    L.ysm_chains_find.restype = C.c_int
+    L.ysm_chains_find.argtypes = [C.POINTER(YsmChainQuery), C.c_int, vp, C.POINTER(vp)]
+    L.ysm_chains_get_counts.restype = C.c_int
+    L.ysm_chains_get_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f64)]
+    L.ysm_chains_copy.restype = C.c_int
+    L.ysm_chains_copy.argtypes = [vp, vp, vp, vp]
+    L.ysm_chains_destroy.restype = None
+    L.ysm_chains_destroy.argtypes = [vp]
+    L.ysm_chains_last_error.restype = C.c_char_p
+    L.ysm_chains_last_error.argtypes = []
     _lib = L
     return L
 

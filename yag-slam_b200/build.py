@@ -5,7 +5,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libysm_b200.so")
-SOURCES = ["ysm.cu", "ysm_kernels.cuh", "ysm_occ.cu"]
+SOURCES = ["ysm.cu", "ysm_kernels.cuh", "ysm_occ.cu", "ysm_chains.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     # cell indices come from Round(double): no FMA contraction, IEEE div/sqrt (defaults)
@@ -31,7 +31,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, "ysm.cu", "ysm_occ.cu"]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, "ysm.cu", "ysm_occ.cu", "ysm_chains.cu"]
     subprocess.check_call(cmd, cwd=CSRC)
     return SO_PATH
 
