@@ -167,6 +167,18 @@ int ysm_occ_copy_counts(const ysm_occ *o, uint32_t *pass_host, uint32_t *hit_hos
 const uint8_t *ysm_occ_device_image(const ysm_occ *o);
 const char *ysm_occ_last_error(void); /* thread-local text of the last failing ysm_occ_* call */
 
+/* ---- match against a map image: replaces the reference's (numba, unfinished) map path --
+ * occupancy_grid_map_to_correlation_grid (yag_slam/helpers.py:24-34) +
+ * Scan2DMatcherPy.match_scan_sets_with_map (yag_slam/scan_matching.py:124-173) -- with Karto's grid
+ * semantics. The handle holds ONE resident correlation grid: image cell (u, v) is ROI cell (u, v) whose
+ * world position is (offset_x + u*resolution, offset_y + v*resolution); cells equal to occupied_value
+ * are 100 and smeared with params->smear_deviation. params->resolution must be the map's resolution.
+ * ysm_match_batch on such a handle runs the usual MatchScan schedule of every query against that grid
+ * (base lists are ignored; nothing is built or cleared per match). img: uint8 [h][w], host. ---- */
+int ysm_create_map(const ysm_params *params, const uint8_t *img, int32_t h, int32_t w,
+                   int32_t occupied_value, double offset_x, double offset_y, int device,
+                   ysm_handle **out);
+
 /* ---- loop-closure chain finder: replaces, for a batch of query scans, the reference's Python
  * GraphSlam.find_possible_loop_closure_chains (yag_slam/graph_slam.py:274-304) with its
  * breadth-first "near linked" traversal (yag_slam/graph.py:71-98, graph_slam.py:32-39) and

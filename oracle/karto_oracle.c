@@ -171,14 +171,14 @@ static int calculate_kernel(ko_matcher *m) {
 }
 
 /* ---- A.1 ScanMatcher::Create ---------------------------------------------- */
-ko_matcher *ko_create(const ko_params *p) {
+static ko_matcher *create_with_roi(const ko_params *p, int roi_override) {
   if (p->resolution <= 0 || p->search_size <= 0 || p->smear_deviation < 0 || p->range_threshold <= 0)
     return NULL;
   ko_matcher *m = (ko_matcher *)calloc(1, sizeof(ko_matcher));
   m->p = *p;
   m->side = (int)(uint32_t)(kt_round(p->search_size / p->resolution) + 1);
   m->margin = (int)(uint32_t)ceil(p->range_threshold / p->resolution);
-  m->roi = m->side + 2 * m->margin;
+  m->roi = roi_override > 0 ? roi_override : m->side + 2 * m->margin;
   /* CorrelationGrid::CreateGrid: border from the raw resolution */
   m->border = (int)kt_round(2.0 * p->smear_deviation / p->resolution) + 1;
   m->width = m->roi + 2 * m->border;
@@ -199,6 +199,8 @@ ko_matcher *ko_create(const ko_params *p) {
   m->lookup_cap = 0;
   return m;
 }
+
+ko_matcher *ko_create(const ko_params *p) { return create_with_roi(p, 0); }
 
 void ko_destroy(ko_matcher *m) {
   if (!m) return;
@@ -547,10 +549,12 @@ static double correlate_scan(ko_matcher *m, const double *qpts, int nq, const do
  * query_pts: the query's filtered world point readings (nq xy pairs) at query_pose.
  * base_pts: concatenated filtered world point readings of the base scans.
  * out[13] = {response, x, y, heading, cov[0..8]} */
+static int match_schedule(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
+                          int do_penalize, int do_refine, double *out);
+
 int ko_match(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
              const double *base_pts, const int *base_counts, int nbase, int do_penalize,
              int do_refine, double *out) {
-  double mean[3];
   double cov[9];
   memset(cov, 0, sizeof(cov));
   cov[0] = cov[4] = cov[8] = 1.0; /* Matrix3 default-constructs... the wrapper hands in identity */
@@ -579,6 +583,16 @@ int ko_match(ko_matcher *m, const double *query_pts, int nq, const double *query
     }
     free(mask);
   }
+  return match_schedule(m, query_pts, nq, query_pose, do_penalize, do_refine, out);
+}
+
+/* coarse -> response expansion -> fine (A.5 steps 1-3) on the grid m currently holds */
+static int match_schedule(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
+                          int do_penalize, int do_refine, double *out) {
+  double mean[3];
+  double cov[9];
+  memset(cov, 0, sizeof(cov));
+  cov[0] = cov[4] = cov[8] = 1.0;
   double csx = 0.5 * (m->side - 1) * m->res_eff;
   double csy = 0.5 * (m->side - 1) * m->res_eff;
   double crx = 2 * m->res_eff, cry = 2 * m->res_eff;
@@ -609,6 +623,48 @@ int ko_match(ko_matcher *m, const double *query_pts, int nq, const double *query
   out[1] = mean[0]; out[2] = mean[1]; out[3] = mean[2];
   memcpy(out + 4, cov, sizeof(cov));
   return 0;
+}
+
+/* ---- match against a map image --------------------------------------------------
+ * The reference sketches this with its numba twin: occupancy_grid_map_to_correlation_grid
+ * (yag_slam/helpers.py:24-34: every cell equal to occupied_value is set to full occupancy and smeared,
+ * no skip rule) and Scan2DMatcherPy.match_scan_sets_with_map (yag_slam/scan_matching.py:124-173, which
+ * calls an un-imported function and cannot run). Restated here with Karto's grid semantics: the
+ * correlation grid's ROI is the map (cell (u, v) of the image = ROI cell (u, v), world offset (ox, oy) =
+ * position of image cell (0, 0)), side = max(w, h) cells, usual border; occupied cells are 100 and
+ * every one of them is smeared (pure max: order independent); MatchScan then runs its usual schedule
+ * (A.5) on that fixed grid. Parity unpinned (no runnable reference). */
+ko_matcher *ko_create_map(const ko_params *p, const uint8_t *img, int h, int w, int occupied_value,
+                          double ox, double oy) {
+  if (!img || h <= 0 || w <= 0) return NULL;
+  ko_matcher *m = create_with_roi(p, h > w ? h : w);
+  if (!m) return NULL;
+  m->grid_off_x = ox;
+  m->grid_off_y = oy;
+  for (int v = 0; v < h; v++)
+    for (int u = 0; u < w; u++)
+      if (img[(size_t)v * w + u] == (uint8_t)occupied_value) {
+        m->grid[(u + m->border) + (size_t)(v + m->border) * m->stride] = GRIDSTATES_OCCUPIED;
+        smear_point(m, u, v);
+      }
+  return m;
+}
+
+int ko_match_map(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
+                 int do_penalize, int do_refine, double *out) {
+  m->last_num_passes = 0;
+  if (nq == 0) {
+    double cov[9];
+    memset(cov, 0, sizeof(cov));
+    out[0] = 0.0;
+    out[1] = query_pose[0]; out[2] = query_pose[1]; out[3] = query_pose[2];
+    cov[0] = MAX_VARIANCE;
+    cov[4] = MAX_VARIANCE;
+    cov[8] = 4 * kt_square(m->p.coarse_angle_resolution);
+    memcpy(out + 4, cov, sizeof(cov));
+    return 0;
+  }
+  return match_schedule(m, query_pts, nq, query_pose, do_penalize, do_refine, out);
 }
 
 /* Only the grid build (AddScans) -- for byte-exact grid parity tests. */

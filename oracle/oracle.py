@@ -67,6 +67,11 @@ def lib():
         L.ko_find_valid_points.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_uint8)]
         L.ko_match.restype = C.c_int
         L.ko_match.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, ip, C.c_int, C.c_int, C.c_int, dp]
+        L.ko_create_map.restype = C.c_void_p
+        L.ko_create_map.argtypes = [C.POINTER(KoParams), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
+                                    C.c_double]
+        L.ko_match_map.restype = C.c_int
+        L.ko_match_map.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.c_int, dp]
         L.ko_build_grid.restype = C.c_int
         L.ko_build_grid.argtypes = [C.c_void_p, dp, dp, ip, C.c_int]
         L.ko_compute_offsets.restype = C.c_int
@@ -207,6 +212,34 @@ class KartoOracle:
         if rc != 0:
             raise RuntimeError("Mapper FATAL ERROR - Unable to find best position")
         return float(out[0]), (float(out[1]), float(out[2]), float(out[3])), out[4:].reshape(3, 3).copy()
+
+
+class KartoMapOracle(KartoOracle):
+    """MatchScan against a fixed correlation grid built from a map image (see
+    ko_create_map in karto_oracle.c): cells equal to occupied_value are 100 and smeared."""
+
+    def __init__(self, cfg, img, offset_xy, occupied_value=0):
+        self.params = make_params(cfg)
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        self._h = lib().ko_create_map(C.byref(self.params), img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[0],
+                                      img.shape[1], int(occupied_value), float(offset_xy[0]), float(offset_xy[1]))
+        if not self._h:
+            raise RuntimeError("oracle: invalid matcher parameters or empty map")
+
+    def match(self, query_pts, query_pose, do_penalize=True, do_refine=False):
+        q = np.ascontiguousarray(query_pts, dtype=np.float64).reshape(-1, 2)
+        pose = np.ascontiguousarray(query_pose, dtype=np.float64)
+        out = np.zeros(13, dtype=np.float64)
+        qq = q if len(q) else np.zeros((1, 2))
+        rc = lib().ko_match_map(self._h, _dp(qq), len(q), _dp(pose), int(do_penalize), int(do_refine), _dp(out))
+        if rc != 0:
+            raise RuntimeError("Mapper FATAL ERROR - Unable to find best position")
+        return out
+
+    def match_many(self, pool_xy, scan_start, scan_count, query_scan, query_poses, do_penalize=True, do_refine=False):
+        pool_xy = np.asarray(pool_xy, dtype=np.float64).reshape(-1, 2)
+        return np.array([self.match(pool_xy[scan_start[q]:scan_start[q] + scan_count[q]], query_poses[i], do_penalize,
+                                    do_refine) for i, q in enumerate(query_scan)]).reshape(-1, 13)
 
 
 def match_batch(cfg, pool_xy, scan_start, scan_count, query_scan, query_poses, base_ptr, base_idx,

@@ -64,7 +64,7 @@ RESULT_DTYPE = np.dtype([("response", "<f8"), ("x", "<f8"), ("y", "<f8"), ("head
 assert RESULT_DTYPE.itemsize == 128
 
 EXPORTS = [
-    "ysm_create", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
+    "ysm_create", "ysm_create_map", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
     "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
     "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
     "ysm_occ_create", "ysm_occ_destroy", "ysm_occ_get_info", "ysm_occ_copy_image", "ysm_occ_copy_counts",
@@ -88,6 +88,8 @@ def lib():
     vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
     L.ysm_create.restype = C.c_int
     L.ysm_create.argtypes = [C.POINTER(YsmParams), C.c_int, C.POINTER(vp)]
+    L.ysm_create_map.restype = C.c_int
+    L.ysm_create_map.argtypes = [C.POINTER(YsmParams), vp, i32, i32, i32, f64, f64, C.c_int, C.POINTER(vp)]
     L.ysm_destroy.restype = None
     L.ysm_destroy.argtypes = [vp]
     L.ysm_last_error.restype = C.c_char_p

@@ -287,6 +287,10 @@ struct ysm_handle {
   cudaEvent_t lane_event = nullptr;
   DevBuf d_pool_shared;
   bool ordered_stamps = false;  // wide smear: AddScan's skip rule is order dependent
+  // match-against-map handles (ysm_create_map): ONE resident correlation grid built from a map image,
+  // every match of a batch sweeps slot 0; nothing is built or cleared per match
+  bool static_grid = false;
+  double map_ox = 0.0, map_oy = 0.0;
   size_t order_smem_attr = 0;
   int64_t work[16] = {0};
   unsigned long long* d_issued = nullptr;  // device counter: lookups the pruned sweep really issued
@@ -340,7 +344,7 @@ static void build_stamp_table(const std::vector<uint8_t>& kern, int K, int& Wt, 
       for (int i = 0; i < K; i++) tab[((size_t)a * K + j) * Wt + 24 + a + i] = kern[(size_t)i + (size_t)K * j];
 }
 
-static int create_one(const ysm_params* p, int device, ysm_handle** out) {
+static int create_one(const ysm_params* p, int device, ysm_handle** out, int roi_override = 0) {
   if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
   *out = nullptr;
   if (!(p->resolution > 0) || !(p->search_size > 0) || p->smear_deviation < 0 || !(p->range_threshold > 0))
@@ -363,7 +367,7 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out) {
   h->side = (int)(uint32_t)(h_round(p->search_size / p->resolution) + 1);
   h->margin = (int)(uint32_t)ceil(p->range_threshold / p->resolution);
   GridC& g = h->g;
-  g.roi = h->side + 2 * h->margin;
+  g.roi = roi_override > 0 ? roi_override : h->side + 2 * h->margin;
   g.border = (int)h_round(2.0 * p->smear_deviation / p->resolution) + 1;
   g.width = g.roi + 2 * g.border;
   g.height = g.width;
@@ -491,6 +495,90 @@ extern "C" int ysm_create(const ysm_params* p, int device, ysm_handle** out) {
       ysm_destroy(h);
       return fail(nullptr, YSM_ECUDA, std::string("lane stream creation failed: ") + cudaGetErrorString(e));
     }
+  }
+  *out = h;
+  return YSM_OK;
+}
+
+// ---- match against a map image ----------------------------------------------------
+// occupancy_grid_map_to_correlation_grid (reference yag_slam/helpers.py:24-34) with Karto's grid
+// semantics: image cell (u, v) is ROI cell (u, v); cells equal to occupied_value become 100 and every
+// one of them is smeared with the kernel (pure max, no skip rule -- order independent). Gather form:
+// one thread per grid cell takes the max over the K x K window of source cells.
+__global__ void __launch_bounds__(256)
+k_map_smear(GridC g, const uint8_t* __restrict__ img, int ih, int iw, int occ, const uint8_t* __restrict__ kern,
+            uint8_t* __restrict__ grid) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.stride || y >= g.height) return;
+  const int tx = x - g.border, ty = y - g.border, hk = g.half_kernel, K = g.K;
+  unsigned v = 0;
+  if (x < g.width) {
+    for (int j = -hk; j <= hk; j++) {
+      const int sv = ty - j;
+      if (sv < 0 || sv >= ih) continue;
+      const uint8_t* row = img + (size_t)sv * iw;
+      for (int i = -hk; i <= hk; i++) {
+        const int su = tx - i;
+        if (su < 0 || su >= iw) continue;
+        if ((int)__ldg(row + su) == occ) v = max(v, (unsigned)__ldg(kern + (i + hk) + K * (j + hk)));
+      }
+    }
+  }
+  grid[(size_t)y * g.stride + x] = (uint8_t)v;
+}
+
+// row masks of the resident grid (one word per 32 x 32 tile: which tile rows hold a non-zero cell) --
+// what k_tile_stamp leaves for scan-built grids; the pruned sweep reads them
+__global__ void __launch_bounds__(256)
+k_map_rowmask(GridC g, const uint8_t* __restrict__ grid, uint32_t* __restrict__ rowmask, int tnx, int ntiles) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= ntiles) return;
+  const int ty = tile / tnx, tx = tile - ty * tnx;
+  const int row = ty * YSM_TILE + lane;
+  bool nz = false;
+  if (row < g.height) {
+    for (int k = 0; k < YSM_TILE; k++) {
+      const int x = tx * YSM_TILE + k;
+      if (x < g.stride && grid[(size_t)row * g.stride + x] != 0) nz = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  if (lane == 0) rowmask[tile] = m;
+}
+
+extern "C" int ysm_create_map(const ysm_params* p, const uint8_t* img, int32_t ih, int32_t iw, int32_t occupied_value,
+                              double offset_x, double offset_y, int device, ysm_handle** out) {
+  if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
+  *out = nullptr;
+  if (!img || ih <= 0 || iw <= 0) return fail(nullptr, YSM_EINVAL, "ysm_create_map: empty map image");
+  ysm_params q = *p;
+  q.max_slots = 1;
+  q.lanes = 1;
+  ysm_handle* h = nullptr;
+  int rc = create_one(&q, device, &h, std::max(ih, iw));
+  if (rc != YSM_OK) return rc;
+  h->static_grid = true;
+  h->ordered_stamps = false;  // every occupied cell is smeared: no order dependence in map mode
+  h->map_ox = offset_x;
+  h->map_oy = offset_y;
+  const GridC& g = h->g;
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_img, (size_t)ih * iw);
+  if (e == cudaSuccess) e = cudaMemcpy(d_img, img, (size_t)ih * iw, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    dim3 grid((g.stride + 255) / 256, g.height);
+    k_map_smear<<<grid, 256>>>(g, d_img, ih, iw, occupied_value, h->d_kernel, h->d_grids);
+    const int ntiles = h->tnx * h->tnx;
+    k_map_rowmask<<<(ntiles + 7) / 8, 256>>>(g, h->d_grids, h->d_rowmask, h->tnx, ntiles);
+    h->launches += 2;
+    e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (d_img) cudaFree(d_img);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("ysm_create_map: ") + cudaGetErrorString(e);
+    ysm_destroy(h);
+    return fail(nullptr, YSM_ECUDA, msg);
   }
   *out = h;
   return YSM_OK;
@@ -708,7 +796,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
   // Latency path: a handful of matches over a small pool. Everything the GPU needs (points,
   // descriptors, pass tables) travels in ONE host->device copy, the fine pass is chained on the
   // device behind the coarse pass (k_reduce points it at the winner), and the host synchronises once.
-  const bool small = b->n_matches <= 8 && b->n_matches <= h->slots &&
+  const bool small = b->n_matches <= 8 && (h->static_grid || b->n_matches <= h->slots) &&
                      (b->pool_on_device || (size_t)b->n_points * 16 <= (1u << 20)) && b->n_scans <= 4096;
   const bool speculate = small && b->do_refine && !(h->debug & YSM_DEBUG_NO_SPECULATE);
 
@@ -743,7 +831,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
   const int tiles_per_stamp = tps1 * tps1;
   const double csx = 0.5 * (h->side - 1) * h->res_eff;
   const double crx = 2 * h->res_eff;
-  const int S = h->slots;
+  const int S = h->static_grid ? 4096 : h->slots;  // matches per wave
   const int nAf = n_steps(0.5 * h->prm.coarse_angle_resolution, h->prm.fine_search_angle_resolution);
 
   std::vector<MatchState> states;
@@ -774,7 +862,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       const int mi = w0 + i;
       MatchState& s = states[i];
       s.idx = mi;
-      s.slot = i;
+      s.slot = h->static_grid ? 0 : i;
       s.q = b->query_scan[mi];
       s.P = b->scan_count[s.q];
       s.pose[0] = b->query_pose[3 * mi];
@@ -782,6 +870,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       s.pose[2] = b->query_pose[3 * mi + 2];
       s.gox = s.pose[0] - (0.5 * (g.roi - 1) * h->res_eff);
       s.goy = s.pose[1] - (0.5 * (g.roi - 1) * h->res_eff);
+      if (h->static_grid) { s.gox = h->map_ox; s.goy = h->map_oy; }
       s.stage = 0;
       s.angle_offset_cur = h->prm.coarse_search_angle_offset;
       s.n_passes = 0;
@@ -791,10 +880,10 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       memset(s.cov, 0, sizeof(s.cov));
       s.mean[0] = s.pose[0]; s.mean[1] = s.pose[1]; s.mean[2] = s.pose[2];
       MatchDev& m = hm[i];
-      m.slot = i;
+      m.slot = h->static_grid ? 0 : i;
       m.base_begin = (int)hbase.size();
       long long mc = 0;
-      if (s.P > 0) {
+      if (s.P > 0 && !h->static_grid) {
         for (int k = b->base_ptr[mi]; k < b->base_ptr[mi + 1]; k++) {
           hbase.push_back(b->base_idx[k]);
           if (small) hscans.push_back(ScanRef{i, k - b->base_ptr[mi], (int)mc, 0});
@@ -820,7 +909,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         s.cov[8] = 4 * h_square(h->prm.coarse_angle_resolution);
         s.best = 0.0;
       }
-      h->last_slot_of_match[mi] = i;
+      h->last_slot_of_match[mi] = h->static_grid ? 0 : i;
     }
     if (cells_total > 0x7fffff00LL) return fail(h, YSM_ENOMEM, "wave has too many base points");
     CK(h->d_cells.ensure(std::max<size_t>(4, (size_t)cells_total * 4)));
@@ -1110,6 +1199,10 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     // ---- K1: grid build ------------------------------------------------------------------------
     auto launch_build = [&]() -> int {
       if (timing) CK(cudaEventRecord(h->ev[0], st));
+      if (h->static_grid) {  // the map grid is resident: nothing to build
+        if (timing) CK(cudaEventRecord(h->ev[1], st));
+        return YSM_OK;
+      }
       const size_t bits_bytes = (size_t)((tiles_per_grid + 3) / 4) * 4;  // one byte per tile
       const size_t fixed = 16 * (size_t)nbase_max + bits_bytes;
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
@@ -1190,7 +1283,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       tr.mark("pass plan (host libm)");
       const char* db = nullptr;
       // latency path, first iteration: everything in ONE cooperative kernel (k_match_small)
-      bool mega = !built && small && !timing && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
+      bool mega = !built && small && !timing && !h->static_grid && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
                   !pl.pa.empty() && pl.fine.empty() && nbase_max <= 64 && hscans.size() <= 512;
       int mega_tpc = 0, mega_psplit = 1, mega_chunks = 0, mega_stage = 0, mega_fvw = 0, mega_log2cap = 6;
       size_t mega_smem = 0;
@@ -1554,7 +1647,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       r._pad = 0;
       r._reserved = 0.0;
     }
-    if (built) {
+    if (built && !h->static_grid) {
       if ((h->debug & YSM_DEBUG_KEEP_GRIDS) && w1 >= b->n_matches) {
         h->grids_dirty = true;  // cleared at the start of the next call (the work list stays resident)
       } else {
@@ -1642,6 +1735,12 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
 // --------------------------------------------------------------------------------------------
 extern "C" int ysm_debug_copy_grid(ysm_handle* h, int32_t match, uint8_t* out_host) {
   if (!h || !out_host) return YSM_EINVAL;
+  if (h->static_grid) {  // the resident map grid
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_host, h->d_grids, (size_t)h->g.data_size, cudaMemcpyDeviceToHost));
+    return YSM_OK;
+  }
   if (match < h->last_wave_begin || match >= h->last_wave_end || !h->grids_dirty)
     return fail(h, YSM_EINVAL, "grid of that match is not resident (set YSM_DEBUG_KEEP_GRIDS; last wave only)");
   CK(cudaSetDevice(h->device));

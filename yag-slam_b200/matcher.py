@@ -162,6 +162,52 @@ class ScanMatcherB200(object):
         return out
 
 
+class MapMatcherB200(ScanMatcherB200):
+    """MatchScan against ONE resident correlation grid built from a map image (SURVEY.md 8(f)-3;
+    ysm_create_map in include/ysm.h). Stands in for the reference's unfinished numba map path
+    (occupancy_grid_map_to_correlation_grid, yag_slam/helpers.py:24-34, and
+    Scan2DMatcherPy.match_scan_sets_with_map, yag_slam/scan_matching.py:124-173) with Karto's grid
+    semantics. `img` is uint8 [h][w] (row 0 = minimum y), `offset_xy` the world position of cell
+    (0, 0), cfg["resolution"] the map resolution; cells equal to `occupied_value` (0 in the
+    reference's map convention, ros1/slam_node_ros1:199-202) are occupied."""
+
+    def __init__(self, cfg, img, offset_xy, occupied_value=0, device=0):
+        d = dict(DEFAULTS)
+        if cfg:
+            d.update({k: v for k, v in dict(cfg).items() if k in d})
+        self.cfg = d
+        p = _capi.YsmParams()
+        for n in _capi.PARAM_FIELDS:
+            setattr(p, n, float(d[n]))
+        p.use_response_expansion = int(bool(d["use_response_expansion"]))
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 2 or img.size == 0:
+            raise ValueError("map image must be a non-empty 2-D uint8 array")
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        rc = self._lib.ysm_create_map(C.byref(p), img.ctypes.data, img.shape[0], img.shape[1], int(occupied_value),
+                                      float(offset_xy[0]), float(offset_xy[1]), int(device), C.byref(self._h))
+        if rc != _capi.YSM_OK:
+            msg = _capi.last_error(None)
+            self._h = None
+            raise _ERRORS.get(rc, RuntimeError)(msg)
+        self.device = int(device)
+        self.map_shape = img.shape
+
+    def correlation_grid(self):
+        """The resident grid cropped to the map, uint8 0..100 (what
+        occupancy_grid_map_to_correlation_grid returns, scaled by 100)."""
+        d = self.dims()
+        b = d["border"]
+        return self.debug_grid(0)[b:b + self.map_shape[0], b:b + self.map_shape[1]]
+
+    def match_map(self, pool_xy, scan_start, scan_count, query_scan, query_pose, penalty=True, do_fine=False, stream=0):
+        """Every query scan (point readings at its initial pose) against the map grid: one record per query."""
+        n = len(query_scan)
+        return self.match_pool(pool_xy, scan_start, scan_count, query_scan, query_pose, np.zeros(n + 1, np.int32),
+                               np.zeros(0, np.int32), penalty, do_fine, stream)
+
+
 def pack_pool(scans_points):
     """Concatenate per-scan (k_i, 2) point-reading arrays into (pool_xy, scan_start, scan_count)."""
     counts = np.array([len(p) for p in scans_points], dtype=np.int32)
