@@ -519,3 +519,56 @@ def test_single_rank_nccl_gather(world):
         dist.destroy_process_group()
     assert full.tobytes() == ref.tobytes()
     m.close()
+
+
+def test_wave_sliced_pool_upload(world):
+    """Lanes + host-resident pool: the pool is uploaded wave by wave (merged contiguous scan ranges, an
+    event behind every wave). Log-shaped access (scan k vs scans k-3..k-1: few ranges per wave), a
+    shuffled pool (fragmented: falls back to one copy) and a pinned pool all give the single-lane records."""
+    import torch
+    from oracle import oracle
+    from yag_slam_b200 import synth
+    from yag_slam_b200.matcher import pack_pool
+    n, P, L = 401, 180, 3
+    rng = np.random.default_rng(77)
+    path = synth.loop_path(n, step=0.2)
+    guess = path + np.concatenate([rng.uniform(-0.08, 0.08, (n, 2)), rng.uniform(-0.03, 0.03, (n, 1))], axis=1)
+    base_pts = [scenarios_scan_points(world, path[i], P, rng) for i in range(n)]
+    query_pts = [scenarios_scan_points(world, path[i], P, rng, guess[i]) for i in range(n)]
+    order = np.arange(2 * n)
+    for shuffled in (False, True):
+        if shuffled:
+            order = rng.permutation(2 * n)
+        inv = np.argsort(order)  # scan id -> position in the pool
+        allpts = base_pts + query_pts
+        pool, starts_p, counts_p = pack_pool([allpts[j] for j in order])
+        starts, counts = starts_p[inv], counts_p[inv]  # indexed by scan id
+        qs = np.arange(n + 1, 2 * n, dtype=np.int32)
+        bp, bi = [0], []
+        for k in range(1, n):
+            bi.extend(range(max(0, k - L), k))
+            bp.append(len(bi))
+        args = (starts, counts, qs, guess[1:], np.array(bp, np.int32), np.array(bi, np.int32), True, True)
+        m1 = _matcher(None, max_slots=64, lanes=1)
+        a = m1.match_pool(pool, *args).copy()
+        m1.close()
+        m2 = _matcher(None, max_slots=128, lanes=2)
+        c = m2.match_pool(pool, *args).copy()
+        assert m2.last_work()["lanes"] == 2
+        if not shuffled:  # only what the matches reference crosses the bus (scan 0's query copy never does)
+            assert m2.last_work()["h2d_bytes"] < pool.nbytes + 4 * 1024 * 1024
+        pinned = torch.from_numpy(pool).pin_memory()
+        d = m2.match_pool(pinned, *args).copy()
+        m2.close()
+        assert a.tobytes() == c.tobytes() == d.tobytes(), "shuffled=%s" % shuffled
+    ref = oracle.match_batch(None, pool, starts, counts, qs, guess[1:], np.array(bp, np.int32), np.array(bi, np.int32),
+                             True, True)
+    _assert_parity(a, ref, "sliced upload")
+
+
+def scenarios_scan_points(world, pose, P, rng, sense_at=None):
+    # points of a scan taken at `pose`, expressed at `sense_at` (the query's initial guess) when given
+    from yag_slam_b200 import synth
+    if sense_at is None:
+        return synth.scan_points(world, pose, P, rng)
+    return synth.scan_points(world, sense_at, P, rng, sense_pose=pose)

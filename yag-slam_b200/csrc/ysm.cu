@@ -15,6 +15,7 @@
 #include <pthread.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <string>
 #include <unordered_map>
@@ -291,6 +292,13 @@ struct ysm_handle {
   // every match of a batch sweeps slot 0; nothing is built or cleared per match
   bool static_grid = false;
   double map_ox = 0.0, map_oy = 0.0;
+  // lanes with a host-resident pool: the pool is uploaded wave by wave on the caller's stream; a lane
+  // waits, before wave [lo, hi) of its share, for the event recorded behind that wave's scans
+  struct SliceWait { int lo, hi; cudaEvent_t ev; bool waited; int seq; std::atomic<int>* seq_done; };
+  std::vector<SliceWait> slice_wait;
+  std::vector<cudaEvent_t> slice_events;  // pool of events (main handle)
+  cudaStream_t upload_stream = nullptr;   // the uploader thread's stream (main handle)
+  std::atomic<int> upload_seq{0};         // slices whose event the uploader has recorded so far
   size_t order_smem_attr = 0;
   int64_t work[16] = {0};
   unsigned long long* d_issued = nullptr;  // device counter: lookups the pruned sweep really issued
@@ -592,6 +600,8 @@ extern "C" void ysm_destroy(ysm_handle* h) {
   h->lanes.clear();
   if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
   if (h->lane_event) cudaEventDestroy(h->lane_event);
+  for (cudaEvent_t ev : h->slice_events) cudaEventDestroy(ev);
+  if (h->upload_stream) cudaStreamDestroy(h->upload_stream);
   h->d_pool_shared.release();
   if (h->d_grids) cudaFree(h->d_grids);
   if (h->d_rowmask) cudaFree(h->d_rowmask);
@@ -849,6 +859,12 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
   for (int w0 = 0; w0 < b->n_matches; w0 += S) {
     const int w1 = std::min(b->n_matches, w0 + S);
     const int nw = w1 - w0;
+    for (ysm_handle::SliceWait& sw : h->slice_wait)
+      if (!sw.waited && sw.lo < w1 && sw.hi > w0) {  // this wave's scans are (being) uploaded behind sw.ev
+        while (sw.seq_done->load(std::memory_order_acquire) <= sw.seq) std::this_thread::yield();  // until recorded
+        CK(cudaStreamWaitEvent(st, sw.ev, 0));
+        sw.waited = true;
+      }
     h->last_wave_begin = w0;
     h->last_wave_end = w1;
     // ---- wave setup: match descriptors, base lists ------------------------------------------
@@ -1685,18 +1701,85 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   CK(cudaSetDevice(h->device));
   ysm_batch sb = *b;
   int64_t h2d = 0;
-  if (!b->pool_on_device) {
-    CK(h->d_pool_shared.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
-    if (b->n_points > 0)
-      CK(cudaMemcpyAsync(h->d_pool_shared.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
-    h2d = (int64_t)b->n_points * 16;
-    sb.pool_xy = (const double*)h->d_pool_shared.p;
-    sb.pool_on_device = 1;
-  }
-  CK(cudaEventRecord(h->lane_event, st));
   std::vector<ysm_handle*> hs;
   hs.push_back(h);
   for (ysm_handle* sub : h->lanes) hs.push_back(sub);
+  for (ysm_handle* x : hs) x->slice_wait.clear();
+  bool lane_event_recorded = false;
+  // wave-sliced pool upload (host-resident pool): what the uploader thread sends, in order
+  struct UploadSlice { std::vector<std::pair<int64_t, int64_t>> ranges; cudaEvent_t ev; };
+  std::vector<UploadSlice> plan;
+  if (!b->pool_on_device) {
+    CK(h->d_pool_shared.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
+    sb.pool_xy = (const double*)h->d_pool_shared.p;
+    sb.pool_on_device = 1;
+    // Upload the pool wave by wave (lane 0 wave 0, lane 1 wave 0, lane 0 wave 1, ...): only the scans a
+    // wave references and no earlier wave brought, as merged contiguous ranges, with an event behind each
+    // wave -- so the first waves start after a fraction of the pool and the rest of the copy overlaps
+    // their kernels. Bad indices or a fragmented access pattern fall back to one whole-pool copy.
+    bool sliced = b->n_points > 0 && b->n_scans > 0 && getenv("YSM_NO_SLICED_UPLOAD") == nullptr;
+    for (int s = 0; sliced && s < b->n_scans; s++)
+      if (b->scan_count[s] < 0 || b->scan_start[s] < 0 || (int64_t)b->scan_start[s] + b->scan_count[s] > b->n_points) sliced = false;
+    for (int i = 0; sliced && i < b->n_matches; i++) {
+      if (b->query_scan[i] < 0 || b->query_scan[i] >= b->n_scans || b->base_ptr[i + 1] < b->base_ptr[i]) sliced = false;
+      for (int k = b->base_ptr[i]; sliced && k < b->base_ptr[i + 1]; k++)
+        if (b->base_idx[k] < 0 || b->base_idx[k] >= b->n_scans) sliced = false;
+    }
+    if (sliced) {
+      CK(cudaEventRecord(h->lane_event, st));  // lanes and uploader start behind the caller's earlier work
+      lane_event_recorded = true;
+      if (!h->upload_stream) CK(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+      h->upload_seq.store(0, std::memory_order_release);
+      std::vector<uint8_t> up((size_t)b->n_scans, 0);
+      std::vector<int> news;
+      int max_waves = 0;
+      for (int l = 0; l < nl; l++) {
+        const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
+        max_waves = std::max(max_waves, (hi - lo + hs[l]->slots - 1) / hs[l]->slots);
+      }
+      for (int w = 0; w < max_waves; w++) {
+        for (int l = 0; l < nl; l++) {
+          const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
+          const int S = hs[l]->slots, r0 = w * S, r1 = std::min(hi - lo, (w + 1) * S);
+          if (r0 >= r1) continue;
+          news.clear();
+          auto need = [&](int sc) {
+            if (!up[sc]) { up[sc] = 1; if (b->scan_count[sc] > 0) news.push_back(sc); }
+          };
+          for (int i = lo + r0; i < lo + r1; i++) {
+            need(b->query_scan[i]);
+            for (int k = b->base_ptr[i]; k < b->base_ptr[i + 1]; k++) need(b->base_idx[k]);
+          }
+          std::sort(news.begin(), news.end(), [&](int a, int c) { return b->scan_start[a] < b->scan_start[c]; });
+          UploadSlice sl;
+          for (int sc : news) {  // merge scans that are adjacent (or overlapping) in the pool
+            const int64_t a = b->scan_start[sc], e = a + b->scan_count[sc];
+            if (!sl.ranges.empty() && a <= sl.ranges.back().second) sl.ranges.back().second = std::max(sl.ranges.back().second, e);
+            else sl.ranges.push_back({a, e});
+          }
+          if (sl.ranges.size() > 64) {  // fragmented: bring everything that is left in one go
+            sl.ranges.assign(1, {0, b->n_points});
+            std::fill(up.begin(), up.end(), 1);
+          }
+          for (const auto& r : sl.ranges) h2d += (r.second - r.first) * 16;
+          const size_t k = plan.size();
+          if (k >= h->slice_events.size()) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->slice_events.push_back(ev);
+          }
+          sl.ev = h->slice_events[k];
+          hs[l]->slice_wait.push_back({r0, r1, sl.ev, false, (int)k, &h->upload_seq});
+          plan.push_back(std::move(sl));
+        }
+      }
+    } else {
+      if (b->n_points > 0)
+        CK(cudaMemcpyAsync(h->d_pool_shared.p, b->pool_xy, (size_t)b->n_points * 16, cudaMemcpyHostToDevice, st));
+      h2d = (int64_t)b->n_points * 16;
+    }
+  }
+  if (!lane_event_recorded) CK(cudaEventRecord(h->lane_event, st));
   std::vector<int> rcs(nl, YSM_OK);
   std::vector<ysm_batch> subs(nl, sb);
   std::vector<std::thread> threads;
@@ -1713,9 +1796,35 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     const int lo = (int)((long long)b->n_matches * l / nl);
     rcs[l] = match_batch_impl(hs[l], &subs[l], out + lo, hs[l]->lane_stream);
   };
+  // The uploader sends the pool in 4 MB pieces on its own stream and waits for each piece before it
+  // submits the next: the H2D copy engine is a FIFO, and the lanes' small descriptor copies must not
+  // queue behind the whole pool. Behind every wave's scans it records that wave's event.
+  cudaError_t up_err = cudaSuccess;
+  auto uploader = [&]() {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->upload_stream, h->lane_event, 0);
+    const char* pe = getenv("YSM_UPLOAD_PIECE_KB");
+    const int64_t piece = std::max<int64_t>(4096, ((pe ? atoll(pe) : 4096) << 10) / 16);  // points (default 4 MB)
+    for (size_t k = 0; k < plan.size(); k++) {
+      for (const auto& r : plan[k].ranges)
+        for (int64_t a = r.first; a < r.second && e == cudaSuccess; a += piece) {
+          const int64_t n = std::min(piece, r.second - a);
+          e = cudaMemcpyAsync((char*)h->d_pool_shared.p + a * 16, (const char*)b->pool_xy + a * 16, (size_t)n * 16,
+                              cudaMemcpyHostToDevice, h->upload_stream);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(h->upload_stream);
+        }
+      if (e == cudaSuccess) e = cudaEventRecord(plan[k].ev, h->upload_stream);
+      // (on an error the lanes are released anyway; the call fails below)
+      h->upload_seq.store((int)k + 1, std::memory_order_release);
+    }
+    up_err = e;
+  };
+  if (!plan.empty()) threads.emplace_back(uploader);
   for (int l = 1; l < nl; l++) threads.emplace_back(run, l);
   run(0);
   for (std::thread& t : threads) t.join();
+  if (up_err != cudaSuccess) return fail(h, YSM_ECUDA, std::string("pool upload: ") + cudaGetErrorString(up_err));
+  for (ysm_handle* x : hs) x->slice_wait.clear();
   // merge the lanes' accounting into the main handle
   for (int l = 1; l < nl; l++) {
     for (int i = 0; i < 16; i++) h->work[i] += hs[l]->work[i];
