@@ -1706,32 +1706,23 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   for (ysm_handle* sub : h->lanes) hs.push_back(sub);
   for (ysm_handle* x : hs) x->slice_wait.clear();
   bool lane_event_recorded = false;
-  // wave-sliced pool upload (host-resident pool): what the uploader thread sends, in order
-  struct UploadSlice { std::vector<std::pair<int64_t, int64_t>> ranges; cudaEvent_t ev; };
+  // Wave-sliced pool upload (host-resident pool). The pool is sent wave by wave (lane 0 wave 0, lane 1
+  // wave 0, lane 0 wave 1, ...): only the scans a wave references and no earlier wave brought, as merged
+  // contiguous ranges, with an event behind each wave -- so the first waves start after a fraction of the
+  // pool and the rest of the copy overlaps their kernels. The ranges are worked out by the uploader
+  // thread itself (below), off the lanes' critical path.
+  struct UploadSlice { int lane, r0, r1; cudaEvent_t ev; };
   std::vector<UploadSlice> plan;
   if (!b->pool_on_device) {
     CK(h->d_pool_shared.ensure(std::max<size_t>(16, (size_t)b->n_points * 16)));
     sb.pool_xy = (const double*)h->d_pool_shared.p;
     sb.pool_on_device = 1;
-    // Upload the pool wave by wave (lane 0 wave 0, lane 1 wave 0, lane 0 wave 1, ...): only the scans a
-    // wave references and no earlier wave brought, as merged contiguous ranges, with an event behind each
-    // wave -- so the first waves start after a fraction of the pool and the rest of the copy overlaps
-    // their kernels. Bad indices or a fragmented access pattern fall back to one whole-pool copy.
-    bool sliced = b->n_points > 0 && b->n_scans > 0 && getenv("YSM_NO_SLICED_UPLOAD") == nullptr;
-    for (int s = 0; sliced && s < b->n_scans; s++)
-      if (b->scan_count[s] < 0 || b->scan_start[s] < 0 || (int64_t)b->scan_start[s] + b->scan_count[s] > b->n_points) sliced = false;
-    for (int i = 0; sliced && i < b->n_matches; i++) {
-      if (b->query_scan[i] < 0 || b->query_scan[i] >= b->n_scans || b->base_ptr[i + 1] < b->base_ptr[i]) sliced = false;
-      for (int k = b->base_ptr[i]; sliced && k < b->base_ptr[i + 1]; k++)
-        if (b->base_idx[k] < 0 || b->base_idx[k] >= b->n_scans) sliced = false;
-    }
+    const bool sliced = b->n_points > 0 && b->n_scans > 0 && getenv("YSM_NO_SLICED_UPLOAD") == nullptr;
     if (sliced) {
       CK(cudaEventRecord(h->lane_event, st));  // lanes and uploader start behind the caller's earlier work
       lane_event_recorded = true;
       if (!h->upload_stream) CK(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
       h->upload_seq.store(0, std::memory_order_release);
-      std::vector<uint8_t> up((size_t)b->n_scans, 0);
-      std::vector<int> news;
       int max_waves = 0;
       for (int l = 0; l < nl; l++) {
         const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
@@ -1742,35 +1733,14 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
           const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
           const int S = hs[l]->slots, r0 = w * S, r1 = std::min(hi - lo, (w + 1) * S);
           if (r0 >= r1) continue;
-          news.clear();
-          auto need = [&](int sc) {
-            if (!up[sc]) { up[sc] = 1; if (b->scan_count[sc] > 0) news.push_back(sc); }
-          };
-          for (int i = lo + r0; i < lo + r1; i++) {
-            need(b->query_scan[i]);
-            for (int k = b->base_ptr[i]; k < b->base_ptr[i + 1]; k++) need(b->base_idx[k]);
-          }
-          std::sort(news.begin(), news.end(), [&](int a, int c) { return b->scan_start[a] < b->scan_start[c]; });
-          UploadSlice sl;
-          for (int sc : news) {  // merge scans that are adjacent (or overlapping) in the pool
-            const int64_t a = b->scan_start[sc], e = a + b->scan_count[sc];
-            if (!sl.ranges.empty() && a <= sl.ranges.back().second) sl.ranges.back().second = std::max(sl.ranges.back().second, e);
-            else sl.ranges.push_back({a, e});
-          }
-          if (sl.ranges.size() > 64) {  // fragmented: bring everything that is left in one go
-            sl.ranges.assign(1, {0, b->n_points});
-            std::fill(up.begin(), up.end(), 1);
-          }
-          for (const auto& r : sl.ranges) h2d += (r.second - r.first) * 16;
           const size_t k = plan.size();
           if (k >= h->slice_events.size()) {
             cudaEvent_t ev;
             CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             h->slice_events.push_back(ev);
           }
-          sl.ev = h->slice_events[k];
-          hs[l]->slice_wait.push_back({r0, r1, sl.ev, false, (int)k, &h->upload_seq});
-          plan.push_back(std::move(sl));
+          hs[l]->slice_wait.push_back({r0, r1, h->slice_events[k], false, (int)k, &h->upload_seq});
+          plan.push_back({l, r0, r1, h->slice_events[k]});
         }
       }
     } else {
@@ -1798,22 +1768,59 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
   };
   // The uploader sends the pool in 4 MB pieces on its own stream and waits for each piece before it
   // submits the next: the H2D copy engine is a FIFO, and the lanes' small descriptor copies must not
-  // queue behind the whole pool. Behind every wave's scans it records that wave's event.
+  // queue behind the whole pool. Behind every wave's scans it records that wave's event. Bad indices
+  // (the lanes will report them) or a fragmented access pattern fall back to sending everything at once.
   cudaError_t up_err = cudaSuccess;
+  int64_t h2d_up = 0;
   auto uploader = [&]() {
     cudaError_t e = cudaSetDevice(h->device);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->upload_stream, h->lane_event, 0);
     const char* pe = getenv("YSM_UPLOAD_PIECE_KB");
     const int64_t piece = std::max<int64_t>(4096, ((pe ? atoll(pe) : 4096) << 10) / 16);  // points (default 4 MB)
+    bool valid = true;
+    for (int sc = 0; valid && sc < b->n_scans; sc++)
+      if (b->scan_count[sc] < 0 || b->scan_start[sc] < 0 || (int64_t)b->scan_start[sc] + b->scan_count[sc] > b->n_points)
+        valid = false;
+    std::vector<uint8_t> up((size_t)b->n_scans, 0);
+    std::vector<int> news;
+    std::vector<std::pair<int64_t, int64_t>> ranges;
+    bool all_sent = false;
     for (size_t k = 0; k < plan.size(); k++) {
-      for (const auto& r : plan[k].ranges)
+      const UploadSlice& sl = plan[k];
+      const int lo = (int)((long long)b->n_matches * sl.lane / nl);
+      news.clear();
+      ranges.clear();
+      for (int i = lo + sl.r0; valid && i < lo + sl.r1; i++) {
+        if (b->query_scan[i] < 0 || b->query_scan[i] >= b->n_scans || b->base_ptr[i + 1] < b->base_ptr[i]) { valid = false; break; }
+        const int q = b->query_scan[i];
+        if (!up[q]) { up[q] = 1; if (b->scan_count[q] > 0) news.push_back(q); }
+        for (int j = b->base_ptr[i]; j < b->base_ptr[i + 1]; j++) {
+          const int sc = b->base_idx[j];
+          if (sc < 0 || sc >= b->n_scans) { valid = false; break; }
+          if (!up[sc]) { up[sc] = 1; if (b->scan_count[sc] > 0) news.push_back(sc); }
+        }
+      }
+      if (valid && !all_sent) {
+        std::sort(news.begin(), news.end(), [&](int a, int c) { return b->scan_start[a] < b->scan_start[c]; });
+        for (int sc : news) {  // merge scans that are adjacent (or overlapping) in the pool
+          const int64_t a = b->scan_start[sc], z = a + b->scan_count[sc];
+          if (!ranges.empty() && a <= ranges.back().second) ranges.back().second = std::max(ranges.back().second, z);
+          else ranges.push_back({a, z});
+        }
+      }
+      if ((!valid || ranges.size() > 64) && !all_sent) {
+        ranges.assign(1, {0, b->n_points});
+        all_sent = true;
+      }
+      for (const auto& r : ranges)
         for (int64_t a = r.first; a < r.second && e == cudaSuccess; a += piece) {
           const int64_t n = std::min(piece, r.second - a);
           e = cudaMemcpyAsync((char*)h->d_pool_shared.p + a * 16, (const char*)b->pool_xy + a * 16, (size_t)n * 16,
                               cudaMemcpyHostToDevice, h->upload_stream);
           if (e == cudaSuccess) e = cudaStreamSynchronize(h->upload_stream);
+          h2d_up += n * 16;
         }
-      if (e == cudaSuccess) e = cudaEventRecord(plan[k].ev, h->upload_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(sl.ev, h->upload_stream);
       // (on an error the lanes are released anyway; the call fails below)
       h->upload_seq.store((int)k + 1, std::memory_order_release);
     }
@@ -1831,7 +1838,7 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     h->t_sweep += hs[l]->t_sweep; h->t_build += hs[l]->t_build; h->t_reduce += hs[l]->t_reduce;
     h->t_total = std::max(h->t_total, hs[l]->t_total);
   }
-  h->work[6] += h2d;
+  h->work[6] += h2d + h2d_up;
   h->work[11] = nl;
   for (int l = 0; l < nl; l++)
     if (rcs[l] != YSM_OK) {
