@@ -261,7 +261,7 @@ struct ysm_handle {
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
   DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
-  DevBuf d_wblob, d_cellmax, d_scan_emit, d_tileflag;
+  DevBuf d_wblob, d_cellmax, d_scan_emit, d_tileflag, d_cand, d_wcand;
   PinBuf h_blob, h_wblob, h_outs, h_angsums, h_flags;
   int epoch = 0;           // completion-flag value of the current latency-kernel launch
   size_t mega_smem_attr = 0;
@@ -613,7 +613,7 @@ extern "C" void ysm_destroy(ysm_handle* h) {
                     &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
                     &h->d_angsums, &h->d_blob, &h->d_wblob, &h->d_cellmax, &h->d_scan_emit,
-                    &h->d_tileflag};
+                    &h->d_tileflag, &h->d_cand, &h->d_wcand};
   for (DevBuf* b : bufs) b->release();
   h->h_blob.release();
   h->h_wblob.release();
@@ -1215,11 +1215,20 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     // ---- K1: grid build ------------------------------------------------------------------------
     auto launch_build = [&]() -> int {
       if (timing) CK(cudaEventRecord(h->ev[0], st));
+      // exact per-tile candidate lists (16-bit counters / cursors in shared memory): not for the ordered
+      // (wide-smear) filter, which edits the cell list afterwards, nor for grids / matches that overflow them
+      const bool use_cand = !h->ordered_stamps && !(h->debug & YSM_DEBUG_NO_CANDLISTS) &&
+                            max_match_cells * tiles_per_stamp <= 65535 && (size_t)tiles_per_grid * 2 <= 64 * 1024;
+      if (use_cand) {
+        CK(h->d_cand.ensure(std::max<size_t>(16, (size_t)cells_total * tiles_per_stamp * 4)));
+        CK(h->d_wcand.ensure(std::max<size_t>(16, (size_t)work_cap * 8)));
+      }
       if (h->static_grid) {  // the map grid is resident: nothing to build
         if (timing) CK(cudaEventRecord(h->ev[1], st));
         return YSM_OK;
       }
-      const size_t bits_bytes = (size_t)((tiles_per_grid + 3) / 4) * 4;  // one byte per tile
+      const size_t bits_bytes = use_cand ? (size_t)((tiles_per_grid + 1) / 2) * 4   // a 16-bit counter per tile
+                                         : (size_t)((tiles_per_grid + 3) / 4) * 4;  // one byte per tile
       const size_t fixed = 16 * (size_t)nbase_max + bits_bytes;
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
       int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
@@ -1241,7 +1250,9 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       k_find_valid<<<nw, nwarps * 32, smem, st>>>(g, d_matches, d_base_idx, d_scan_start, d_scan_count, d_pool,
                                                    (uint32_t*)h->d_ptcell.p, (uint32_t*)h->d_cells.p,
                                                    (int*)h->d_cellcount.p, (uint2*)h->d_gbox.p, (int2*)h->d_work.p,
-                                                   d_workcount, pmax, nbase_max, stage);
+                                                   d_workcount, pmax, nbase_max, stage,
+                                                   use_cand ? (uint32_t*)h->d_cand.p : nullptr,
+                                                   use_cand ? (uint2*)h->d_wcand.p : nullptr, tps1);
       h->launches++;
       kt.mark("k_find_valid");
       if (h->ordered_stamps) {
@@ -1267,7 +1278,9 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
                                                        (const int2*)h->d_work.p, d_workcount, h->d_stamp_tab, h->d_grids,
-                                                       h->d_rowmask, h->rm_words);
+                                                       h->d_rowmask, h->rm_words,
+                                                       use_cand ? (const uint32_t*)h->d_cand.p : nullptr,
+                                                       use_cand ? (const uint2*)h->d_wcand.p : nullptr);
       h->launches++;
       kt.mark("k_tile_stamp");
       if (timing) CK(cudaEventRecord(h->ev[1], st));

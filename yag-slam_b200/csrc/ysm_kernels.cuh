@@ -112,12 +112,47 @@ __device__ int g_fv_trace = 0;
     g_fv_ts[k] = t_;                                                       \
   }
 
+// warp-aggregated bump of the 16-bit counter of tile t (t < 0: this lane has none): lanes naming the same
+// tile are served by ONE shared-memory atomic; returns this lane's slot = old counter value + its rank
+__device__ __forceinline__ unsigned tile_counter_bump(unsigned* s_cnt, int t, int lane) {
+  const unsigned grp = __match_any_sync(0xffffffffu, t);
+  const int leader = __ffs(grp) - 1, sh = 16 * (t & 1);
+  unsigned old = 0u;
+  if (t >= 0 && lane == leader) old = atomicAdd(&s_cnt[t >> 1], (unsigned)__popc(grp) << sh);
+  old = __shfl_sync(0xffffffffu, old, leader);  // full-mask shuffle: every lane reads its group's leader
+  return ((old >> sh) & 0xFFFFu) + (unsigned)__popc(grp & ((1u << lane) - 1u));
+}
+
+// the same for the (up to) 2 x 2 tiles of one cell at once: the four match / atomic / shuffle chains are
+// issued back to back so their latencies overlap
+__device__ __forceinline__ void tile_counter_bump4(unsigned* s_cnt, const int (&t)[4], int lane, unsigned (&slot)[4]) {
+  unsigned grp[4], old[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) grp[k] = __match_any_sync(0xffffffffu, t[k]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    old[k] = 0u;
+    if (t[k] >= 0 && lane == __ffs(grp[k]) - 1)
+      old[k] = atomicAdd(&s_cnt[t[k] >> 1], (unsigned)__popc(grp[k]) << (16 * (t[k] & 1)));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) old[k] = __shfl_sync(0xffffffffu, old[k], __ffs(grp[k]) - 1);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    slot[k] = ((old[k] >> (16 * (t[k] & 1))) & 0xFFFFu) + (unsigned)__popc(grp[k] & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void
 find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, const int* scan_start,
                 const int* scan_count, const double* pool, uint32_t* pt_cell, uint32_t* cells, int* cell_count,
                 uint2* gbox, int2* work, int* work_count, int pmax, int nbase_max, int stage, int vbx,
-                unsigned char* smem_raw, int fv_warps = 0) {
+                unsigned char* smem_raw, int fv_warps = 0, uint32_t* cand = nullptr, uint2* wcand = nullptr,
+                int stamp_tiles_axis = 0) {
+  // cand != nullptr (throughput path): besides the work list, every touched tile gets the exact list of
+  // the cells whose stamp reaches it (wcand[work item] = {offset, count} into cand), so the stamping
+  // kernel needs no candidate search. The per-tile flags are then 16-bit counters / fill cursors.
   __shared__ int s_tile_total, s_tile_base;
+  __shared__ int s_wsum_t[32], s_wsum_c[32];
   // fv_warps > 0: only that many warps take scans (the shared arrays are sized for them)
   const int nwarps = fv_warps > 0 ? min(fv_warps, (int)(blockDim.x >> 5)) : (int)(blockDim.x >> 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,7 +163,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
   unsigned* s_bits = reinterpret_cast<unsigned*>(s_dir + 3 * nbase_max);           // touched-tile flags, one BYTE per tile
   unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_bits);                // (plain stores: no atomics)
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
-  const int nbitw = (tnx * tnx + 3) >> 2;  // words of 4 flags
+  const int nbitw = cand ? (tnx * tnx + 1) >> 1 : (tnx * tnx + 3) >> 2;  // words of 4 byte flags / 2 u16 counters
   // small waves: each warp stages its scan's points in shared memory (SoA) so the filter's
   // dependent loads are LDS instead of L2 round trips
   double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 16 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
@@ -221,7 +256,7 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
                 const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
                 for (int ty = ty0; ty <= ty1; ty++)
                   for (int tx = tx0; tx <= tx1; tx++) {
-                    s_flag[ty * tnx + tx] = 1;
+                    if (!cand) s_flag[ty * tnx + tx] = 1;
                   }
               }
             }
@@ -256,6 +291,116 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
   int tot = 0;
   for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
   if (threadIdx.x == 0) cell_count[vbx] = tot;
+  if (cand) {
+    // ---- exact per-tile candidate lists ------------------------------------------------------------
+    // every thread owns a contiguous chunk of counter words: block-wide exclusive scan of
+    // (touched tiles, candidates), then work items + list offsets, then the fill
+    const int tps1 = stamp_tiles_axis;  // tiles a stamp can span per axis
+    const uint32_t* mc = cells + m.cells_off;
+    __syncthreads();  // the compacted cells (global, written by this CTA) are complete
+    for (int i0 = 0; i0 < tot; i0 += (int)blockDim.x) {  // count pass (block-uniform trip count)
+      const int i = i0 + (int)threadIdx.x;
+      int ax = 0, ay = 0;
+      if (i < tot) {
+        const uint32_t c = mc[i];
+        ax = (int)(c & 0xFFFFu);
+        ay = (int)(c >> 16);
+      }
+      const int tx0 = (ax - g.half_kernel) / YSM_TILE, tx1 = (ax + g.half_kernel) / YSM_TILE;
+      const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
+      if (tps1 == 2) {
+        int t4[4];
+        unsigned sl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          t4[k] = (i < tot && ty0 + (k >> 1) <= ty1 && tx0 + (k & 1) <= tx1) ? (ty0 + (k >> 1)) * tnx + tx0 + (k & 1) : -1;
+        tile_counter_bump4(s_bits, t4, lane, sl);
+      } else {
+        for (int dy = 0; dy < tps1; dy++)
+          for (int dx = 0; dx < tps1; dx++) {
+            const int t = (i < tot && ty0 + dy <= ty1 && tx0 + dx <= tx1) ? (ty0 + dy) * tnx + tx0 + dx : -1;
+            tile_counter_bump(s_bits, t, lane);
+          }
+      }
+    }
+    __syncthreads();
+    const int per = (nbitw + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int w0 = min(nbitw, (int)threadIdx.x * per), w1 = min(nbitw, w0 + per);
+    int nt = 0, nc = 0;
+    for (int w = w0; w < w1; w++) {
+      const unsigned v = s_bits[w], a = v & 0xFFFFu, bb = v >> 16;
+      nt += (a != 0u) + (bb != 0u);
+      nc += (int)(a + bb);
+    }
+    int it = nt, ic = nc;  // inclusive scans inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ut = __shfl_up_sync(0xffffffffu, it, o), uc = __shfl_up_sync(0xffffffffu, ic, o);
+      if (lane >= o) { it += ut; ic += uc; }
+    }
+    if (lane == 31) { s_wsum_t[warp] = it; s_wsum_c[warp] = ic; }
+    __syncthreads();
+    int pt = 0, pc = 0, tt = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      if (w < warp) { pt += s_wsum_t[w]; pc += s_wsum_c[w]; }
+      tt += s_wsum_t[w];
+    }
+    if (threadIdx.x == 0) s_tile_base = tt ? atomicAdd(work_count, tt) : 0;
+    __syncthreads();
+    int pos = s_tile_base + pt + it - nt;
+    unsigned off = (unsigned)(pc + ic - nc);
+    const unsigned cbase = (unsigned)m.cells_off * (unsigned)(tps1 * tps1);
+    for (int w = w0; w < w1; w++) {
+      const unsigned v = s_bits[w], a = v & 0xFFFFu, bb = v >> 16;
+      unsigned cur = 0u;
+      if (a) {
+        work[pos] = make_int2(vbx, 2 * w);
+        wcand[pos] = make_uint2(cbase + off, a);
+        cur |= off;
+        off += a;
+        pos++;
+      }
+      if (bb) {
+        work[pos] = make_int2(vbx, 2 * w + 1);
+        wcand[pos] = make_uint2(cbase + off, bb);
+        cur |= off << 16;
+        off += bb;
+        pos++;
+      }
+      s_bits[w] = cur;  // fill cursors (list-relative; < 65536 by the host's guard)
+    }
+    __syncthreads();
+    for (int i0 = 0; i0 < tot; i0 += (int)blockDim.x) {  // fill pass
+      const int i = i0 + (int)threadIdx.x;
+      uint32_t c = 0u;
+      int ax = 0, ay = 0;
+      if (i < tot) {
+        c = mc[i];
+        ax = (int)(c & 0xFFFFu);
+        ay = (int)(c >> 16);
+      }
+      const int tx0 = (ax - g.half_kernel) / YSM_TILE, tx1 = (ax + g.half_kernel) / YSM_TILE;
+      const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
+      if (tps1 == 2) {
+        int t4[4];
+        unsigned sl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          t4[k] = (i < tot && ty0 + (k >> 1) <= ty1 && tx0 + (k & 1) <= tx1) ? (ty0 + (k >> 1)) * tnx + tx0 + (k & 1) : -1;
+        tile_counter_bump4(s_bits, t4, lane, sl);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (t4[k] >= 0) cand[cbase + sl[k]] = c;
+      } else {
+        for (int dy = 0; dy < tps1; dy++)
+          for (int dx = 0; dx < tps1; dx++) {
+            const int t = (i < tot && ty0 + dy <= ty1 && tx0 + dx <= tx1) ? (ty0 + dy) * tnx + tx0 + dx : -1;
+            const unsigned slot = tile_counter_bump(s_bits, t, lane);
+            if (t >= 0) cand[cbase + slot] = c;
+          }
+      }
+    }
+    return;
+  }
   // touched tiles -> the wave's (match, tile) work list
   int cnt = 0;
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) cnt += __popc(s_bits[i]);
@@ -499,10 +644,11 @@ k_find_valid(GridC g, const MatchDev* __restrict__ matches, const int* __restric
              const int* __restrict__ scan_start, const int* __restrict__ scan_count,
              const double* __restrict__ pool, uint32_t* __restrict__ pt_cell,
              uint32_t* __restrict__ cells, int* __restrict__ cell_count, uint2* __restrict__ gbox,
-             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max, int stage) {
+             int2* __restrict__ work, int* __restrict__ work_count, int pmax, int nbase_max, int stage,
+             uint32_t* __restrict__ cand, uint2* __restrict__ wcand, int stamp_tiles_axis) {
   extern __shared__ __align__(16) unsigned char dsm_fv[];
   find_valid_body(g, matches, base_idx, scan_start, scan_count, pool, pt_cell, cells, cell_count, gbox, work,
-                  work_count, pmax, nbase_max, stage, (int)blockIdx.x, dsm_fv);
+                  work_count, pmax, nbase_max, stage, (int)blockIdx.x, dsm_fv, 0, cand, wcand, stamp_tiles_axis);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -644,7 +790,8 @@ __host__ __device__ __forceinline__ size_t tile_stamp_smem(int K, int Wt, int nw
 __device__ __forceinline__ void
 tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, const int* cell_count,
                 const uint2* gbox, const int2* work, const int* work_count, const uint16_t* stamp_tab, uint8_t* grids,
-                uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm, int S = 1) {
+                uint32_t* rowmask, int rm_words, int vbx, int vgx, unsigned char* dsm, int S = 1,
+                const uint32_t* cand = nullptr, const uint2* wcand = nullptr) {
   // S > 1 (latency path): S warps share one tile -- each scans its share of the cell groups into a
   // private copy of the tile, the copies are max-combined at write-out (named barrier per group)
   __shared__ unsigned s_rows[16];
@@ -678,6 +825,22 @@ tile_stamp_body(const GridC& g, const MatchDev* matches, const uint32_t* cells, 
 #pragma unroll
     for (int k = 0; k < 16; k++) t[k] = 0u;
     int n = 0;
+    if (wcand) {
+      // exact candidate list of this tile (k_find_valid): no search
+      const uint2 wc = wcand[wi];
+      const uint32_t* cl = cand + wc.x;
+      const int cnt = (int)wc.y;
+      for (int i0 = 0; i0 < cnt; i0 += 32) {
+        if (i0 + lane < cnt) list[n + lane] = stamp_step(cl[i0 + lane], h, K, Wt, x0t, y0t);
+        n += min(32, cnt - i0);
+        if (n > YSM_TILE_LIST) {  // warp-uniform
+          __syncwarp();
+          tile_scatter_rows(t, list, n, lane_tab_s, K);
+          __syncwarp();
+          n = 0;
+        }
+      }
+    } else
     for (int gs = 0; gs < ngroups; gs += 32 * S) {
       // groups of 32 cells whose bounding box (grown by the stamp) reaches the tile
       const int g0 = gs + sub * 32;
@@ -763,10 +926,10 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
              const int* __restrict__ cell_count, const uint2* __restrict__ gbox,
              const int2* __restrict__ work, const int* __restrict__ work_count,
              const uint16_t* __restrict__ stamp_tab, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
-             int rm_words) {
+             int rm_words, const uint32_t* __restrict__ cand, const uint2* __restrict__ wcand) {
   extern __shared__ __align__(16) unsigned char dsm_ts[];
   tile_stamp_body(g, matches, cells, cell_count, gbox, work, work_count, stamp_tab, grids, rowmask, rm_words,
-                  (int)blockIdx.x, (int)gridDim.x, dsm_ts);
+                  (int)blockIdx.x, (int)gridDim.x, dsm_ts, 1, cand, wcand);
 }
 
 // zero the tiles a wave touched (the slot grids are kept all-zero between matches). A warp takes 32
