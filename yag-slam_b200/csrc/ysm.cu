@@ -1231,7 +1231,8 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
                                          : (size_t)((tiles_per_grid + 3) / 4) * 4;  // one byte per tile
       const size_t fixed = 16 * (size_t)nbase_max + bits_bytes;
       // small waves: one warp per base scan (up to 32) so the scans are filtered concurrently
-      int nwarps = nw >= 2 * h->num_sms ? 8 : std::min(32, std::max(8, nbase_max));
+      // (large waves: a warp per base scan up to 16, so no warp sits out a second round of scans)
+      int nwarps = nw >= 2 * h->num_sms ? std::min(16, std::max(8, nbase_max)) : std::min(32, std::max(8, nbase_max));
       while (nwarps > 1 && (size_t)nwarps * 4 * pmax + fixed > 200 * 1024) nwarps >>= 1;
       size_t smem = (size_t)nwarps * 4 * pmax + fixed;
       int stage = 0;
