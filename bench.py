@@ -42,16 +42,16 @@ def parse_args():
     ap.add_argument("--beams", type=int, default=720)
     ap.add_argument("--base", type=int, default=10)
     ap.add_argument("--lanes", type=int, default=0,
-                    help="matcher lanes (host threads + streams) per GPU; 0 = 3 when this rank has >= 8 host cores, else 2")
+                    help="matcher lanes (host threads + streams) per GPU; 0 = 3 when this rank has >= 4 host cores, else 2")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
 
 def pick_lanes(args):
-    """Every lane is a host thread that plans passes and waits on its stream: three overlap best on a
-    box with cores to spare (r01s: 307k -> 315k matches/s), two when the ranks of a multi-GPU run share
-    the host (32 cores for 8 ranks on this pool's 8-GPU boxes)."""
+    """Every lane is a host thread that plans passes and waits on its stream. Three overlap best, at
+    N=1 (r01s: 307k -> 315k matches/s on 16 cores) and at N=8 with 4 cores per rank (r01u: 2.34M -> 2.39M);
+    two when a rank has fewer than 4 host cores."""
     if args.lanes > 0:
         return args.lanes
     world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
@@ -59,7 +59,7 @@ def pick_lanes(args):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return 3 if cores // world >= 8 else 2
+    return 3 if cores // world >= 4 else 2
 
 
 def workload_config(args):
