@@ -1554,7 +1554,6 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
 __device__ __forceinline__ void
 reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* offsets, const double* resp, double best,
             const unsigned long long* cellmax, const double* trig, const uint8_t* grids, PassOut* po, int* angsums) {
-  __shared__ double s_tmp[16];
   __shared__ int s_list[YSM_TIE_CAP];
   __shared__ int s_sorted[YSM_TIE_CAP];
   __shared__ int s_count;
@@ -1735,10 +1734,28 @@ reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* of
         }
       }
     }
-    norm = block_reduce_sum(norm, s_tmp);
-    axx = block_reduce_sum(axx, s_tmp);
-    axy = block_reduce_sum(axy, s_tmp);
-    ayy = block_reduce_sum(ayy, s_tmp);
+    // the four sums in one pass (same order per sum as block_reduce_sum: xor-shuffles, then the warps in order)
+    {
+      __shared__ double s_tmp4[32][4];
+      for (int o = 16; o > 0; o >>= 1) {
+        norm += __shfl_xor_sync(0xffffffffu, norm, o);
+        axx += __shfl_xor_sync(0xffffffffu, axx, o);
+        axy += __shfl_xor_sync(0xffffffffu, axy, o);
+        ayy += __shfl_xor_sync(0xffffffffu, ayy, o);
+      }
+      __syncthreads();
+      if ((tid & 31) == 0) {
+        s_tmp4[tid >> 5][0] = norm; s_tmp4[tid >> 5][1] = axx; s_tmp4[tid >> 5][2] = axy; s_tmp4[tid >> 5][3] = ayy;
+      }
+      __syncthreads();
+      if (tid < 4) {
+        double r = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += s_tmp4[w][tid];
+        s_acc[tid] = r;  // (s_acc is free again: avg_x / avg_y were read above)
+      }
+      __syncthreads();
+      norm = s_acc[0]; axx = s_acc[1]; axy = s_acc[2]; ayy = s_acc[3];
+    }
     if (tid == 0) {
       po->norm = norm; po->axx = axx; po->axy = axy; po->ayy = ayy;
     }
@@ -1905,8 +1922,8 @@ __global__ void __launch_bounds__(512, 2)
 k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ PassOut s_po[2];
-  __shared__ PassDev s_f;
-  __shared__ TableDev s_ft;
+  __shared__ PassDev s_f, s_ps;
+  __shared__ TableDev s_ft, s_tb;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #define YSM_TSTAMP(k)                                                                  \
@@ -1935,6 +1952,20 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   const PassAngle* pa_list = reinterpret_cast<const PassAngle*>(db + A.o_pa);
   const double* trig = reinterpret_cast<const double*>(db + A.o_trig);
   double* passmax = reinterpret_cast<double*>(db + A.o_pmax);
+  // The coarse reduce of pass p runs on CTA gridDim-1-p (CTAs from the end of the grid have no scan to
+  // filter and usually no sweep task): it fetches its descriptors -- and the unresolved ones of the
+  // pass's speculative fine pass -- now, off the critical path (two dependent L2 round trips each).
+  const int my_pid = (int)gridDim.x - 1 - (int)blockIdx.x;
+  const bool pre = my_pid < A.ncoarse;
+  if (pre) {
+    load_struct_cg(&s_ps, passes + my_pid, tid);
+    __syncthreads();
+    load_struct_cg(&s_tb, tables + s_ps.table, tid);
+    if (s_ps.spec >= 0) load_struct_cg(&s_f, passes + s_ps.spec, tid);
+    __syncthreads();
+    if (s_ps.spec >= 0) load_struct_cg(&s_ft, tables + s_f.table, tid);
+    __syncthreads();
+  }
   // ---- P1a: FindValidPoints, CTA per base scan ------------------------------------------------------
   const ScanRef* scanlist = reinterpret_cast<const ScanRef*>(db + A.o_scanlist);
   for (int v = blockIdx.x; v < A.nscans_total; v += gridDim.x) {
@@ -1994,18 +2025,14 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   YSM_TSTAMP(7)
   // ---- P4a: per coarse pass: reduce, resolve its fine pass at the winner ------------------------------
   const int nw8 = (int)(sizeof(PassOut) / 8);
-  for (int pid = blockIdx.x; pid < A.ncoarse; pid += gridDim.x) {
-    const PassDev ps = passes[pid];
-    const TableDev tb = tables[ps.table];
+  for (int pid = my_pid; pid < A.ncoarse; pid += gridDim.x) {  // (one iteration: the grid is larger than ncoarse)
+    const PassDev& ps = s_ps;
+    const TableDev& tb = s_tb;
     reduce_body(g, ps, tb, A.offsets, A.resp, __ldcg(passmax + pid), A.cellmax, trig, A.grids, &s_po[0], A.angs_host);
     __syncthreads();
     if (tid < nw8) reinterpret_cast<double*>(A.outs_host + pid)[tid] = reinterpret_cast<const double*>(&s_po[0])[tid];
     if (ps.spec >= 0) {
-      if (tid == 0) {
-        s_f = passes[ps.spec];
-        s_ft = tables[s_f.table];
-        spec_resolve(ps, s_po[0], trig, &s_f, &s_ft);
-      }
+      if (tid == 0) spec_resolve(ps, s_po[0], trig, &s_f, &s_ft);  // s_f / s_ft: preloaded above
       __syncthreads();
       // publish the resolved descriptors for the CTAs of the next phases
       if (tid < (int)(sizeof(PassDev) / 8))
@@ -2028,12 +2055,14 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   grid.sync();
   YSM_TSTAMP(9)
   // ---- P4b: fine sweep, CTA = (fine pass, angle) -----------------------------------------------------
+  int held_fid = -1;  // fine pass whose resolved descriptors sit in s_f / s_ft
   for (int v = blockIdx.x; v < A.nspec * A.nAf; v += gridDim.x) {
     const int fid = A.ncoarse + v / A.nAf, a = v % A.nAf;
     load_struct_cg(&s_f, passes + fid, tid);
     __syncthreads();
     load_struct_cg(&s_ft, tables + s_f.table, tid);
     __syncthreads();
+    held_fid = fid;
     if (a < s_f.nA)
       fine_angle_body(g, pen, s_f, s_ft, fid, a, trig, pool, A.offsets, A.grids, A.resp, passmax, reinterpret_cast<int*>(dsm));
     __syncthreads();
@@ -2044,10 +2073,12 @@ k_match_small(GridC g, PenaltyC pen, SmallArgs A) {
   // ---- P4c: per fine pass: reduce + angular covariance sums, publish --------------------------------
   for (int fi = blockIdx.x; fi < A.nspec; fi += gridDim.x) {
     const int fid = A.ncoarse + fi;
-    load_struct_cg(&s_f, passes + fid, tid);
-    __syncthreads();
-    load_struct_cg(&s_ft, tables + s_f.table, tid);
-    __syncthreads();
+    if (held_fid != fid) {  // (the fine sweep of this CTA already fetched them when fi == 0)
+      load_struct_cg(&s_f, passes + fid, tid);
+      __syncthreads();
+      load_struct_cg(&s_ft, tables + s_f.table, tid);
+      __syncthreads();
+    }
     reduce_body(g, s_f, s_ft, A.offsets, A.resp, __ldcg(passmax + fid), A.cellmax, trig, A.grids, &s_po[1], A.angs_host);
     __syncthreads();
     if (tid < nw8) reinterpret_cast<double*>(A.outs_host + fid)[tid] = reinterpret_cast<const double*>(&s_po[1])[tid];
