@@ -1,7 +1,7 @@
 #!/bin/bash
 # r01t (1 GPU): evidence at HEAD -- full GPU suite, smoke, bench both arms, launch list, ncu --set full of the
 # grid-build kernels (exact candidate lists) and the pruned sweep
-TAG=${1:-r01t}
+TAG=${1:-r01v}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
