@@ -50,6 +50,33 @@ int chain_fail(int code, const std::string& msg) {
 
 constexpr int kChainCap = 1024;  // largest loop_search_min_chain_size (the running chain never gets longer)
 
+// Device scratch of the calling thread, grown on demand and kept between calls (a chain search is a
+// few hundred microseconds of kernels; per-call cudaMalloc / cudaFree would cost milliseconds).
+// Two arenas: inputs + per-query state, and the result lists sized after the counting pass.
+struct Arena {
+  char* p = nullptr;
+  size_t cap = 0, used = 0;
+  int device = -1;
+  cudaError_t reserve(int dev, size_t bytes) {
+    used = 0;
+    if (dev == device && bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0; device = dev;
+    const size_t want = bytes + bytes / 4 + 4096;
+    const cudaError_t e = cudaMalloc((void**)&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T* take(size_t count) {
+    const size_t b = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* r = reinterpret_cast<T*>(p + used);
+    used += b;
+    return r;
+  }
+};
+thread_local Arena t_in, t_out;
+inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
+
 struct ChainArgs {
   int n, nq, q0;             // vertices, queries of this chunk, first query of the chunk
   int nw;                    // visited words per query
@@ -266,16 +293,19 @@ extern "C" int ysm_chains_find(const ysm_chain_query* in, int device, void* stre
   }
   CCK(cudaEventCreate(&ev0));
   CCK(cudaEventCreate(&ev1));
-  CCK(cudaMalloc((void**)&d_pose, 16 * (size_t)n));
-  CCK(cudaMalloc((void**)&d_hash, 16 * (size_t)n));
-  CCK(cudaMalloc((void**)&d_aptr, 4 * (size_t)(n + 1)));
-  CCK(cudaMalloc((void**)&d_aidx, 4 * (size_t)std::max(ne, 1)));
-  CCK(cudaMalloc((void**)&d_query, 4 * (size_t)nq));
-  CCK(cudaMalloc((void**)&d_counts, 8 * (size_t)nq));
-  CCK(cudaMalloc((void**)&d_cbase, 4 * (size_t)nq));
-  CCK(cudaMalloc((void**)&d_mbase, 4 * (size_t)nq));
-  CCK(cudaMalloc((void**)&d_vis, 4 * (size_t)nw * (size_t)nq));  // kept across the two passes
-  CCK(cudaMalloc((void**)&d_queue, 4 * (size_t)n * (size_t)chunk));
+  CCK(t_in.reserve(device, 2 * a256(16 * (size_t)n) + a256(4 * (size_t)(n + 1)) + a256(4 * (size_t)std::max(ne, 1)) +
+                               3 * a256(4 * (size_t)nq) + a256(8 * (size_t)nq) + a256(4 * (size_t)nw * (size_t)nq) +
+                               a256(4 * (size_t)n * (size_t)chunk)));
+  d_pose = t_in.take<double2>((size_t)n);
+  d_hash = t_in.take<double2>((size_t)n);
+  d_aptr = t_in.take<int>((size_t)n + 1);
+  d_aidx = t_in.take<int>((size_t)std::max(ne, 1));
+  d_query = t_in.take<int>((size_t)nq);
+  d_counts = t_in.take<int2>((size_t)nq);
+  d_cbase = t_in.take<int>((size_t)nq);
+  d_mbase = t_in.take<int>((size_t)nq);
+  d_vis = t_in.take<unsigned>((size_t)nw * (size_t)nq);  // kept across the two passes
+  d_queue = t_in.take<int>((size_t)n * (size_t)chunk);
   CCK(cudaMemcpyAsync(d_pose, in->pose_xy, 16 * (size_t)n, cudaMemcpyHostToDevice, st));
   CCK(cudaMemcpyAsync(d_hash, in->hash_xy ? in->hash_xy : in->pose_xy, 16 * (size_t)n, cudaMemcpyHostToDevice, st));
   CCK(cudaMemcpyAsync(d_aptr, in->adj_ptr, 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
@@ -311,8 +341,9 @@ extern "C" int ysm_chains_find(const ysm_chain_query* in, int device, void* stre
   clen.assign((size_t)std::max<long long>(tot_c, 1), 0);
   c->members.assign((size_t)tot_m, 0);
   if (tot_c > 0) {
-    CCK(cudaMalloc((void**)&d_clen, 4 * (size_t)tot_c));
-    CCK(cudaMalloc((void**)&d_mem, 4 * (size_t)std::max<long long>(tot_m, 1)));
+    CCK(t_out.reserve(device, a256(4 * (size_t)tot_c) + a256(4 * (size_t)std::max<long long>(tot_m, 1))));
+    d_clen = t_out.take<int>((size_t)tot_c);
+    d_mem = t_out.take<int>((size_t)std::max<long long>(tot_m, 1));
     CCK(cudaMemcpyAsync(d_cbase, cbase.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
     CCK(cudaMemcpyAsync(d_mbase, mbase.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
     // pass 2: write chain lengths and members
@@ -333,8 +364,6 @@ extern "C" int ysm_chains_find(const ysm_chain_query* in, int device, void* stre
   c->chain_ptr.assign((size_t)tot_c + 1, 0);
   for (long long i = 0; i < tot_c; i++) c->chain_ptr[(size_t)i + 1] = c->chain_ptr[(size_t)i] + clen[(size_t)i];
 done:
-  cudaFree(d_pose); cudaFree(d_hash); cudaFree(d_aptr); cudaFree(d_aidx); cudaFree(d_query); cudaFree(d_counts);
-  cudaFree(d_cbase); cudaFree(d_mbase); cudaFree(d_vis); cudaFree(d_queue); cudaFree(d_clen); cudaFree(d_mem);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (rc != YSM_OK) {
