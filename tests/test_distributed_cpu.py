@@ -21,6 +21,21 @@ def _fake_match(pool, starts, counts, query_scan, query_pose, base_ptr, base_idx
     return out
 
 
+def _fake_trace(img, angles, starts):
+    a = np.asarray(angles, dtype=np.float32)
+    s = np.asarray(starts, dtype=np.float32).reshape(-1, 2)
+    out = np.zeros((len(s), len(a), 5), dtype=np.float32)
+    out[:, :, 0], out[:, :, 1] = s[:, None, 0], s[:, None, 1]
+    out[:, :, 2] = s[:, None, 0] + np.cos(np.deg2rad(a))[None, :]
+    out[:, :, 3] = s[:, None, 1] + np.sin(np.deg2rad(a))[None, :]
+    out[:, :, 4] = 1.0 + s[:, None, 0] * 0.01
+    return out
+
+
+def _starts(n=7):
+    return np.stack([np.arange(n) * 3.0 + 1, np.arange(n) * 2.0 + 5], axis=1)
+
+
 def _problem(n=11):
     rng = np.random.default_rng(0)
     nb = rng.integers(1, 4, n)
@@ -38,7 +53,8 @@ def _worker(rank, world, port, q):
     try:
         args = _problem()
         full = distributed.match_pool_sharded(_fake_match, *args, penalty=True, do_fine=True)
-        q.put((rank, full.tobytes()))
+        rays = distributed.raytrace_sharded(_fake_trace, None, np.arange(0, 360, 45.0), _starts())
+        q.put((rank, full.tobytes() + rays.tobytes()))
     finally:
         dist.destroy_process_group()
 
@@ -66,5 +82,5 @@ def test_two_rank_gather_equals_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    ref = _fake_match(*_problem(), True, True)
-    assert got[0] == ref.tobytes() and got[1] == ref.tobytes()
+    ref = _fake_match(*_problem(), True, True).tobytes() + _fake_trace(None, np.arange(0, 360, 45.0), _starts()).tobytes()
+    assert got[0] == ref and got[1] == ref

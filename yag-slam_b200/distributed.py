@@ -70,3 +70,34 @@ def match_pool_sharded(match_fn, pool_xy, scan_start, scan_count, query_scan, qu
     else:
         local = np.zeros(0, dtype=_capi.RESULT_DTYPE)
     return all_gather_results(local, n, group=group, device=device)
+
+
+def raytrace_sharded(trace_fn, img, angles_deg, starts_xy, group=None, device=None):
+    """Ray-walk sweeps from many start cells, sharded by start cell with the map replicated on every
+    rank: each rank runs `trace_fn(img, angles, starts[lo:hi])`
+    (raytracing.raytrace_many or any callable of that shape -> (n, n_angles, 5) float32), then one
+    all-gather returns the (n_starts, n_angles, 5) array to every rank."""
+    import torch
+    import torch.distributed as dist
+
+    starts = np.ascontiguousarray(starts_xy, dtype=np.float64).reshape(-1, 2)
+    na, n = len(angles_deg), len(starts)
+    if not (dist.is_available() and dist.is_initialized()):
+        return trace_fn(img, angles_deg, starts)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(n, rank, world)
+    per = -(-n // world) if n else 0
+    buf = np.zeros((max(per, 1), na, 5), dtype=np.float32)
+    if hi > lo:
+        buf[:hi - lo] = trace_fn(img, angles_deg, starts[lo:hi])
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1, na, 5), t, group=group)
+    out = out.cpu().numpy()
+    full = np.zeros((n, na, 5), dtype=np.float32)
+    for r in range(world):
+        l, h = shard_range(n, r, world)
+        full[l:h] = out[r, :h - l]
+    return full
