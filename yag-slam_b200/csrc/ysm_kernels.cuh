@@ -505,6 +505,9 @@ fv_scan_body(const GridC& g, const MatchDev* matches, const int* base_idx, const
     for (int i = tid; i < n; i += blockDim.x) {
       const int j = ja[i];
       if (j < n) {
+        // (racecheck reports this byte as a read/write hazard: another thread may set s_mark[i] in this
+        // same round. The race is benign -- marks only ever go 0 -> 1 and an early-seen mark is a true one
+        // (i reachable => ja[i] reachable), so the set reached after the last round is the same.)
         if (s_mark[i]) s_mark[j] = 1;
         jb[i] = ja[j];
       } else {
