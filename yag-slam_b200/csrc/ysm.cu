@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <new>
+#include <exception>
 #include <thread>
 #include <string>
 #include <unordered_map>
@@ -1702,8 +1704,20 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
 }
 
 // --------------------------------------------------------------------------------------------
+static int match_batch_lanes(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream);
+
 extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
   if (!h || !b || !out) return YSM_EINVAL;
+  try {  // no exception crosses the C ABI
+    return match_batch_lanes(h, b, out, stream);
+  } catch (const std::bad_alloc&) {
+    return fail(h, YSM_ENOMEM, "host allocation failed");
+  } catch (const std::exception& e) {
+    return fail(h, YSM_ECUDA, std::string("internal error: ") + e.what());
+  }
+}
+
+static int match_batch_lanes(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nl = 1 + (int)h->lanes.size();
   // (kernel timing / grid introspection are per-stream: those debug modes stay on the main lane)
@@ -1840,9 +1854,21 @@ extern "C" int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* ou
     }
     up_err = e;
   };
-  if (!plan.empty()) threads.emplace_back(uploader);
-  for (int l = 1; l < nl; l++) threads.emplace_back(run, l);
+  // (no exception may cross the C ABI: if a thread cannot be started, its work runs on this thread)
+  auto spawn = [&](auto&& fn) -> bool {
+    try {
+      threads.emplace_back(fn);
+      return true;
+    } catch (const std::exception&) {
+      return false;
+    }
+  };
+  if (!plan.empty() && !spawn(uploader)) uploader();  // (inline: the whole pool is sent before any lane starts)
+  std::vector<int> inline_lanes;
+  for (int l = 1; l < nl; l++)
+    if (!spawn([&run, l] { run(l); })) inline_lanes.push_back(l);
   run(0);
+  for (int l : inline_lanes) run(l);
   for (std::thread& t : threads) t.join();
   if (up_err != cudaSuccess) return fail(h, YSM_ECUDA, std::string("pool upload: ") + cudaGetErrorString(up_err));
   for (ysm_handle* x : hs) x->slice_wait.clear();

@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -244,7 +245,18 @@ extern "C" int ysm_chains_copy(const ysm_chains* c, int32_t* query_chain_ptr, in
   return YSM_OK;
 }
 
+static int chains_find_impl(const ysm_chain_query* in, int device, void* stream, ysm_chains** out);
+
 extern "C" int ysm_chains_find(const ysm_chain_query* in, int device, void* stream, ysm_chains** out) {
+  try {  // no exception crosses the C ABI
+    return chains_find_impl(in, device, stream, out);
+  } catch (const std::exception& e) {
+    if (out) *out = nullptr;
+    return chain_fail(YSM_ENOMEM, std::string("ysm_chains_find: ") + e.what());
+  }
+}
+
+static int chains_find_impl(const ysm_chain_query* in, int device, void* stream, ysm_chains** out) {
   if (!in || !out) return chain_fail(YSM_EINVAL, "ysm_chains_find: null argument");
   *out = nullptr;
   const int n = in->n_vertices, nq = in->n_queries;
