@@ -139,12 +139,14 @@ class Wrapper(object):
             arr = dict(counts=np.zeros(nb + 1, np.int32), starts=np.zeros(nb + 1, np.int32),
                        qidx=np.zeros(1, np.int32), pose=np.zeros((1, 3), np.float64),
                        bptr=np.array([0, nb], np.int32), bidx=np.arange(1, nb + 1, dtype=np.int32),
-                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE))
+                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), pool=np.zeros((4096, 2), np.float64))
+            arr["resf"] = arr["res"].view(np.float64).reshape(-1)  # the 128-B record as 16 doubles
             b.n_matches, b.n_scans = 1, nb + 1
             b.scan_start, b.scan_count = arr["starts"].ctypes.data, arr["counts"].ctypes.data
             b.query_scan, b.query_pose = arr["qidx"].ctypes.data, arr["pose"].ctypes.data
             b.base_ptr, b.base_idx = arr["bptr"].ctypes.data, (arr["bidx"].ctypes.data if nb else None)
             b.pool_on_device = 0
+            b.pool_xy = arr["pool"].ctypes.data
             c = self._one[nb] = (b, arr, C.byref(b), arr["res"].ctypes.data)
         b, arr, bref, resp = c
         pts = [query.point_readings()]
@@ -155,17 +157,21 @@ class Wrapper(object):
             starts[i] = tot
             counts[i] = len(p)
             tot += len(p)
-        pool = np.concatenate(pts) if tot else np.zeros((1, 2))
+        pool = arr["pool"]  # persistent staging buffer: its address is written to the descriptor once
+        if tot > len(pool):
+            pool = arr["pool"] = np.zeros((2 * tot, 2), np.float64)
+            b.pool_xy = pool.ctypes.data
+        if tot:
+            np.concatenate(pts, out=pool[:tot])
         arr["pose"][0] = query.sensor_pose()
-        b.pool_xy, b.n_points = pool.ctypes.data, tot
-        b.do_penalize, b.do_refine = int(bool(penalty)), int(bool(do_fine))
+        b.n_points = tot
+        b.do_penalize, b.do_refine = (1 if penalty else 0), (1 if do_fine else 0)
         m = self._m
         rc = m._lib.ysm_match_batch(m._h, bref, resp, None)
         if rc != _capi.YSM_OK:
             raise _ERRORS.get(rc, RuntimeError)(_capi.last_error(m._h))
-        r = arr["res"][0]
-        return MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
-                           Pose2(float(r["x"]), float(r["y"]), float(r["heading"])))
+        f = arr["resf"]
+        return MatchResult(float(f[0]), f[4:13].reshape(3, 3).copy(), Pose2(f[1], f[2], f[3]))
 
     def match_scan_batch(self, queries, base_sets, penalty=True, do_fine=False):
         """Independent (query, base set) matches in one launch sequence. Scans shared between
