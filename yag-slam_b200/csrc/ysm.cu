@@ -1089,11 +1089,13 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
             const double start_angle = heading - fo;
             for (int f = 0; f < nAf; f++) {
               const double angle = start_angle + (double)(uint32_t)f * fr;
-              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f)] = cos(angle);
-              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f) + 1] = sin(angle);
+              const double ca = cos(angle), sa = sin(angle);
+              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f)] = ca;
+              pl.trig[2 * ((size_t)t_off + (size_t)a * nAf + f) + 1] = sa;
               const double hn = h_normalize_angle(angle);
-              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f)] = cos(hn);
-              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f) + 1] = sin(hn);
+              const bool same = dbits(hn) == dbits(angle);  // (the usual case: nothing to re-evaluate)
+              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f)] = same ? ca : cos(hn);
+              pl.trig[2 * ((size_t)ht_off + (size_t)a * nAf + f) + 1] = same ? sa : sin(hn);
             }
           }
           const int Ppad = align_up(s.P, 4);
