@@ -162,3 +162,71 @@ def test_matcher_golden_pins_the_oracle():
     o = KartoOracle()
     r, p, c = o.match(g["testpy_query"], g["testpy_pose"], [g["testpy_base"]], True, True)
     assert (np.concatenate([[r], p, c.ravel()]) == g["testpy_ref"]).all()
+
+
+def test_wrapper_single_query_glue_packs_the_descriptor_and_reads_the_record():
+    """Wrapper.match_scan's single-query fast path with the library call stubbed out (no GPU): the
+    cached descriptor points at the persistent staging pool, which holds query + base point readings
+    in order, and the 128-B record is turned into the reference's result types."""
+    import ctypes as C
+    from yag_slam_b200 import _capi
+    seen = {}
+
+    class FakeLib(object):
+        def ysm_match_batch(self, h, bref, resp, stream):
+            b = bref._obj
+            n = b.n_points
+            seen["pool"] = np.ctypeslib.as_array(C.cast(b.pool_xy, C.POINTER(C.c_double)), shape=(max(n, 1), 2))[:n].copy()
+            seen["starts"] = np.ctypeslib.as_array(C.cast(b.scan_start, C.POINTER(C.c_int32)), shape=(b.n_scans,)).copy()
+            seen["counts"] = np.ctypeslib.as_array(C.cast(b.scan_count, C.POINTER(C.c_int32)), shape=(b.n_scans,)).copy()
+            seen["pose"] = np.ctypeslib.as_array(C.cast(b.query_pose, C.POINTER(C.c_double)), shape=(3,)).copy()
+            seen["flags"] = (b.n_matches, b.do_penalize, b.do_refine, b.pool_on_device)
+            rec = np.ctypeslib.as_array(C.cast(resp, C.POINTER(C.c_double)), shape=(16,))
+            rec[:13] = [0.75, 1.5, -2.5, 0.25] + list(range(9))
+            return _capi.YSM_OK
+
+    class FakeMatcher(object):
+        _lib, _h = FakeLib(), None
+
+    w = karto_compat.Wrapper.__new__(karto_compat.Wrapper)
+    w._one, w._m = {}, FakeMatcher()
+    world, rng = synth.make_world(), np.random.default_rng(3)
+    lp = synth.laser_params(90)
+    cfg = karto_compat.LaserScanConfig(lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], "")
+    path = synth.loop_path(4)
+    scans = [karto_compat.LocalizedRangeScan(cfg, synth.cast_scan(world, p, 90, rng), karto_compat.Pose2(*p),
+                                             karto_compat.Pose2(*p), i, 0.0) for i, p in enumerate(path)]
+    for nb, pen, fine in ((3, True, False), (1, False, True), (3, False, False), (0, True, True)):
+        q, base = scans[3], scans[:nb]
+        r = w.match_scan(q, base, pen, fine)
+        pts = [q.point_readings()] + [s.point_readings() for s in base]
+        assert (seen["pool"] == np.concatenate(pts)).all()
+        assert list(seen["counts"]) == [len(p) for p in pts]
+        assert list(seen["starts"]) == list(np.cumsum([0] + [len(p) for p in pts[:-1]]))
+        assert tuple(seen["pose"]) == q.sensor_pose() and seen["flags"] == (1, int(pen), int(fine), 0)
+        assert type(r.response) is float and r.response == 0.75
+        assert (r.best_pose.x, r.best_pose.y, r.best_pose.yaw) == (1.5, -2.5, 0.25) and type(r.best_pose.x) is float
+        assert r.covariance.shape == (3, 3) and r.covariance[1][2] == 5.0
+    # a scan set larger than the staging pool grows it (and re-points the descriptor)
+    big = karto_compat.LocalizedRangeScan(cfg, np.full(5000, 3.0), karto_compat.Pose2(0, 0, 0), karto_compat.Pose2(0, 0, 0), 9, 0.0)
+    big.config = karto_compat.LaserScanConfig(-np.pi, np.pi, 2 * np.pi / 5000, 0.05, 30.0, 20.0, "")
+    w.match_scan(big, [scans[0]], True, True)
+    assert len(seen["pool"]) == 5000 + len(scans[0].point_readings())
+    assert (seen["pool"][:5000] == big.point_readings()).all()
+
+
+def test_relocalisation_batch_generator_is_consistent_with_the_oracle(world):
+    """synth.make_relocalisation_batch (BASELINE cfg 5 shape, scaled down): descriptors are well formed,
+    the generator is seeded, and the oracle relocalises the perturbed queries onto their true poses."""
+    from oracle import oracle
+    b = synth.make_relocalisation_batch(world, 24, 360, 4, seed=5, n_log=40)
+    b2 = synth.make_relocalisation_batch(world, 24, 360, 4, seed=5, n_log=40)
+    assert b["pool"].tobytes() == b2["pool"].tobytes() and (b["query_pose"] == b2["query_pose"]).all()
+    assert len(b["starts"]) == 40 + 24 and b["starts"][-1] + b["counts"][-1] == len(b["pool"])
+    assert (b["query_scan"] == 40 + np.arange(24)).all() and (np.diff(b["base_ptr"]) == 4).all()
+    assert (b["base_idx"].reshape(-1, 4)[:, -1] == b["log_scan"] - 1).all() and b["base_idx"].min() >= 0
+    assert np.abs(b["query_pose"] - b["truth"]).max(axis=0).tolist() <= [0.2, 0.2, 0.15]
+    r = np.asarray(oracle.match_batch(None, b["pool"], b["starts"], b["counts"], b["query_scan"], b["query_pose"],
+                                      b["base_ptr"], b["base_idx"], True, True, 0)).reshape(-1, 13)
+    err = np.hypot(r[:, 1] - b["truth"][:, 0], r[:, 2] - b["truth"][:, 1])
+    assert np.median(err) < 0.03 and (r[:, 0] > 0.5).all()
