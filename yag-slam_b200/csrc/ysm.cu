@@ -1317,7 +1317,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       tr.mark("pass plan (host libm)");
       const char* db = nullptr;
       // latency path, first iteration: everything in ONE cooperative kernel (k_match_small)
-      bool mega = !built && small && !timing && !h->static_grid && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
+      bool mega = iter == 0 && !built && small && !timing && !h->static_grid && !(h->debug & (YSM_DEBUG_NO_MEGA | YSM_DEBUG_KEEP_GRIDS)) &&
                   !pl.pa.empty() && pl.fine.empty() && nbase_max <= 64 && hscans.size() <= 512;
       int mega_tpc = 0, mega_psplit = 1, mega_chunks = 0, mega_stage = 0, mega_fvw = 0, mega_log2cap = 6;
       size_t mega_smem = 0;
@@ -1448,6 +1448,12 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         CK(cudaLaunchCooperativeKernel((const void*)k_match_small, dim3(ctas), dim3(512), kargs, mega_smem, st));
         h->launches++;
         h->work[12]++;
+        // The tile clear is queued behind the kernel right away: the host would only spin on the flags
+        // meanwhile, so the launch leaves the call's critical path. A match the kernel could not finish
+        // (tied coarse winners, response expansion) has its grid rebuilt by the general path in the next
+        // iteration (built = false; the clear after the loop then belongs to that rebuild).
+        clear_wave(h, d_matches, st);
+        built = false;
         tr.mark("latency kernel launch");
         // wait for the per-pass completion flags the kernel writes after its results
         volatile int* flags = (volatile int*)h->h_flags.p;
