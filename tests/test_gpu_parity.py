@@ -206,6 +206,33 @@ def test_latency_path_device_chained_fine_pass(world):
     m.close()
 
 
+def test_heading_wraparound_on_every_path(world):
+    """Queries heading along -x (heading = -pi on the top edge of the loop, guesses on both sides of
+    the +-pi cut): the coarse / fine search angles leave [-pi, pi], so NormalizeAngle changes them
+    (separate cos/sin of the normalised headings for the tie average, atan2 of the averaged heading
+    lands on either side of the cut). Latency kernel, general path and throughput path vs the oracle."""
+    import scenarios
+    from yag_slam_b200 import _capi
+    for n, slots in ((1, 4), (6, 8), (200, 0)):
+        b = scenarios.make_batch(world, n, 360, 3, 71 + n, perturb=(0.07, 0.05), path_start=38.0,
+                                 path_step=0.25 if n <= 6 else 0.07)  # (every pose stays on the top edge)
+        assert (np.abs(np.abs(b["query_pose"][:, 2]) - np.pi) < 0.06).all()
+        if n > 1:
+            assert (b["query_pose"][:, 2] < -np.pi).any() and (b["query_pose"][:, 2] > -np.pi).any()
+        ref = scenarios.oracle_results(None, b, True, True)
+        m = _matcher(None, max_slots=slots)
+        a = _run(m, b, True, True).copy()
+        lat = m.last_work()["latency_kernel_launches"]
+        assert lat == (1 if n <= 6 else 0)
+        _assert_parity(a, ref, "wrap n=%d" % n)
+        if n <= 6:
+            m.set_debug(_capi.DEBUG_NO_MEGA | _capi.DEBUG_NO_SPECULATE)
+            c = _run(m, b, True, True).copy()
+            assert a.tobytes() == c.tobytes()
+        m.close()
+        assert (np.abs(a["heading"]) > 3.0).all()  # matched headings stay next to the cut, on either side
+
+
 def test_lanes_split_large_batches(world):
     """Large batches are split over internal lanes (own slots / stream / host thread); results are
     those of the single-lane path and of the oracle, with a host pool and with a device pool."""

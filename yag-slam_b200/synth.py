@@ -137,11 +137,11 @@ def scan_points(world, pose, n_beams, rng, sense_pose=None, range_threshold=20.0
 
 
 def make_match_batch(world, n_matches, n_beams, n_base, seed, perturb=(0.2, 0.15), degenerate_frac=0.0,
-               range_threshold=20.0, shared_query=False, path_step=0.25):
+               range_threshold=20.0, shared_query=False, path_step=0.25, path_start=0.0):
     """n_matches independent (query, n_base running scans) problems along the loop path.
     Returns dict(pool, starts, counts, query_scan, query_pose, base_ptr, base_idx, points=list)."""
     rng = np.random.default_rng(seed)
-    path = loop_path(n_matches + n_base + 1, step=path_step)
+    path = loop_path(n_matches + n_base + 1, step=path_step, start_s=path_start)
     pts = []
     base_of = {}
 
