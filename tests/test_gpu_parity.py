@@ -233,6 +233,23 @@ def test_heading_wraparound_on_every_path(world):
         assert (np.abs(a["heading"]) > 3.0).all()  # matched headings stay next to the cut, on either side
 
 
+def test_long_base_chains(world):
+    """Base sets much longer than the running-scan buffer (loop-closure chains have no upper length,
+    graph_slam.py:274-304): 70 scans per match exceeds the latency kernel's 64-scan limit (general
+    path), 40 x 8 matches sits inside it, and 70 x 40 matches runs the throughput path with more cells
+    per match than the 16-bit per-tile candidate counters take (searched build)."""
+    import scenarios
+    for n, nb, slots, lat in ((2, 70, 4, 0), (8, 40, 8, 1), (40, 70, 0, 0)):
+        b = scenarios.make_batch(world, n, 360, nb, 300 + n, perturb=(0.07, 0.03), path_step=0.1)
+        ref = scenarios.oracle_results(None, b, True, True)
+        m = _matcher(None, max_slots=slots)
+        out = _run(m, b, True, True).copy()
+        assert m.last_work()["latency_kernel_launches"] == lat
+        _assert_parity(out, ref, "long chains n=%d nb=%d" % (n, nb))
+        assert _run(m, b, True, True).tobytes() == out.tobytes()  # slots were cleared
+        m.close()
+
+
 def test_lanes_split_large_batches(world):
     """Large batches are split over internal lanes (own slots / stream / host thread); results are
     those of the single-lane path and of the oracle, with a host pool and with a device pool."""
