@@ -385,7 +385,7 @@ def latency_probe(device, with_cpu=False):
     world = synth.make_world()
     w = kc.Wrapper(kc.ScanMatcherConfig(), device=device, max_slots=4)
     out = {}
-    for name, P, nb, reps in (("cfg1", 360, 1, 300), ("cfg2", 720, 10, 200)):
+    for name, P, nb, reps in (("cfg1", 360, 1, 1000), ("cfg2", 720, 10, 500)):
         lp = synth.laser_params(P)
         rng = np.random.default_rng(1)
         path = synth.loop_path(nb + 1)
