@@ -50,7 +50,8 @@ typedef struct ysm_params {
   int64_t max_grid_bytes;  /* HBM budget for those grids; 0 = 16 GiB */
   int32_t lanes;           /* 0/1: single; 2..4: large batches are split over that many internal matcher
                               instances (own slots, stream, host thread) so host work overlaps kernels */
-  int32_t _pad;
+  int32_t resident_idle_us; /* single-query latency path: the resident kernel leaves the device after this many
+                              microseconds without a request (0 = 2000; < 0 = never use the resident kernel) */
 } ysm_params;
 
 /* Derived sizes (ScanMatcher::Create / CorrelationGrid::CreateGrid). */
@@ -236,6 +237,11 @@ int64_t ysm_launch_count(const ysm_handle *h);
 int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, double *reduce_ms,
                        double *total_ms);
 
+/* Round trip of an empty request through the resident latency kernel (doorbell in mapped host memory ->
+ * kernel -> tagged result chunk): the floor under every single-query latency. Starts the kernel if
+ * needed; rtt_us receives n wall-clock round trips in microseconds. */
+int ysm_debug_ping(ysm_handle *h, int32_t n, double *rtt_us);
+
 /* work done by the last ysm_match_batch call (for roofline accounting in bench.py):
  * out[0] grid lookups of the coarse lattice sweeps (L), out[1] lattice sweep launches,
  * out[2] lookup-offset table entries computed (T), out[3] poses evaluated,
@@ -243,7 +249,8 @@ int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, 
  * out[6] host->device bytes, out[7] device->host bytes, out[8] sweep launches that used zero-row pruning,
  * out[9] lattice lookups actually issued after pruning (counted only with YSM_DEBUG_TIME_KERNELS),
  * out[10] fine passes that ran chained on the device behind their coarse pass (latency path),
- * out[11] lanes used by the call, out[12] launches of the single-kernel latency path;
+ * out[11] lanes used by the call, out[12] launches of the single-kernel latency path,
+ * out[13] requests served by the resident latency kernel;
  * fills out[0..n), n <= 16 */
 int ysm_last_work(const ysm_handle *h, int64_t *out, int32_t n);
 

@@ -21,7 +21,7 @@ DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS, DEBUG_NO_PRUNE, DEBUG_NO_SPECULATE, DEBUG_
 class YsmParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in PARAM_FIELDS] + [
         ("use_response_expansion", C.c_int32), ("max_slots", C.c_int32), ("max_grid_bytes", C.c_int64),
-        ("lanes", C.c_int32), ("_pad", C.c_int32)]
+        ("lanes", C.c_int32), ("resident_idle_us", C.c_int32)]
 
 
 class YsmDims(C.Structure):
@@ -67,6 +67,7 @@ EXPORTS = [
     "ysm_create", "ysm_create_map", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
     "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
     "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
+    "ysm_debug_ping",
     "ysm_occ_create", "ysm_occ_destroy", "ysm_occ_get_info", "ysm_occ_copy_image", "ysm_occ_copy_counts",
     "ysm_occ_device_image", "ysm_occ_last_error",
     "ysm_chains_find", "ysm_chains_get_counts", "ysm_chains_copy", "ysm_chains_destroy", "ysm_chains_last_error",
@@ -116,6 +117,8 @@ def lib():
     L.ysm_last_kernel_ms.argtypes = [vp] + [C.POINTER(f64)] * 4
     L.ysm_last_work.restype = C.c_int
     L.ysm_last_work.argtypes = [vp, C.POINTER(C.c_int64), i32]
+    L.ysm_debug_ping.restype = C.c_int
+    L.ysm_debug_ping.argtypes = [vp, i32, C.POINTER(f64)]
     L.ysm_occ_create.restype = C.c_int
     L.ysm_occ_create.argtypes = [C.POINTER(YsmOccScans), C.c_int, vp, C.POINTER(vp)]
     L.ysm_occ_destroy.restype = None

@@ -5,7 +5,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("YSM_LIB") or os.path.join(CSRC, "libysm_b200.so")  # YSM_LIB: A/B another build of the library
-SOURCES = ["ysm.cu", "ysm_kernels.cuh", "ysm_occ.cu", "ysm_chains.cu"]
+SOURCES = ["ysm.cu", "ysm_kernels.cuh", "ysm_resident.cuh", "ysm_internal.h", "ysm_occ.cu", "ysm_chains.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     # cell indices come from Round(double): no FMA contraction, IEEE div/sqrt (defaults)

@@ -21,6 +21,7 @@
 //
 // Compile with -fmad=false (build.py): dx*dx + dy*dy must round as the reference's
 // (dx)**2 + (dy)**2 does.
+#include "ysm_internal.h"
 #include "../../include/ysm.h"
 
 #include <cuda_runtime.h>
@@ -248,6 +249,7 @@ extern "C" int ysm_chains_copy(const ysm_chains* c, int32_t* query_chain_ptr, in
 static int chains_find_impl(const ysm_chain_query* in, int device, void* stream, ysm_chains** out);
 
 extern "C" int ysm_chains_find(const ysm_chain_query* in, int device, void* stream, ysm_chains** out) {
+  ysm_quiesce_device(device);  // (a resident latency kernel would make the allocations / syncs below wait)
   try {  // no exception crosses the C ABI
     return chains_find_impl(in, device, stream, out);
   } catch (const std::exception& e) {

@@ -20,6 +20,7 @@
 //   K6e k_occ_classify    UpdateCell: pass > 2 ? (hit/pass > 0.1 ? occupied : free) : unknown
 //
 // Compile with -fmad=false (see build.py): every double operation is separately rounded.
+#include "ysm_internal.h"
 #include "../../include/ysm.h"
 
 #include <cuda_runtime.h>
@@ -258,6 +259,7 @@ extern "C" const char* ysm_occ_last_error(void) { return t_err.c_str(); }
 extern "C" void ysm_occ_destroy(ysm_occ* o) {
   if (!o) return;
   cudaSetDevice(o->device);
+  ysm_quiesce_device(o->device);
   if (o->d_pass) cudaFree(o->d_pass);
   if (o->d_hit) cudaFree(o->d_hit);
   if (o->d_image) cudaFree(o->d_image);
@@ -274,6 +276,7 @@ extern "C" void ysm_occ_destroy(ysm_occ* o) {
   } while (0)
 
 extern "C" int ysm_occ_create(const ysm_occ_scans* in, int device, void* stream, ysm_occ** out) {
+  ysm_quiesce_device(device);  // (a resident latency kernel would make the allocations / syncs below wait)
   if (!in || !out) return occ_fail(YSM_EINVAL, "ysm_occ_create: null argument");
   *out = nullptr;
   if (in->n_scans <= 0 || !in->pose || !in->laser || !in->beam_ptr)

@@ -117,15 +117,33 @@ class Wrapper(object):
     """karto_scanmatcher.Wrapper(config) (reference scan_matching.py:38,41; test.py:25,38).
     The GPU handle is created on construction, like ScanMatcher::Create."""
 
+    SINGLE_SLOTS = 8  # correlation grids of the single-query matcher (one is used per match_scan)
+
     def __init__(self, config, device=0, max_slots=0, max_grid_bytes=0):
         self.config = config
         cfg = config._as_dict() if hasattr(config, "_as_dict") else dict(config)
-        self._m = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
+        self._args = (cfg, device, max_slots, max_grid_bytes)
+        # The reference's call pattern is one query at a time (graph_slam.py:220,236,326): that needs one
+        # resident grid, not the throughput path's HBM budget (16 GiB by default). The batch matcher is
+        # created by the first match_scan_batch that does not fit these few slots.
+        self._m = ScanMatcherB200(cfg, device=device, max_slots=min(max_slots, self.SINGLE_SLOTS) or self.SINGLE_SLOTS,
+                                  max_grid_bytes=max_grid_bytes, lanes=1)
+        self._mt = None
         self._one = {}  # single-query descriptors, keyed by base-set size
 
     @property
     def matcher(self):
         return self._m
+
+    def batch_matcher(self, n_matches):
+        """The matcher a batch of n_matches runs on: the single-query one while it fits its slots, else the
+        throughput matcher (created on first use with the constructor's slot / HBM budget)."""
+        if n_matches <= self._m.dims()["slots"]:
+            return self._m
+        if self._mt is None:
+            cfg, device, max_slots, max_grid_bytes = self._args
+            self._mt = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
+        return self._mt
 
     def match_scan(self, query, base_scans, penalty=True, do_fine=False):
         """Wrapper.match_scan(query, base_scans, penalty, do_fine) (reference scan_matching.py:41).
@@ -192,7 +210,8 @@ class Wrapper(object):
             base_ptr.append(len(base_idx))
         pool, starts, counts = pack_pool([s.point_readings() for s in scans])
         poses = np.array([q.sensor_pose() for q in queries], dtype=np.float64).reshape(-1, 3)
-        res = self._m.match_pool(pool, starts, counts, qidx, poses, base_ptr, base_idx, penalty, do_fine)
+        res = self.batch_matcher(len(qidx)).match_pool(pool, starts, counts, qidx, poses, base_ptr, base_idx, penalty,
+                                                       do_fine)
         return [MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
                             Pose2(float(r["x"]), float(r["y"]), float(r["heading"]))) for r in res]
 

@@ -29,7 +29,7 @@ def _is_cuda_tensor(x):
 
 
 class ScanMatcherB200(object):
-    def __init__(self, cfg=None, device=0, max_slots=0, max_grid_bytes=0, lanes=2):
+    def __init__(self, cfg=None, device=0, max_slots=0, max_grid_bytes=0, lanes=2, resident_idle_us=0):
         d = dict(DEFAULTS)
         if cfg:
             d.update({k: v for k, v in dict(cfg).items() if k in d})
@@ -41,6 +41,7 @@ class ScanMatcherB200(object):
         p.max_slots = int(max_slots)
         p.max_grid_bytes = int(max_grid_bytes)
         p.lanes = int(lanes)
+        p.resident_idle_us = int(resident_idle_us)
         self._lib = _capi.lib()
         self._h = C.c_void_p()
         rc = self._lib.ysm_create(C.byref(p), int(device), C.byref(self._h))
@@ -82,8 +83,16 @@ class ScanMatcherB200(object):
         self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
                          "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
-                         "speculative_fine_passes", "lanes", "latency_kernel_launches"),
+                         "speculative_fine_passes", "lanes", "latency_kernel_launches", "resident_requests"),
                         (int(x) for x in v)))
+
+    def ping(self, n=1):
+        """Round trips (microseconds) of n empty requests through the resident latency kernel."""
+        out = (C.c_double * int(n))()
+        rc = self._lib.ysm_debug_ping(self._h, int(n), out)
+        if rc != _capi.YSM_OK:
+            raise _ERRORS.get(rc, RuntimeError)(_capi.last_error(self._h))
+        return np.array(out[:], dtype=np.float64)
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
                    penalty=True, do_fine=False, stream=0, out=None):
@@ -127,6 +136,9 @@ class ScanMatcherB200(object):
         b.do_refine = int(bool(do_fine))
         if out is None:
             out = np.zeros(n, dtype=_capi.RESULT_DTYPE)
+        elif (not isinstance(out, np.ndarray) or out.dtype != _capi.RESULT_DTYPE or out.ndim != 1 or len(out) < n
+              or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous 1-D array of RESULT_DTYPE with room for every match")
         rc = self._lib.ysm_match_batch(self._h, C.byref(b), out.ctypes.data, C.c_void_p(int(stream)))
         del keep
         if rc != _capi.YSM_OK:

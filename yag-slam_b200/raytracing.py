@@ -36,10 +36,16 @@ def raytrace_many(img, angles_deg, starts_xy, device=0, stream=0):
         on_dev, h, w, ptr, keep = True, img.height, img.width, img.device_image, img
         device = img.device
     elif on_dev:
+        if str(img.dtype) != "torch.uint8" or img.dim() != 2 or not img.is_contiguous():
+            raise ValueError("device map must be a contiguous 2-D uint8 tensor")
+        if img.device.index is not None and int(img.device.index) != int(device):
+            raise ValueError("device map lives on cuda:%d, not on the requested device %d" % (img.device.index, device))
         h, w = int(img.shape[0]), int(img.shape[1])
         ptr, keep = int(img.data_ptr()), img
     else:
         keep = np.ascontiguousarray(img, dtype=np.uint8)
+        if keep.ndim != 2:
+            raise ValueError("map must be a 2-D uint8 image")
         h, w = keep.shape[:2]
         ptr = keep.ctypes.data
     rc = _capi.lib().ysm_raytrace(ptr, h, w, int(on_dev), angles.ctypes.data, len(angles), starts.ctypes.data,
