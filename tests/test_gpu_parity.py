@@ -173,7 +173,9 @@ def test_latency_path_device_chained_fine_pass(world):
         a = _run(m, b, True, True).copy()
         w = m.last_work()
         spec = w["speculative_fine_passes"]
-        assert w["latency_kernel_launches"] == 1, "the single-kernel latency path did not run"
+        # one query: the resident kernel; a handful: the single cooperative kernel
+        assert (w["resident_requests"] == 1) if n == 1 else (w["latency_kernel_launches"] == 1), \
+            "the latency path did not run"
         m.set_debug(_capi.DEBUG_NO_MEGA)
         a2 = _run(m, b, True, True).copy()
         w2 = m.last_work()
@@ -187,7 +189,15 @@ def test_latency_path_device_chained_fine_pass(world):
         m.close()
         _assert_parity(a, ref, "latency kernel")
         _assert_parity(c, ref, "general path")
-        assert a.tobytes() == a2.tobytes() == c.tobytes() == c2.tobytes()
+        assert a2.tobytes() == c.tobytes() == c2.tobytes()
+        if n > 1:
+            assert a.tobytes() == a2.tobytes()
+        else:
+            # the resident kernel reduces the A.9 covariance sums over a different tree: same pose / response
+            # bits, covariance equal to rounding
+            for k in ("response", "x", "y", "heading", "n_passes", "n_ties"):
+                assert (a[k] == a2[k]).all(), k
+            assert np.allclose(a["cov"], a2["cov"], rtol=1e-12, atol=0)
         _assert_parity(coarse_only, scenarios.oracle_results(cfg, b, True, False), "latency kernel, coarse only")
         if degen == 0.0:
             assert spec >= 1, "the device-chained fine pass never ran"
@@ -222,8 +232,9 @@ def test_heading_wraparound_on_every_path(world):
         ref = scenarios.oracle_results(None, b, True, True)
         m = _matcher(None, max_slots=slots)
         a = _run(m, b, True, True).copy()
-        lat = m.last_work()["latency_kernel_launches"]
-        assert lat == (1 if n <= 6 else 0)
+        w = m.last_work()
+        lat = w["latency_kernel_launches"]
+        assert (w["resident_requests"] == 1) if n == 1 else (lat == (1 if n <= 6 else 0))
         _assert_parity(a, ref, "wrap n=%d" % n)
         if n <= 6:
             m.set_debug(_capi.DEBUG_NO_MEGA | _capi.DEBUG_NO_SPECULATE)

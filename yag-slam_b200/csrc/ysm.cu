@@ -258,8 +258,10 @@ struct Resident {
   cudaStream_t st = nullptr; // non-blocking stream the kernel runs on
   unsigned char* mb = nullptr;    // mapped host memory: doorbell | exit line | spec | result chunks | request | points
   unsigned char* mb_dev = nullptr;
-  size_t o_db = 0, o_exit = 0, o_spec = 0, o_out = 0, o_req = 0, o_pts = 0, mb_bytes = 0;
-  unsigned char* d_small = nullptr;  // bars[128] | quit_round | abort | ncells | fail | passmax
+  size_t o_db = 0, o_exit = 0, o_prof = 0, o_spec = 0, o_out = 0, o_req = 0, o_pts = 0, mb_bytes = 0;
+  unsigned char* d_small = nullptr;  // barrier counters | quit_round | abort | passmax | winner word (2 KB)
+  unsigned* d_fsum = nullptr;        // fine lookup sums
+  double* d_spec = nullptr;          // device copy of the spec tables
   unsigned char* d_ctl = nullptr;
   uint32_t* d_cells = nullptr;
   double* d_qpts = nullptr;
@@ -856,10 +858,12 @@ static std::atomic<int> g_res_alive{0};
 
 static void res_ring(Resident& R, unsigned seq, unsigned w1, unsigned w2, unsigned w3) {
   // 16-byte doorbell {seq, w1, w2, w3}: the half that holds seq is stored last (x86 keeps the store order,
-  // the GPU reads the 16 bytes with one request)
-  uint64_t* db = reinterpret_cast<uint64_t*>(R.mb + R.o_db);
-  __atomic_store_n(&db[1], (uint64_t)w2 | ((uint64_t)w3 << 32), __ATOMIC_RELEASE);
-  __atomic_store_n(&db[0], (uint64_t)seq | ((uint64_t)w1 << 32), __ATOMIC_RELEASE);
+  // the GPU reads the 16 bytes with one request). One copy per polling CTA, each on its own line.
+  for (int k = YSM_RES_POLLERS; k >= 0; k--) {
+    uint64_t* db = reinterpret_cast<uint64_t*>(R.mb + R.o_db + (size_t)k * YSM_RES_DB_STRIDE);
+    __atomic_store_n(&db[1], (uint64_t)w2 | ((uint64_t)w3 << 32), __ATOMIC_RELEASE);
+    __atomic_store_n(&db[0], (uint64_t)seq | ((uint64_t)w1 << 32), __ATOMIC_RELEASE);
+  }
 }
 
 // (g_res_mu held) ends the handle's resident kernel and waits until it has left the device
@@ -895,6 +899,8 @@ static void res_free(ysm_handle* h) {
   if (R->st) cudaStreamDestroy(R->st);
   if (R->mb) cudaFreeHost(R->mb);
   if (R->d_small) cudaFree(R->d_small);
+  if (R->d_fsum) cudaFree(R->d_fsum);
+  if (R->d_spec) cudaFree(R->d_spec);
   if (R->d_ctl) cudaFree(R->d_ctl);
   if (R->d_cells) cudaFree(R->d_cells);
   if (R->d_qpts) cudaFree(R->d_qpts);
@@ -910,8 +916,9 @@ static int res_alloc(ysm_handle* h) {
   Resident* R = new Resident();
   h->res = R;
   size_t o = 0;
-  R->o_db = o; o += 64;
-  R->o_exit = o; o += 64;
+  R->o_db = o; o += (size_t)(YSM_RES_POLLERS + 1) * YSM_RES_DB_STRIDE;
+  R->o_exit = o; o += 128;
+  R->o_prof = o; o += 8 * (size_t)YSM_RES_PROF * 256;
   R->o_spec = o; o += 64 + sizeof(double) * (size_t)YSM_RES_SPEC_DOUBLES;
   o = (o + 127) & ~(size_t)127;
   R->o_out = o; o += 16 * (size_t)YSM_RES_CHUNKS;
@@ -924,7 +931,9 @@ static int res_alloc(ysm_handle* h) {
   void* d = nullptr;
   CK(cudaHostGetDevicePointer(&d, R->mb, 0));
   R->mb_dev = (unsigned char*)d;
-  CK(cudaMalloc((void**)&R->d_small, 1024));
+  CK(cudaMalloc((void**)&R->d_small, 2048));
+  CK(cudaMalloc((void**)&R->d_fsum, 4 * 4096));
+  CK(cudaMalloc((void**)&R->d_spec, 8 * (size_t)YSM_RES_SPEC_DOUBLES));
   CK(cudaMalloc((void**)&R->d_ctl, sizeof(ResReq)));
   CK(cudaMalloc((void**)&R->d_cells, 4 * (size_t)YSM_RES_CELLS_CAP));
   CK(cudaMalloc((void**)&R->d_qpts, 16 * (size_t)YSM_RES_PMAX));
@@ -942,7 +951,8 @@ static size_t res_scratch_bytes(int pstride) {
 static int res_launch(ysm_handle* h, size_t smem, unsigned last_seq) {
   Resident& R = *h->res;
   const GridC& g = h->g;
-  CK(cudaMemsetAsync(R.d_small, 0, 1024, R.st));  // barrier counters and per-request accumulators start at zero
+  CK(cudaMemsetAsync(R.d_small, 0, 2048, R.st));  // barrier counters and per-request accumulators start at zero
+  CK(cudaMemsetAsync(R.d_fsum, 0, 4 * 4096, R.st));
   if (R.cellmax_cap) CK(cudaMemsetAsync(R.d_cellmax, 0, R.cellmax_cap * 8, R.st));
   memset(R.mb + R.o_exit, 0, 16);
   ResArgs A;
@@ -953,13 +963,15 @@ static int res_launch(ysm_handle* h, size_t smem, unsigned last_seq) {
   A.spec = R.mb_dev + R.o_spec;
   A.out = (uint4*)(R.mb_dev + R.o_out);
   A.exit_line = (unsigned*)(R.mb_dev + R.o_exit);
+  A.prof = R.G <= 256 ? (unsigned long long*)(R.mb_dev + R.o_prof) : nullptr;
   A.ctl = R.d_ctl;
-  A.bars = (unsigned*)R.d_small;
-  A.quit_round = (unsigned*)(R.d_small + 512);
-  A.abort_flag = (int*)(R.d_small + 576);
-  A.ncells = (int*)(R.d_small + 640);
-  A.fail = (int*)(R.d_small + 704);
-  A.passmax = (double*)(R.d_small + 768);
+  A.bars = (unsigned long long*)R.d_small;  // 5 counters, 128 bytes apart
+  A.quit_round = (unsigned*)(R.d_small + 1024);
+  A.abort_flag = (int*)(R.d_small + 1088);
+  A.passmax = (double*)(R.d_small + 1152);
+  A.win = (unsigned long long*)(R.d_small + 1216);
+  A.fsum = R.d_fsum;
+  A.spec_dev = R.d_spec;
   A.cells = R.d_cells;
   A.cells_cap = YSM_RES_CELLS_CAP;
   A.qpts = R.d_qpts;
@@ -1051,7 +1063,7 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   }
   if ((int64_t)b->scan_start[q] + P > b->n_points || b->scan_start[q] < 0) return 1;
   const int pstride = (pmax + 7) & ~7;
-  if (pmax > YSM_RES_PMAX || (long long)(nbase + 1) * pstride > YSM_RES_PTS_CAP || cells > YSM_RES_CELLS_CAP) return 1;
+  if (pmax > YSM_RES_PMAX || (long long)(nbase + 1) * pstride > YSM_RES_PTS_CAP || (long long)nbase * pstride > YSM_RES_CELLS_CAP) return 1;
 
   // ---- the two passes: coarse now, fine resolved on the device at the coarse winner ----
   const double pose[3] = {b->query_pose[0], b->query_pose[1], b->query_pose[2]};
@@ -1061,7 +1073,7 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   const int nA = n_steps(a_off, a_res), nAf = n_steps(fo, fr);
   const int nX = n_steps(csx, crx), nY = nX;
   const int fnX = n_steps(crx * 0.5, h->res_eff), fnY = fnX;
-  if (nA < 1 || nA > YSM_RES_MAXNA || nAf < 1 || nA * nAf > 4096 || nA > 255 || nAf > 255) return 1;
+  if (nA < 1 || nA > YSM_RES_MAXNA || nAf < 1 || nA * nAf > 4096 || nA > 255 || nAf > 64 || fnX * fnY > 64) return 1;
   if ((long long)nX * nY * nA > (1 << 21) || fnX * fnY * nAf > 4096) return 1;
   const int Ppad = align_up(P, 4);
   const size_t tab_bytes = stamp_table_bytes(g.K, g.Wt);
@@ -1222,6 +1234,30 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
                                   "spec tables in smem", "sweep done (wait)", "coarse reduce", "fine pass"};
     for (int k = 0; k < 8; k++)
       fprintf(stderr, "[ysm-resident] %-26s %8.2f us\n", names[k], (double)(ts[k + 1] - ts[k]) * 1e-3);
+    if (has_fine)
+      fprintf(stderr, "[ysm-resident]   fine: winner published +%.2f, workers' sums arrived +%.2f, finish %.2f us\n",
+              (double)(ts[9] - ts[7]) * 1e-3, (double)(ts[10] - ts[9]) * 1e-3, (double)(ts[8] - ts[10]) * 1e-3);
+    // per-CTA phases (written after barrier 3: give the stores a moment)
+    std::this_thread::sleep_for(std::chrono::microseconds(200));
+    const uint64_t* pf = reinterpret_cast<const uint64_t*>(R.mb + R.o_prof);
+    static const char* pn[] = {"ctl in smem -> offsets", "collect", "stamp", "barrier 2 (wait)", "sweep", "tail + barrier 3 + clear"};
+    for (int k = 0; k < 6; k++) {
+      std::vector<double> v;
+      for (int c = 1; c < R.G; c++) v.push_back((double)(int64_t)(pf[(size_t)c * YSM_RES_PROF + k + 1] - pf[(size_t)c * YSM_RES_PROF + k]) * 1e-3);
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, "[ysm-resident]   workers %-26s min %6.2f  med %6.2f  max %6.2f us\n", pn[k], v.front(), v[v.size() / 2], v.back());
+    }
+    {
+      const uint64_t* f1 = pf + (size_t)1 * YSM_RES_PROF;  // CTA 1: base scan 0
+      fprintf(stderr, "[ysm-resident]   CTA 1 phase A: pull %.2f, next[] %.2f, chain %.2f, cells %.2f us; detect skew vs CTA 0 %+.2f us\n",
+              (double)(int64_t)(f1[9] - f1[8]) * 1e-3, (double)(int64_t)(f1[10] - f1[9]) * 1e-3, (double)(int64_t)(f1[11] - f1[10]) * 1e-3,
+              (double)(int64_t)(f1[12] - f1[11]) * 1e-3, (double)(int64_t)(f1[8] - pf[8]) * 1e-3);
+    }
+    int tmax = 0, tsum = 0;
+    for (int c = 0; c < R.G; c++) { const int t = (int)pf[(size_t)c * YSM_RES_PROF + 7]; tmax = std::max(tmax, t); tsum += t; }
+    uint64_t b1min = ~0ull, b1max = 0;
+    for (int c = 0; c < R.G; c++) { b1min = std::min(b1min, pf[(size_t)c * YSM_RES_PROF]); b1max = std::max(b1max, pf[(size_t)c * YSM_RES_PROF]); }
+    fprintf(stderr, "[ysm-resident]   tiles stamped %d (max %d per CTA); barrier-1 exit skew %.2f us\n", tsum, tmax, (double)(b1max - b1min) * 1e-3);
   }
   if (status != RES_ST_OK) return 1;
   PassOut po, fo_out;

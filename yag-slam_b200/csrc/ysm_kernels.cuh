@@ -1036,22 +1036,33 @@ struct PassAngle {
 
 // GetResponse normalisation + the odometry penalty of CorrelateScan for the
 // pose (ix, iy, a) whose integer lookup sum is `sum`.
+// the two halves of the odometry penalty (dp: distance, ap: angle); the same expressions, in the same order,
+// as CorrelateScan (A.7)
+__device__ __forceinline__ double penalty_distance(const PassDev& ps, const PenaltyC& pen, int ix, int iy) {
+  const double x = -ps.offx + (double)ix * ps.resx;
+  const double y = -ps.offy + (double)iy * ps.resy;
+  const double sqd = x * x + y * y;
+  const double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
+  return dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
+}
+__device__ __forceinline__ double penalty_angle(const PassDev& ps, const PenaltyC& pen, int a) {
+  const double angle = (ps.ch - ps.angle_offset) + (double)a * ps.angle_res;
+  const double da = angle - ps.ch;
+  const double sqa = da * da;
+  const double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
+  return ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
+}
+// response of a pose from its integer lookup sum and the penalty product dp * ap computed beforehand
+__device__ __forceinline__ double response_from(const PassDev& ps, unsigned sum, double dpap) {
+  double r = (double)sum / (double)((unsigned)ps.P * 100u);
+  if (ps.penalize && !kt_double_equal(r, 0.0)) r *= dpap;
+  return r;
+}
+
 __device__ __forceinline__ double response_of(const PassDev& ps, const PenaltyC& pen, unsigned sum, int ix,
                                               int iy, int a) {
   double r = (double)sum / (double)((unsigned)ps.P * 100u);
-  if (ps.penalize && !kt_double_equal(r, 0.0)) {
-    const double x = -ps.offx + (double)ix * ps.resx;
-    const double y = -ps.offy + (double)iy * ps.resy;
-    const double sqd = x * x + y * y;
-    double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
-    dp = dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
-    const double angle = (ps.ch - ps.angle_offset) + (double)a * ps.angle_res;
-    const double da = angle - ps.ch;
-    const double sqa = da * da;
-    double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
-    ap = ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
-    r *= (dp * ap);
-  }
+  if (ps.penalize && !kt_double_equal(r, 0.0)) r *= (penalty_distance(ps, pen, ix, iy) * penalty_angle(ps, pen, a));
   return r;
 }
 

@@ -41,6 +41,8 @@ namespace ysm {
 #define YSM_RES_MAXNA 128
 #define YSM_RES_CHUNKS 256   // 16-byte result chunks
 #define YSM_RES_TS 24        // trace timestamps
+#define YSM_RES_DB_STRIDE 256
+#define YSM_RES_PROF 16      // per-CTA trace timestamps
 
 enum { RES_CMD_NONE = 0, RES_CMD_MATCH = 1, RES_CMD_QUIT = 2, RES_CMD_PING = 3 };
 enum { RES_ST_OK = 0, RES_ST_FALLBACK = 1, RES_ST_PONG = 2 };
@@ -70,25 +72,29 @@ struct ResSpecHdr {
 
 struct ResArgs {
   // mapped host memory
-  const uint4* db;              // doorbell: {seq, cmd | nbase << 8 | nA << 16 | nAf << 24, Pq | pstride << 16, ctl bytes}
+  const uint4* db;              // doorbells, one per polling CTA, YSM_RES_DB_STRIDE bytes apart (concurrent reads of ONE
+                                // host address are served one PCIe round trip after the other):
+                                // {seq, cmd | nbase << 8 | nA << 16 | nAf << 24, Pq | pstride << 16, ctl bytes}
   const unsigned char* req;     // ResReq
   const double* pts;            // scan s at pts + 2 * s * pstride ([nbase] = query)
   const unsigned char* spec;    // ResSpecHdr | heading[nA] | ftrig4[nA][nAf][4]
   uint4* out;                   // result chunks {payload lo, payload hi, seq, index}
+  unsigned long long* prof;     // [gridDim][YSM_RES_PROF] per-CTA phase timestamps of traced requests
   unsigned* exit_line;          // {last seq served, exit code}
   // HBM
   unsigned char* ctl;           // device copy of ResReq
-  unsigned* bars;               // counters, 32 words apart: [0] barrier 1, [32] barrier 2, [64] sweep done, [96] barrier 3
+  unsigned long long* bars;     // counters, YSM_RES_BAR_STRIDE words apart: barrier 1, barrier 2, sweep done, fine done, barrier 3
+  unsigned long long* win;      // CTA 0 -> workers: the coarse winner {seq, angle | ix << 8 | iy << 20} (or "no fine pass")
+  unsigned* fsum;               // fine lookup sums [iy][ix][a], accumulated by the workers
+  double* spec_dev;             // device copy of the spec tables (CTA 0 -> workers)
   unsigned* quit_round;         // CTA 0 -> pollers: round number that ends the kernel
   int* abort_flag;
-  uint32_t* cells;              // occupied cells of the match (any order)
-  int* ncells;
+  uint32_t* cells;              // [nbase][pstride] cell of every base point reading (YSM_INVALID_CELL: dropped)
   int cells_cap;
   double* qpts;                 // query point readings
   double* resp;                 // [iy][ix][a] coarse responses
   unsigned long long* cellmax;  // [iy][ix]
   double* passmax;
-  int* fail;
   const uint16_t* stamp_tab;
   uint8_t* grid;                // slot 0
   unsigned last_seq;
@@ -117,18 +123,39 @@ __device__ __forceinline__ unsigned res_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void res_red_release(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long res_ld_acquire64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void res_red_release64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void res_st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void res_st_release64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-// thread 0 of a CTA: wait until *ctr has reached `target` (wrap-safe). false: aborted / timed out.
-__device__ __forceinline__ bool res_wait(const unsigned* ctr, unsigned target, int* abort_flag, unsigned long long stall_ns) {
+// A barrier is a monotone 64-bit counter in HBM: the low word counts arrivals, the high word the arrivals
+// that report a failure (so the verdict of a phase travels with the barrier: no extra round trip).
+#define YSM_RES_BAR_STRIDE 16  // u64 words between counters (128 bytes)
+__device__ __forceinline__ void res_arrive(unsigned long long* ctr, bool fail) {
+  res_red_release64(ctr, 1ull + (fail ? (1ull << 32) : 0ull));
+}
+// thread 0 of a CTA: wait until the arrivals have reached `target` (wrap-safe); *hi receives the failure
+// count. false: aborted / stalled.
+__device__ __forceinline__ bool res_wait(const unsigned long long* ctr, unsigned target, unsigned* hi, int* abort_flag,
+                                         unsigned long long stall_ns) {
   unsigned long long t0 = 0ull;
   unsigned spins = 0u;
-  while ((int)(res_ld_acquire(ctr) - target) < 0) {
+  for (;;) {
+    const unsigned long long v = res_ld_acquire64(ctr);
+    if ((int)((unsigned)v - target) >= 0) {
+      *hi = (unsigned)(v >> 32);
+      return true;
+    }
     if ((++spins & 0x3FFu) == 0u) {
       const unsigned long long now = res_timer();
       if (t0 == 0ull) t0 = now;
@@ -136,18 +163,21 @@ __device__ __forceinline__ bool res_wait(const unsigned* ctr, unsigned target, i
       if (res_ld_acquire(reinterpret_cast<const unsigned*>(abort_flag)) != 0u) return false;
     }
   }
-  return true;
 }
 
-// all threads of the CTA; s_ok is a shared int. Returns false when the kernel must stop.
-__device__ __forceinline__ bool res_barrier(unsigned* ctr, unsigned target, int* abort_flag, int* s_ok, unsigned long long stall_ns) {
+// all threads of the CTA; s_io is a shared int[2]: [0] = ok, [1] = failure count seen. `fail` is read from
+// thread 0. Returns false when the kernel must stop.
+__device__ __forceinline__ bool res_barrier(unsigned long long* ctr, unsigned target, bool fail, int* abort_flag, int* s_io,
+                                            unsigned long long stall_ns) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    res_red_release(ctr, 1u);
-    *s_ok = res_wait(ctr, target, abort_flag, stall_ns) ? 1 : 0;
+    res_arrive(ctr, fail);
+    unsigned hi = 0u;
+    s_io[0] = res_wait(ctr, target, &hi, abort_flag, stall_ns) ? 1 : 0;
+    s_io[1] = (int)hi;
   }
   __syncthreads();
-  return *s_ok != 0;
+  return s_io[0] != 0;
 }
 
 __host__ __device__ __forceinline__ size_t res_fv_smem(int pstride) {
@@ -162,8 +192,8 @@ __device__ __forceinline__ unsigned res_tile_hash(int t) { return (unsigned)t * 
 // ---- phase A: FindValidPoints of one base scan, points pulled from mapped host memory ----
 __device__ __forceinline__ void
 res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int pstride, unsigned char* scratch,
-                int* s_misc) {
-  const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
+                int* s_misc, unsigned long long* pf) {
+  const int tid = threadIdx.x, T = blockDim.x;
   double* s_px = reinterpret_cast<double*>(scratch);
   double* s_py = s_px + pstride;
   unsigned short* s_next = reinterpret_cast<unsigned short*>(s_py + pstride);
@@ -187,6 +217,7 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
     s_mark[i] = i == 0;
   }
   __syncthreads();
+  if (threadIdx.x == 0) pf[9] = res_timer();
   const int n = min(s_misc[8], pstride);
   const double vpx = s_m[0], vpy = s_m[1], gox = s_m[2], goy = s_m[3];
   const double msd = 0.1 * 0.1;  // math::Square(0.1)
@@ -202,6 +233,7 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
     s_ja[i] = (unsigned short)j;
   }
   __syncthreads();
+  if (threadIdx.x == 0) pf[10] = res_timer();
   // the trigger chain 0 -> next[0] -> ... by pointer doubling (see fv_scan_body)
   unsigned short* ja = s_ja;
   unsigned short* jb = s_jb;
@@ -218,8 +250,11 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
     __syncthreads();
     unsigned short* t = ja; ja = jb; jb = t;
   }
-  for (int j0 = 0; j0 < n; j0 += T) {
-    const int j = j0 + tid;
+  if (threadIdx.x == 0) pf[11] = res_timer();
+  // one entry per point reading (YSM_INVALID_CELL: dropped); the smear is a pure max, so phase B may take the
+  // cells in any order and no compaction is needed
+  uint32_t* out = A.cells + (size_t)s * pstride;
+  for (int j = tid; j < pstride; j += T) {
     uint32_t cell = YSM_INVALID_CELL;
     if (j < n) {
       int f = j;
@@ -242,22 +277,13 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
         }
       }
     }
-    // the smear is a pure max: the cells may be listed in any order
-    const unsigned bal = __ballot_sync(0xffffffffu, cell != YSM_INVALID_CELL);
-    int base = 0;
-    if (lane == 0 && bal) base = atomicAdd(A.ncells, __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (cell != YSM_INVALID_CELL) {
-      const int pos = base + __popc(bal & ((1u << lane) - 1u));
-      if (pos < A.cells_cap) A.cells[pos] = cell;
-      else *A.fail = 1;
-    }
+    out[j] = cell;
   }
 }
 
 // ---- phase B: the tiles this CTA owns ------------------------------------------------------------------
 __device__ __forceinline__ void
-res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_tile, int* s_cnt, uint32_t* s_steps) {
+res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_tile, int* s_cnt, uint32_t* s_steps, int* s_fail) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int h = g.half_kernel;
@@ -286,11 +312,11 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_
             if (old == -1 || old == t) {
               const int k2 = atomicAdd(&s_cnt[sl], 1);
               if (k2 < YSM_RES_CAND) s_steps[sl * YSM_RES_CAND + k2] = stamp_step(c[k], h, g.K, g.Wt, tx * YSM_TILE, ty * YSM_TILE);
-              else *A.fail = 1;
+              else *s_fail = 1;
               placed = true;
             }
           }
-          if (!placed) *A.fail = 1;
+          if (!placed) *s_fail = 1;
         }
     }
   }
@@ -428,7 +454,34 @@ res_sweep_prep(const GridC& g, const ResReq& rq, const ResArgs& A, int a, int* s
   __syncthreads();
 }
 
-__device__ __forceinline__ void
+// one lattice row-task: the integer lookup sum of this lane's pose over points [0, np); 16 independent byte
+// loads in flight per lane (s_off holds offsets biased to be non-negative, gp includes the bias)
+__device__ __forceinline__ unsigned res_sweep_row(const uint8_t* gp, const unsigned* s_off, int np) {
+  unsigned sum0 = 0, sum1 = 0;
+  int p = 0;
+  for (; p + 16 <= np; p += 16) {
+    const uint4 o0 = *reinterpret_cast<const uint4*>(s_off + p);
+    const uint4 o1 = *reinterpret_cast<const uint4*>(s_off + p + 4);
+    const uint4 o2 = *reinterpret_cast<const uint4*>(s_off + p + 8);
+    const uint4 o3 = *reinterpret_cast<const uint4*>(s_off + p + 12);
+    const unsigned v0 = gp[o0.x], v1 = gp[o0.y], v2 = gp[o0.z], v3 = gp[o0.w];
+    const unsigned v4 = gp[o1.x], v5 = gp[o1.y], v6 = gp[o1.z], v7 = gp[o1.w];
+    const unsigned v8 = gp[o2.x], v9 = gp[o2.y], v10 = gp[o2.z], v11 = gp[o2.w];
+    const unsigned v12 = gp[o3.x], v13 = gp[o3.y], v14 = gp[o3.z], v15 = gp[o3.w];
+    sum0 += (v0 + v1 + v2 + v3) + (v4 + v5 + v6 + v7);
+    sum1 += (v8 + v9 + v10 + v11) + (v12 + v13 + v14 + v15);
+  }
+  for (; p + 4 <= np; p += 4) {
+    const uint4 o0 = *reinterpret_cast<const uint4*>(s_off + p);
+    sum0 += (unsigned)gp[o0.x] + gp[o0.y] + gp[o0.z] + gp[o0.w];
+  }
+  for (; p < np; p++) sum1 += (unsigned)gp[s_off[p]];
+  return sum0 + sum1;
+}
+
+// returns false (CTA-uniform) when a lookup could leave the grid: Karto's per-lookup bounds check is the
+// general path's business
+__device__ __forceinline__ bool
 res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResArgs& A, int a, int chunk, const int* s_i,
               const int* s_minmax, unsigned* s_part, double* s_wmax) {
   const PassDev& ps = rq.coarse;
@@ -444,13 +497,13 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
   const int minoff = s_minmax[0];
   const long long lo = (long long)s_minmax[0] + s_minmax[2] + s_minmax[4];
   const long long hi = (long long)s_minmax[1] + s_minmax[3] + s_minmax[5];
-  const bool safe = lo >= 0 && hi < (long long)g.data_size;  // CTA-uniform: no lookup can leave the grid
-  const unsigned dsz = (unsigned)g.data_size;
+  if (!(lo >= 0 && hi < (long long)g.data_size)) return false;
   const int np = ps.P;
   const int slice = warp % psplit, wtask = warp / psplit, ntw = nwarps / psplit;
-  const int plen = (((np + psplit - 1) / psplit) + 7) & ~7;
+  const int plen = (((np + psplit - 1) / psplit) + 3) & ~3;
   const int pb = min(np, slice * plen), pe = min(np, pb + plen);
   const int iters = (task1 - task0 + ntw - 1) / ntw;  // CTA-uniform
+  const double ap = ps.penalize ? penalty_angle(ps, pen, a) : 1.0;
   double wmax = 0.0;
   for (int it = 0; it < iters; it++) {
     const int task = task0 + wtask + it * ntw;
@@ -458,11 +511,12 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
     const int iy = tv ? task / nxc : 0, xc = tv ? task - iy * nxc : 0;
     const int ix = (xc << 5) + lane;
     const bool active = tv && ix < ps.nX;
+    // the penalty does not depend on the sum: its divisions overlap the lookups
+    const double dpap = (ps.penalize && active && slice == 0) ? penalty_distance(ps, pen, ix, iy) * ap : 1.0;
     unsigned sum = 0;
     if (tv) {
       const int base = s_row[iy] + s_col[active ? ix : 0] + minoff;
-      const uint8_t* gp = A.grid + base;
-      sum = safe ? sweep_row<false>(gp, s_off + pb, pe - pb, base, dsz) : sweep_row<true>(gp, s_off + pb, pe - pb, base, dsz);
+      sum = res_sweep_row(A.grid + base, s_off + pb, pe - pb);
     }
     if (psplit > 1) {
       s_part[warp * 32 + lane] = sum;
@@ -472,7 +526,7 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
       __syncthreads();
     }
     if (active && slice == 0) {
-      const double rr = response_of(ps, pen, sum, ix, iy, a);
+      const double rr = response_from(ps, sum, dpap);
       A.resp[((size_t)iy * ps.nX + ix) * ps.nA + a] = rr;
       atomicMax(A.cellmax + (size_t)iy * ps.nX + ix, (unsigned long long)__double_as_longlong(rr));
       wmax = rr > wmax ? rr : wmax;
@@ -489,6 +543,7 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
     for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
     atomicMax(reinterpret_cast<unsigned long long*>(A.passmax), (unsigned long long)__double_as_longlong(m));
   }
+  return true;
 }
 
 // ---- tail (CTA 0) -----------------------------------------------------------------------------------------
@@ -499,35 +554,53 @@ struct ResTail {
   double acc[4];
   double tmp4[32][4];
   PassOut po[2];
-  unsigned long long fbest;
   int angs[YSM_RES_MAXNA];
 };
 
-// CorrelateScan epilogue of the coarse pass (reduce_body's logic for one CTA of any size): ties in
-// storage order, sequential sums, A.9 accumulators. Returns false when the tie list overflows.
+// CorrelateScan epilogue of the coarse pass (reduce_body's logic, restated for one CTA with few dependent
+// L2 round trips): round 1 = best response + the per-cell maxima (kept in registers for A.9), round 2 = the
+// responses of the few cells that can hold a tied pose; ties in storage order, sequential sums.
+// Returns false when a list overflows (the host takes the general path).
+#define YSM_RES_CELLS_PT 4   // lattice cells a thread keeps in registers (more: re-read)
 __device__ __forceinline__ bool
 res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
   const PassDev& ps = rq.coarse;
-  const int tid = threadIdx.x, T = blockDim.x;
-  const double best = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(A.passmax)));
-  if (tid == 0) S.count = 0;
-  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
   const int ncell = ps.nX * ps.nY;
-  for (int c = tid; c < ncell; c += T) {
+  if (tid == 0) { S.count = 0; S.n = 0; }
+  double cm[YSM_RES_CELLS_PT];
+#pragma unroll
+  for (int k = 0; k < YSM_RES_CELLS_PT; k++) {
+    const int c = tid + k * T;
+    cm[k] = c < ncell ? __longlong_as_double((long long)__ldcg(A.cellmax + c)) : -1.0;
+  }
+  const double best = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(A.passmax)));
+  __syncthreads();
+  // cells whose maximum is within the tie tolerance of the best (S.sorted doubles as the cell list)
+#pragma unroll
+  for (int k = 0; k < YSM_RES_CELLS_PT; k++) {
+    if (cm[k] >= best - YSM_KT_TOLERANCE) {  // (cells past the lattice hold -1)
+      const int pos = atomicAdd(&S.n, 1);
+      if (pos < YSM_RES_TIECAP) S.sorted[pos] = tid + k * T;
+    }
+  }
+  for (int c = tid + YSM_RES_CELLS_PT * T; c < ncell; c += T) {
     const double m = __longlong_as_double((long long)__ldcg(A.cellmax + c));
     if (m >= best - YSM_KT_TOLERANCE) {
-      const double* pc = A.resp + (size_t)c * ps.nA;
-      for (int a0 = 0; a0 < ps.nA; a0 += 8) {
-        double r[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) r[u] = a0 + u < ps.nA ? __ldcg(pc + a0 + u) : -1.0;
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          if (r[u] >= 0.0 && kt_double_equal(r[u], best)) {
-            const int pos = atomicAdd(&S.count, 1);
-            if (pos < YSM_RES_TIECAP) S.list[pos] = c * ps.nA + a0 + u;
-          }
-      }
+      const int pos = atomicAdd(&S.n, 1);
+      if (pos < YSM_RES_TIECAP) S.sorted[pos] = c;
+    }
+  }
+  __syncthreads();
+  const int ncand = S.n;
+  if (ncand > YSM_RES_TIECAP) return false;
+  for (int it = tid; it < ncand * ps.nA; it += T) {
+    const int j = it / ps.nA, a = it - j * ps.nA;
+    const int c = S.sorted[j];
+    const double r = __ldcg(A.resp + (size_t)c * ps.nA + a);
+    if (kt_double_equal(r, best)) {
+      const int pos = atomicAdd(&S.count, 1);
+      if (pos < YSM_RES_TIECAP) S.list[pos] = c * ps.nA + a;
     }
   }
   __syncthreads();
@@ -568,10 +641,9 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
   double norm = 0.0, axx = 0.0, axy = 0.0, ayy = 0.0;
   if (!(best < YSM_KT_TOLERANCE)) {
     const double dx = S.po[0].avg_x - ps.cx, dy = S.po[0].avg_y - ps.cy;
-    for (int c = tid; c < ncell; c += T) {
-      const int iy = c / ps.nX, ix = c - iy * ps.nX;
-      const double pm = __longlong_as_double((long long)__ldcg(A.cellmax + c));
+    auto add_cell = [&](int c, double pm) {
       if (pm >= (best - 0.1)) {
+        const int iy = c / ps.nX, ix = c - iy * ps.nX;
         const double x = startX + (double)ix * ps.resx;
         const double y = startY + (double)iy * ps.resy;
         norm += pm;
@@ -579,7 +651,12 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
         axy += ((x - dx) * (y - dy) * pm);
         ayy += ((y - dy) * (y - dy) * pm);
       }
-    }
+    };
+#pragma unroll
+    for (int k = 0; k < YSM_RES_CELLS_PT; k++)
+      if (tid + k * T < ncell) add_cell(tid + k * T, cm[k]);
+    for (int c = tid + YSM_RES_CELLS_PT * T; c < ncell; c += T)
+      add_cell(c, __longlong_as_double((long long)__ldcg(A.cellmax + c)));
   }
   for (int o = 16; o > 0; o >>= 1) {
     norm += __shfl_xor_sync(0xffffffffu, norm, o);
@@ -587,89 +664,130 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
     axy += __shfl_xor_sync(0xffffffffu, axy, o);
     ayy += __shfl_xor_sync(0xffffffffu, ayy, o);
   }
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
     S.tmp4[tid >> 5][0] = norm; S.tmp4[tid >> 5][1] = axx; S.tmp4[tid >> 5][2] = axy; S.tmp4[tid >> 5][3] = ayy;
   }
   __syncthreads();
-  if (tid < 4) {
-    double r = 0.0;
-    for (int w = 0; w < (int)(T >> 5); w++) r += S.tmp4[w][tid];
-    if (tid == 0) S.po[0].norm = r;
-    else if (tid == 1) S.po[0].axx = r;
-    else if (tid == 2) S.po[0].axy = r;
-    else S.po[0].ayy = r;
+  if (tid < 32) {
+    const int nw = (int)(T >> 5);
+    double v0 = lane < nw ? S.tmp4[lane][0] : 0.0, v1 = lane < nw ? S.tmp4[lane][1] : 0.0;
+    double v2 = lane < nw ? S.tmp4[lane][2] : 0.0, v3 = lane < nw ? S.tmp4[lane][3] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+    }
+    if (lane == 0) { S.po[0].norm = v0; S.po[0].axx = v1; S.po[0].axy = v2; S.po[0].ayy = v3; }
   }
   __syncthreads();
   return true;
 }
 
-// fine CorrelateScan at the coarse winner: offsets, 3 x 3 x nAf sweep, max / ties, angular covariance sums.
-// s_q: query points; s_ft: [nAf][4] cos / sin of the fine angles and of their normalised headings.
-__device__ __forceinline__ bool
-res_fine(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResArgs& A, ResTail& S, PassDev& f, const TableDev& ft,
-         const double2* s_q, const double* s_ft, int* s_foff, unsigned* s_fsum, double* s_fr) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = blockDim.x, nwarps = T >> 5;
-  const int nAf = f.nA, P = f.P, Ppad = f.Ppad;
-  for (int it = tid; it < nAf * P; it += T) {
-    const int a = it / P, p = it - a * P;
-    int gx, gy;
-    offset_cell(ft, g.scale, s_q[p].x, s_q[p].y, s_ft[4 * a], s_ft[4 * a + 1], gx, gy);
-    s_foff[a * Ppad + p] = gx + gy * g.stride;
-  }
-  if (tid == 0) S.fbest = 0ull;
-  __syncthreads();
-  const int nxy = f.nX * f.nY, nposes = nxy * nAf;
+// ---- fine CorrelateScan at the coarse winner, spread over the machine ------------------------------------
+// CTA 0 publishes the winner (angle, lattice cell); the workers, idle after the coarse sweep, each take
+// (fine angle, 32 query points) items: rotate the points (ComputeOffsets), look up the 3 x 3 cells, one warp
+// reduction per pose, integer atomics into fsum[iy][ix][a]. CTA 0 then finishes: responses, max / ties,
+// angular covariance sums. (On ONE SM the 3 x 3 x nAf x P scattered byte lookups cost ~0.5 cycle each.)
+#define YSM_RES_WIN_NOFINE 0xFFFFFFFFu
+
+// the fine pass's search centre from the winning coarse lattice cell: with a single winner the tie average
+// is (cx + (startX + ix * resx)) / 1.0 -- the same expression everywhere
+__device__ __forceinline__ void res_fine_centre(const PassDev& ps, int ix, int iy, double& cx, double& cy) {
+  cx = (0.0 + (ps.cx + (-ps.offx + (double)ix * ps.resx))) / 1.0;
+  cy = (0.0 + (ps.cy + (-ps.offy + (double)iy * ps.resy))) / 1.0;
+}
+
+// one warp, one item
+__device__ __forceinline__ void
+res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsigned winw, double2 pt, bool valid) {
+  const PassDev& ps = rq.coarse;
+  const PassDev& f = rq.fine;
+  const TableDev& ft = rq.ftab;
+  const int lane = threadIdx.x & 31;
+  const int nAf = f.nA, nxy = f.nX * f.nY;
+  const int a = item % nAf;  // fine angle (the chunk of points came with `pt`)
+  const int wa = (int)(winw & 0xFFu), wix = (int)((winw >> 8) & 0xFFFu), wiy = (int)(winw >> 20);
+  double cx, cy;
+  res_fine_centre(ps, wix, wiy, cx, cy);
+  const double* row = A.spec_dev + rq.nA + 4 * ((size_t)wa * nAf + a);
+  const double cosine = __ldcg(row), sine = __ldcg(row + 1);
+  int gx, gy;
+  offset_cell(ft, g.scale, pt.x, pt.y, cosine, sine, gx, gy);
+  const int o = gx + gy * g.stride;
   const unsigned dsz = (unsigned)g.data_size;
-  for (int pose = warp; pose < nposes; pose += nwarps) {
-    const int c = pose / nAf, a = pose - c * nAf;
-    const int iy = c / f.nX, ix = c - iy * f.nX;
-    const double x = -f.offx + (double)ix * f.resx;
-    const double y = -f.offy + (double)iy * f.resy;
-    const int gx = world_to_grid1(f.cx + x, f.gox, g.scale) + g.border;
-    const int gy = world_to_grid1(f.cy + y, f.goy, g.scale) + g.border;
-    const int base = gx + gy * g.stride;
-    const int* off = s_foff + a * Ppad;
-    unsigned sum = 0;
-    for (int p0 = lane; p0 < P; p0 += 384) {
-      unsigned idx[12];
+  for (int c0 = 0; c0 < nxy; c0 += 3) {
+    unsigned v[3];
 #pragma unroll
-      for (int u = 0; u < 12; u++) idx[u] = (p0 + 32 * u < P) ? (unsigned)(base + off[p0 + 32 * u]) : 0xFFFFFFFFu;
-#pragma unroll
-      for (int u = 0; u < 12; u++) if (idx[u] < dsz) sum += (unsigned)A.grid[idx[u]];
+    for (int u = 0; u < 3; u++) {
+      unsigned idx = 0xFFFFFFFFu;
+      if (c0 + u < nxy) {
+        const int iy = (c0 + u) / f.nX, ix = (c0 + u) - iy * f.nX;
+        const double x = -f.offx + (double)ix * f.resx;
+        const double y = -f.offy + (double)iy * f.resy;
+        const int bx = world_to_grid1(cx + x, f.gox, g.scale) + g.border;
+        const int by = world_to_grid1(cy + y, f.goy, g.scale) + g.border;
+        idx = (unsigned)(bx + by * g.stride + o);
+      }
+      v[u] = (valid && idx < dsz) ? (unsigned)A.grid[idx] : 0u;
     }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) {
-      const double rr = response_of(f, pen, sum, ix, iy, a);
-      s_fsum[pose] = sum;
-      s_fr[pose] = rr;  // storage order [iy][ix][a] == pose index
-      atomicMax(&S.fbest, (unsigned long long)__double_as_longlong(rr));
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const unsigned r = __reduce_add_sync(0xffffffffu, v[u]);
+      if (lane == 0 && c0 + u < nxy && r) atomicAdd(A.fsum + (c0 + u) * nAf + a, r);
     }
   }
-  __syncthreads();
-  const double best = __longlong_as_double((long long)S.fbest);
-  // ties in storage order: ordered compaction warp by warp
+}
+
+// CTA 0, after the workers' sums: responses, max / ties (storage order), angular covariance sums.
+// s_fsum: the sums copied to shared memory; s_ft: [nAf][4] trig rows of the winning angle.
+__device__ __forceinline__ bool
+res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& f, const double* s_ft, const unsigned* s_fsum,
+                double* s_fr) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = blockDim.x, nwarps = T >> 5;
+  const int nAf = f.nA, nxy = f.nX * f.nY, nposes = nxy * nAf;
+  double* s_dp = &S.tmp4[0][0];   // [nxy] distance penalty of cell c   (nxy <= 64)
+  double* s_ap = &S.tmp4[16][0];  // [nAf] angle penalty of angle a     (nAf <= 64)
   if (tid == 0) S.count = 0;
-  __syncthreads();
-  for (int c0 = 0; c0 < nposes; c0 += T) {
-    const int i = c0 + tid;
-    const bool tie = i < nposes && kt_double_equal(s_fr[i], best);
-    const unsigned bal = __ballot_sync(0xffffffffu, tie);
-    if (lane == 0) S.sorted[warp] = __popc(bal);  // (sorted[] is free here; T / 32 <= TIECAP)
-    __syncthreads();
-    int before = S.count;
-    for (int w = 0; w < warp; w++) before += S.sorted[w];
-    const int pos = before + __popc(bal & ((1u << lane) - 1u));
-    if (tie && pos < YSM_RES_TIECAP) S.list[pos] = i;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = S.count;
-      for (int w = 0; w < nwarps; w++) tot += S.sorted[w];
-      S.count = tot;
-    }
-    __syncthreads();
+  if (tid < nxy) {
+    const int iy = tid / f.nX, ix = tid - iy * f.nX;
+    s_dp[tid] = penalty_distance(f, pen, ix, iy);
+  } else if (tid >= 64 && tid < 64 + nAf) {
+    s_ap[tid - 64] = penalty_angle(f, pen, tid - 64);
   }
+  __syncthreads();
+  double mx = 0.0;
+  for (int pose = tid; pose < nposes; pose += T) {
+    const int c = pose / nAf, a = pose - c * nAf;
+    const double rr = response_from(f, s_fsum[pose], s_dp[c] * s_ap[a]);
+    s_fr[pose] = rr;
+    mx = rr > mx ? rr : mx;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = t > mx ? t : mx;
+  }
+  __syncthreads();  // (s_dp / s_ap were read above: tmp4 is reused for the maxima)
+  if (lane == 0) S.tmp4[warp][0] = mx;
+  __syncthreads();
+  double best = 0.0;
+  for (int w = 0; w < nwarps; w++) best = S.tmp4[w][0] > best ? S.tmp4[w][0] : best;
+  // ties (few): collected in any order, then rank-sorted into storage order
+  for (int i = tid; i < nposes; i += T)
+    if (kt_double_equal(s_fr[i], best)) {
+      const int pos = atomicAdd(&S.count, 1);
+      if (pos < YSM_RES_TIECAP) S.sorted[pos] = i;
+    }
+  __syncthreads();
   const int nt = S.count;
   if (nt > YSM_RES_TIECAP) return false;
+  for (int e = tid; e < nt; e += T) {
+    const int v = S.sorted[e];
+    int rank = 0;
+    for (int k = 0; k < nt; k++) rank += (S.sorted[k] < v);
+    S.list[rank] = v;
+  }
+  __syncthreads();
   if (tid == 0) {
     const double startX = -f.offx, startY = -f.offy;
     double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
@@ -693,15 +811,14 @@ res_fine(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResArgs& A
     po.norm = 0.0; po.axx = 0.0; po.axy = 0.0; po.ayy = 0.0;
     po.n_ties = nt;
     po.first_idx = nt > 0 ? S.list[0] : -1;
+    S.first = -1;
   }
   __syncthreads();
-  // ComputeAngularCovariance sums: un-penalised GetResponse at the best cell for every fine angle. The
-  // best cell is one of the 3 x 3 lattice cells whenever the mean rounds onto it: reuse those sums.
+  // ComputeAngularCovariance sums: un-penalised GetResponse at the best cell for every fine angle. The best
+  // cell is one of the lattice cells whenever the mean rounds onto one (else: general path).
   if (nt > 0) {
     const int gx = world_to_grid1(S.po[1].avg_x, f.gox, g.scale) + g.border;
     const int gy = world_to_grid1(S.po[1].avg_y, f.goy, g.scale) + g.border;
-    if (tid == 0) S.first = -1;
-    __syncthreads();
     if (tid < nxy) {
       const int iy = tid / f.nX, ix = tid - iy * f.nX;
       const double x = -f.offx + (double)ix * f.resx;
@@ -712,21 +829,8 @@ res_fine(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResArgs& A
     }
     __syncthreads();
     const int cell = S.first;
-    if (cell >= 0) {
-      for (int a = tid; a < nAf; a += T) S.angs[a] = (int)s_fsum[cell * nAf + a];
-    } else {
-      const int base = gx + gy * g.stride;
-      for (int a = warp; a < nAf; a += nwarps) {
-        const int* off = s_foff + a * Ppad;
-        unsigned sum = 0;
-        for (int p = lane; p < P; p += 32) {
-          const unsigned idx = (unsigned)(base + off[p]);
-          if (idx < dsz) sum += (unsigned)A.grid[idx];
-        }
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) S.angs[a] = (int)sum;
-      }
-    }
+    if (cell < 0) return false;
+    for (int a = tid; a < nAf; a += T) S.angs[a] = (int)s_fsum[cell * nAf + a];
   } else {
     for (int a = tid; a < nAf; a += T) S.angs[a] = 0;
   }
@@ -762,13 +866,16 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
   __shared__ __align__(16) ResReq s_rq;
   __shared__ ResTail s_tail;
   __shared__ int s_tile[YSM_RES_MAXT], s_cnt[YSM_RES_MAXT], s_slots[YSM_RES_MAXT];
-  __shared__ int s_nt, s_ok, s_cmd;
+  __shared__ int s_nt, s_cmd, s_fail;
+  __shared__ int s_io[2];
   __shared__ uint4 s_db;
   __shared__ int s_minmax[8];
   __shared__ __align__(8) int s_misc[16];
   __shared__ double s_wmax[32];
   __shared__ unsigned long long s_ts[YSM_RES_TS];
-  const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
+  __shared__ unsigned long long s_win;
+  __shared__ unsigned long long s_pf[YSM_RES_PROF];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = blockDim.x;
   const int G = (int)gridDim.x, bid = (int)blockIdx.x;
   // the stamp table stays in shared memory for the kernel's lifetime
   const int ntab4 = (int)(stamp_table_bytes(g.K, g.Wt) / 16);
@@ -779,16 +886,25 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
   unsigned char* dyn = dsm + (size_t)ntab4 * 16;
   const uint32_t lane_tab_s = (uint32_t)__cvta_generic_to_shared(dsm) + (uint32_t)(lane * g.Wt * 2);
   const bool poller = bid <= YSM_RES_POLLERS;
+  const bool worker = bid >= 1;
   const ResReq* hreq = reinterpret_cast<const ResReq*>(A.req);
+  unsigned long long* bar1 = A.bars;
+  unsigned long long* bar2 = A.bars + YSM_RES_BAR_STRIDE;
+  unsigned long long* bar_sweep = A.bars + 2 * YSM_RES_BAR_STRIDE;
+  unsigned long long* bar_fine = A.bars + 3 * YSM_RES_BAR_STRIDE;
+  unsigned long long* bar3 = A.bars + 4 * YSM_RES_BAR_STRIDE;
   unsigned seq_done = A.last_seq;
-  unsigned round = 0u, t1 = 0u, t2 = 0u, t3 = 0u, t4 = 0u;
+  unsigned round = 0u, t1 = 0u, t2 = 0u, t3 = 0u, t4 = 0u, t5 = 0u;
+  unsigned fails2 = 0u, fails3 = 0u;  // failure counts seen so far at barrier 2 / the sweep-done counter
   unsigned long long idle0 = res_timer();
   int exit_code = 0;
   if (tid < YSM_RES_MAXT) { s_tile[tid] = -1; s_cnt[tid] = 0; }
+  if (tid == 0) { s_nt = 0; s_fail = 0; }
   __syncthreads();
 #define RES_TS(k) if (bid == 0 && tid == 0) s_ts[k] = res_timer();
   for (;;) {
     round++;
+    unsigned long long* pf = s_pf;  // per-CTA phase timestamps (thread 0)
     // ---- wait for the doorbell -----------------------------------------------------------------------
     int cmd = RES_CMD_NONE;
     if (poller) {
@@ -796,7 +912,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
         int c = RES_CMD_NONE;
         for (unsigned spins = 1u;; spins++) {
-          d = res_ld_volatile_v4(A.db);
+          d = res_ld_volatile_v4(reinterpret_cast<const unsigned char*>(A.db) + (size_t)bid * YSM_RES_DB_STRIDE);
           if (d.x != seq_done) { c = (int)(d.y & 0xFFu); break; }
           if (bid == 0) {
             if ((spins & 7u) == 0u && res_timer() - idle0 > A.idle_ns) {
@@ -816,6 +932,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       cmd = s_cmd;
     }
     if (bid == 0 && tid == 0) s_ts[0] = res_timer();
+    if (threadIdx.x == 0) pf[8] = res_timer();
     if (poller && cmd == RES_CMD_MATCH) {
       const uint4 d = s_db;
       const int nbase = (int)((d.y >> 8) & 0xFFu), pstride = (int)(d.z >> 16);
@@ -828,7 +945,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       } else {
         for (int s = bid - 1; s <= nbase; s += YSM_RES_POLLERS) {
           if (s < nbase) {
-            res_filter_scan(g, A, hreq, s, pstride, dyn, s_misc);
+            res_filter_scan(g, A, hreq, s, pstride, dyn, s_misc, pf);
           } else {
             const int Pq = (int)(d.z & 0xFFFFu);
             const double2* src = reinterpret_cast<const double2*>(A.pts + 2 * (size_t)s * pstride);
@@ -839,7 +956,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         }
       }
     } else if (bid == 0) {
-      // quit / ping / idle: a 32-byte control block made here
+      // quit / ping / idle: a two-word control block made here
       if (tid == 0) {
         unsigned* c = reinterpret_cast<unsigned*>(A.ctl);
         c[0] = s_db.x;
@@ -848,62 +965,78 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       if (cmd == RES_CMD_PING && tid == 0)
         res_st_volatile_v4(A.out, make_uint4((unsigned)RES_ST_PONG, 1u, s_db.x, 0u));
     }
+    if (threadIdx.x == 0) pf[12] = res_timer();
     RES_TS(1)
     // ---- barrier 1: cells, query points and control block are in HBM ----------------------------
     t1 += (unsigned)G;
-    if (!res_barrier(A.bars, t1, A.abort_flag, &s_ok, A.stall_ns)) { exit_code = 2; break; }
+    if (!res_barrier(bar1, t1, false, A.abort_flag, s_io, A.stall_ns)) { exit_code = 2; break; }
     RES_TS(2)
-    {
-      const unsigned* c = reinterpret_cast<const unsigned*>(A.ctl);
-      if (tid == 0) { s_misc[0] = (int)__ldcg(c); s_misc[1] = (int)__ldcg(c + 1); }
-      __syncthreads();
-    }
-    const unsigned seq = (unsigned)s_misc[0];
-    cmd = s_misc[1];
-    __syncthreads();
-    if (cmd == RES_CMD_QUIT || cmd == RES_CMD_NONE) break;
-    if (cmd == RES_CMD_PING) {
-      seq_done = seq;
-      idle0 = res_timer();
-      continue;
-    }
-    // the request's control block -> shared memory (header, descriptors, the nA trig rows)
+    // control block -> shared memory in ONE round of loads: header, descriptors and the first 32 trig rows
+    // (the usual 21 search angles)
     {
       const int hdr4 = (int)(offsetof(ResReq, trig4) / 16);
       const uint4* src = reinterpret_cast<const uint4*>(A.ctl);
       uint4* dst = reinterpret_cast<uint4*>(&s_rq);
-      for (int i = tid; i < hdr4; i += T) dst[i] = __ldcg(src + i);
-      __syncthreads();
-      const int n4 = hdr4 + 2 * s_rq.nA;
-      for (int i = hdr4 + tid; i < n4; i += T) dst[i] = __ldcg(src + i);
+      for (int i = tid; i < hdr4 + 64; i += T) dst[i] = __ldcg(src + i);
       __syncthreads();
     }
+    const unsigned seq = s_rq.seq;
+    cmd = (int)s_rq.cmd;
+    if (cmd == RES_CMD_QUIT || cmd == RES_CMD_NONE) break;
+    if (cmd == RES_CMD_PING) {
+      seq_done = seq;
+      idle0 = res_timer();
+      __syncthreads();
+      continue;
+    }
+    if (s_rq.nA > 32) {
+      const int hdr4 = (int)(offsetof(ResReq, trig4) / 16);
+      const uint4* src = reinterpret_cast<const uint4*>(A.ctl);
+      uint4* dst = reinterpret_cast<uint4*>(&s_rq);
+      for (int i = hdr4 + 64 + tid; i < hdr4 + 2 * s_rq.nA; i += T) dst[i] = __ldcg(src + i);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) pf[0] = res_timer();
     const ResReq& rq = s_rq;
     const PassDev& ps = rq.coarse;
     const int nv = rq.nA * rq.task_chunks;
     int v = bid - 1;
-    const bool worker = bid >= 1;
     // lookup offsets of this CTA's first angle (they do not depend on the grid): before the stamping
     if (worker && v < nv) res_sweep_prep(g, rq, A, v % rq.nA, reinterpret_cast<int*>(dyn + A.o_off), s_minmax);
-    if (bid == 0) {
-      // the tail needs the query points in shared memory
-      double2* s_q = reinterpret_cast<double2*>(dyn + A.o_off + rq.o_q);
-      for (int i = tid; i < ps.P; i += T) s_q[i] = __ldcg(reinterpret_cast<const double2*>(A.qpts) + i);
+    // the fine pass's items of this CTA (fine angle x 32 query points; warp w takes item bid - 1 + w (G - 1)):
+    // the points wait in registers
+    const int fine_chunks = (ps.P + 31) >> 5, fine_items = rq.do_refine ? rq.nAf * fine_chunks : 0;
+    const int my_item = (bid - 1) + warp * (G - 1);
+    const bool have_item = worker && my_item < fine_items;
+    double2 my_pt = make_double2(0.0, 0.0);
+    bool my_valid = false;
+    if (have_item) {
+      const int p = (my_item / rq.nAf) * 32 + lane;
+      my_valid = p < ps.P;
+      if (my_valid) my_pt = __ldcg(reinterpret_cast<const double2*>(A.qpts) + p);
     }
+    if (threadIdx.x == 0) pf[1] = res_timer();
     // ---- phase B: stamp the tiles this CTA owns -------------------------------------------------------
     {
-      const int total = min(__ldcg(A.ncells), A.cells_cap);
+      const int total = min(rq.nbase * rq.pstride, A.cells_cap);
       uint32_t* s_steps = reinterpret_cast<uint32_t*>(dyn);
       uint32_t* s_stage = s_steps + YSM_RES_MAXT * YSM_RES_CAND;
-      res_collect(g, A, total, G, bid, s_tile, s_cnt, s_steps);
+      res_collect(g, A, total, G, bid, s_tile, s_cnt, s_steps, &s_fail);
       __syncthreads();
+      if (threadIdx.x == 0) pf[2] = res_timer();
       res_stamp(g, A, s_tile, s_cnt, s_steps, s_slots, &s_nt, s_stage, lane_tab_s);
     }
+    if (threadIdx.x == 0) pf[3] = res_timer();
     RES_TS(3)
     t2 += (unsigned)G;
-    if (!res_barrier(A.bars + 32, t2, A.abort_flag, &s_ok, A.stall_ns)) { exit_code = 2; break; }
+    if (!res_barrier(bar2, t2, s_fail != 0, A.abort_flag, s_io, A.stall_ns)) { exit_code = 2; break; }
     RES_TS(4)
-    const bool failed = __ldcg(A.fail) != 0;
+    if (threadIdx.x == 0) pf[4] = res_timer();
+    const bool failed = (unsigned)s_io[1] != fails2;  // some CTA overflowed its tile lists
+    fails2 = (unsigned)s_io[1];
+    __syncthreads();
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
     // ---- phase C: coarse sweep ------------------------------------------------------------------------------
     if (worker && !failed) {
       bool first = true;
@@ -913,16 +1046,48 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
           res_sweep_prep(g, rq, A, v % rq.nA, reinterpret_cast<int*>(dyn + A.o_off), s_minmax);
         }
         first = false;
-        res_sweep_run(g, pen, rq, A, v % rq.nA, v / rq.nA, reinterpret_cast<const int*>(dyn + A.o_off), s_minmax,
-                      reinterpret_cast<unsigned*>(dyn), s_wmax);
+        if (!res_sweep_run(g, pen, rq, A, v % rq.nA, v / rq.nA, reinterpret_cast<const int*>(dyn + A.o_off), s_minmax,
+                           reinterpret_cast<unsigned*>(dyn), s_wmax) && tid == 0)
+          s_fail = 1;
       }
     }
+    if (threadIdx.x == 0) pf[5] = res_timer();
     if (worker) {
       __syncthreads();
-      if (tid == 0) res_red_release(A.bars + 64, 1u);
+      if (tid == 0) {
+        res_arrive(bar_sweep, s_fail != 0);
+        s_fail = 0;
+      }
+      // ---- fine pass items: wait for the winner, sum, arrive ---------------------------------------
+      if (rq.do_refine) {
+        if (tid == 0) {
+          unsigned long long w = 0ull;
+          unsigned spins = 0u;
+          unsigned long long t0 = 0ull;
+          int ok = 1;
+          for (;;) {
+            w = res_ld_acquire64(A.win);
+            if ((unsigned)(w >> 32) == seq) break;
+            if ((++spins & 0x3FFu) == 0u) {
+              const unsigned long long now = res_timer();
+              if (t0 == 0ull) t0 = now;
+              if (now - t0 > A.stall_ns) atomicExch(A.abort_flag, 1);
+              if (res_ld_acquire(reinterpret_cast<const unsigned*>(A.abort_flag)) != 0u) { ok = 0; break; }
+            }
+          }
+          s_win = w;
+          s_io[0] = ok;
+        }
+        __syncthreads();
+        if (!s_io[0]) { exit_code = 2; break; }
+        const unsigned winw = (unsigned)s_win;
+        if (winw != YSM_RES_WIN_NOFINE && have_item) res_fine_item(g, rq, A, my_item, winw, my_pt, my_valid);
+        __syncthreads();
+        if (tid == 0) res_arrive(bar_fine, false);
+      }
     }
     if (bid == 0) {
-      // spec tables: the host writes them while the GPU runs phases A-C
+      // spec tables: the host writes them while the GPU runs phases A-C; a copy goes to HBM for the workers
       int status = failed ? RES_ST_FALLBACK : RES_ST_OK;
       int has_fine = 0;
       double* s_spec = reinterpret_cast<double*>(dyn + A.o_off + rq.o_spec);
@@ -935,49 +1100,77 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
           while (res_ld_volatile_v4(A.spec).x != seq) {
             if ((++spins & 0xFFu) == 0u && res_timer() - t0 > 2000000000ull) { ok = 0; break; }
           }
-          s_ok = ok;
+          s_io[0] = ok;
         }
         __syncthreads();
-        if (!s_ok) status = RES_ST_FALLBACK;
+        if (!s_io[0]) status = RES_ST_FALLBACK;
         else {
           const double2* src = reinterpret_cast<const double2*>(A.spec + sizeof(ResSpecHdr));
           double2* dst = reinterpret_cast<double2*>(s_spec);
-          for (int i = tid; i < (spec_doubles + 1) / 2; i += T) dst[i] = __ldcv(src + i);
+          double2* dst2 = reinterpret_cast<double2*>(A.spec_dev);
+          for (int i = tid; i < (spec_doubles + 1) / 2; i += T) {
+            const double2 w = __ldcv(src + i);
+            dst[i] = w;
+            dst2[i] = w;
+          }
         }
       }
       RES_TS(5)
       t3 += (unsigned)(G - 1);
-      if (tid == 0) s_ok = res_wait(A.bars + 64, t3, A.abort_flag, A.stall_ns) ? 1 : 0;
+      if (tid == 0) {
+        unsigned hi = 0u;
+        s_io[0] = res_wait(bar_sweep, t3, &hi, A.abort_flag, A.stall_ns) ? 1 : 0;
+        s_io[1] = (int)hi;
+      }
       __syncthreads();
-      if (!s_ok) { exit_code = 2; break; }
+      if (!s_io[0]) { exit_code = 2; break; }
+      if ((unsigned)s_io[1] != fails3) status = RES_ST_FALLBACK;  // (a sweep CTA met a window that can leave the grid)
+      fails3 = (unsigned)s_io[1];
       RES_TS(6)
       if (status == RES_ST_OK) {
         if (!res_reduce_coarse(rq, A, s_tail)) status = RES_ST_FALLBACK;
       }
       RES_TS(7)
-      if (status == RES_ST_OK && rq.do_refine) {
+      if (rq.do_refine) {
+        // MatchScan goes straight to the fine pass when the coarse pass has ONE winner with a non-zero
+        // response: its centre is the winning lattice pose, the heading the atan2(sin, cos) the host tabulated
+        // for that coarse angle. Otherwise the host reschedules the match (ties, response expansion).
         const PassOut& po = s_tail.po[0];
-        if (po.n_ties == 1 && po.best > YSM_KT_TOLERANCE) {
-          // MatchScan goes straight to the fine pass: its centre is the winning lattice pose, the heading
-          // the atan2(sin, cos) the host tabulated for that coarse angle
-          const int a = po.first_idx % ps.nA;
+        const bool go = status == RES_ST_OK && po.n_ties == 1 && po.best > YSM_KT_TOLERANCE;
+        const int a = go ? po.first_idx % ps.nA : 0;
+        const int cell = go ? po.first_idx / ps.nA : 0;
+        const int wiy = cell / ps.nX, wix = cell - wiy * ps.nX;
+        if (!go) status = RES_ST_FALLBACK;
+        if (tid == 0) {
+          const unsigned winw = go ? ((unsigned)a | ((unsigned)wix << 8) | ((unsigned)wiy << 20)) : YSM_RES_WIN_NOFINE;
+          res_st_release64(A.win, ((unsigned long long)seq << 32) | winw);
           PassDev& f = s_rq.fine;
-          if (tid == 0) {
-            f.cx = po.avg_x;
-            f.cy = po.avg_y;
-            f.ch = s_spec[a];
+          f.cx = po.avg_x;
+          f.cy = po.avg_y;
+          f.ch = s_spec[a];
+        }
+        RES_TS(9)
+        t4 += (unsigned)(G - 1);
+        if (tid == 0) {
+          unsigned hi = 0u;
+          s_io[0] = res_wait(bar_fine, t4, &hi, A.abort_flag, A.stall_ns) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_io[0]) { exit_code = 2; break; }
+        RES_TS(10)
+        if (go) {
+          const PassDev& f = s_rq.fine;
+          const int nposes = f.nX * f.nY * f.nA;
+          unsigned* s_fsum = reinterpret_cast<unsigned*>(dyn + A.o_off + rq.o_fsum);
+          double* s_fr = reinterpret_cast<double*>(s_fsum + ((nposes + 1) & ~1));
+          for (int i = tid; i < nposes; i += T) {
+            s_fsum[i] = __ldcg(A.fsum + i);
+            A.fsum[i] = 0u;  // (for the next request)
           }
           __syncthreads();
           const double* s_ft = s_spec + rq.nA + (size_t)4 * a * rq.nAf;
-          unsigned* s_fsum = reinterpret_cast<unsigned*>(dyn + A.o_off + rq.o_fsum);
-          double* s_fr = reinterpret_cast<double*>(s_fsum + ((f.nX * f.nY * f.nA + 1) & ~1));
-          if (res_fine(g, pen, rq, A, s_tail, f, rq.ftab, reinterpret_cast<const double2*>(dyn + A.o_off + rq.o_q), s_ft,
-                       reinterpret_cast<int*>(dyn + A.o_off + rq.o_foff), s_fsum, s_fr))
-            has_fine = 1;
-          else
-            status = RES_ST_FALLBACK;
-        } else {
-          status = RES_ST_FALLBACK;  // tied winners / response 0: the host reschedules (expansion, ties)
+          if (res_fine_finish(g, pen, s_tail, f, s_ft, s_fsum, s_fr)) has_fine = 1;
+          else status = RES_ST_FALLBACK;
         }
       }
       RES_TS(8)
@@ -986,16 +1179,17 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       // reset the per-request accumulators for the next request
       const int ncell = ps.nX * ps.nY;
       for (int i = tid; i < ncell; i += T) A.cellmax[i] = 0ull;
-      if (tid == 0) {
-        *A.passmax = 0.0;
-        *A.ncells = 0;
-        *A.fail = 0;
-      }
+      if (tid == 0) *A.passmax = 0.0;
     }
-    // ---- barrier 3: the tail has read the grid; zero the tiles this CTA stamped ---------------------
-    t4 += (unsigned)G;
-    if (!res_barrier(A.bars + 96, t4, A.abort_flag, &s_ok, A.stall_ns)) { exit_code = 2; break; }
+    // ---- barrier 3: the fine pass has read the grid; zero the tiles this CTA stamped ----------------
+    t5 += (unsigned)G;
+    if (!res_barrier(bar3, t5, false, A.abort_flag, s_io, A.stall_ns)) { exit_code = 2; break; }
     res_clear(g, A, s_tile, s_slots, s_nt);
+    if (rq.trace && A.prof && tid == 0) {
+      pf[6] = res_timer();
+      pf[7] = (unsigned long long)s_nt;
+      for (int k = 0; k < YSM_RES_PROF; k++) A.prof[(size_t)bid * YSM_RES_PROF + k] = pf[k];
+    }
     __syncthreads();
     if (tid < YSM_RES_MAXT) { s_tile[tid] = -1; s_cnt[tid] = 0; }
     if (tid == 0) s_nt = 0;
