@@ -81,6 +81,11 @@ typedef struct ysm_batch {
   int32_t do_refine;           /* Wrapper.match_scan arg 4 */
   int32_t pool_on_device;      /* 1: pool_xy is a device pointer already resident in HBM */
   int32_t _pad;
+  const uint64_t *scan_tag;    /* [n_scans] host, or NULL. A non-zero tag names the CONTENT of a scan: the caller promises
+                                  that two scans with the same tag (and point count) hold the same point readings. The
+                                  single-query path keeps tagged scans in a device-resident store, so the running scans
+                                  of sequential mapping (graph_slam.py:326) are uploaded once, not once per match.
+                                  0 = untagged (always uploaded). */
 } ysm_batch;
 
 /* 128-byte result record (what Wrapper.match_scan returns: response, best_pose, covariance). */
@@ -250,7 +255,8 @@ int ysm_debug_ping(ysm_handle *h, int32_t n, double *rtt_us);
  * out[9] lattice lookups actually issued after pruning (counted only with YSM_DEBUG_TIME_KERNELS),
  * out[10] fine passes that ran chained on the device behind their coarse pass (latency path),
  * out[11] lanes used by the call, out[12] launches of the single-kernel latency path,
- * out[13] requests served by the resident latency kernel;
+ * out[13] requests served by the resident latency kernel, out[14] scans it took from the device-resident
+ * scan store instead of host memory;
  * fills out[0..n), n <= 16 */
 int ysm_last_work(const ysm_handle *h, int64_t *out, int32_t n);
 

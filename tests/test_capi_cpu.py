@@ -28,11 +28,44 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert sorted(_capi.EXPORTS) == names
 
 
+def _header_struct_fields(name):
+    """Field names of `typedef struct name { ... } name;` in include/ysm.h, in declaration order."""
+    src = open(os.path.join(ROOT, "include", "ysm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+        for n in names.split(","):
+            out.append(re.sub(r"[\s\*]|\[.*?\]", "", n))
+    return out
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(_capi.YsmParams) == 11 * 8 + 4 + 4 + 8 + 4 + 4
     assert C.sizeof(_capi.YsmDims) == 10 * 4 + 8
-    assert C.sizeof(_capi.YsmBatch) == 4 + 4 + 8 + 7 * 8 + 4 * 4
+    assert C.sizeof(_capi.YsmBatch) == 4 + 4 + 8 + 7 * 8 + 4 * 4 + 8
     assert _capi.RESULT_DTYPE.itemsize == 128
+    for cls, name in ((_capi.YsmParams, "ysm_params"), (_capi.YsmBatch, "ysm_batch"), (_capi.YsmDims, "ysm_dims"),
+                      (_capi.YsmOccScans, "ysm_occ_scans"), (_capi.YsmOccInfo, "ysm_occ_info"),
+                      (_capi.YsmChainQuery, "ysm_chain_query")):
+        assert [f[0] for f in cls._fields_] == _header_struct_fields(name), name
+    assert list(_capi.RESULT_DTYPE.names) == _header_struct_fields("ysm_result")
+
+
+def test_integration_md_stub_structs_match_header():
+    """The ctypes stub a maintainer would paste from INTEGRATION.md declares the same fields, in the same
+    order, as include/ysm.h (a stale stub passes a short struct and the library reads past it)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cls, name in (("_Params", "ysm_params"), ("_Batch", "ysm_batch"), ("_OccScans", "ysm_occ_scans"),
+                      ("_OccInfo", "ysm_occ_info")):
+        body = re.search(r"class %s\(C\.Structure\):.*?\n\n" % cls, doc, flags=re.S).group(0)
+        assert re.findall(r'"([a-z_0-9]+)"', body) == _header_struct_fields(name), cls
+    assert re.findall(r'\("([a-z_]+)", "<', re.search(r"_RESULT = np\.dtype\(\[.*?\]\)", doc, flags=re.S).group(0)) \
+        == _header_struct_fields("ysm_result")
 
 
 def test_point_readings_bit_exact_vs_oracle():

@@ -268,6 +268,11 @@ struct Resident {
   double* d_resp = nullptr;
   unsigned long long* d_cellmax = nullptr;
   size_t resp_cap = 0, cellmax_cap = 0;
+  // device-resident scan store (ysm_batch::scan_tag): slot -> content tag
+  double* d_cache = nullptr;
+  struct Slot { uint64_t tag = 0; int count = 0; uint64_t last_use = 0; bool valid = false; };
+  Slot slots[YSM_RES_CACHE_SLOTS];
+  uint64_t use_clock = 0;
   unsigned seq = 0;
   size_t smem = 0;           // dynamic shared memory of the running instance
   size_t scratch = 0;        // ... of which worker scratch (fixes where the lookup offsets start)
@@ -277,7 +282,6 @@ struct Resident {
 };
 #define YSM_RES_PTS_CAP 131072   // points the mailbox holds
 #define YSM_RES_CELLS_CAP 131072
-#define YSM_RES_PMAX 4096
 #define YSM_RES_SPEC_DOUBLES (YSM_RES_MAXNA + 4 * 4096)
 
 struct ysm_handle {
@@ -856,13 +860,33 @@ static std::mutex g_res_mu;
 static ysm_handle* g_res_owner[64] = {nullptr};
 static std::atomic<int> g_res_alive{0};
 
-static void res_ring(Resident& R, unsigned seq, unsigned w1, unsigned w2, unsigned w3) {
-  // 16-byte doorbell {seq, w1, w2, w3}: the half that holds seq is stored last (x86 keeps the store order,
-  // the GPU reads the 16 bytes with one request). One copy per polling CTA, each on its own line.
+// One tagged 16-byte word of a doorbell line: the word that carries the tag is stored last (x86 keeps the store
+// order; the GPU reads the 16 bytes with one request and accepts a line only when all its tags agree).
+static inline void res_put(unsigned char* line, int k, unsigned a, unsigned b, unsigned c, unsigned d, int tag_pos) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(line + 16 * k);
+  const unsigned v[4] = {a, b, c, d};
+  for (int i = 0; i < 4; i++)
+    if (i != tag_pos) __atomic_store_n(&w[i], v[i], __ATOMIC_RELAXED);
+  __atomic_store_n(&w[tag_pos], v[tag_pos], __ATOMIC_RELEASE);
+}
+
+struct ResScanInfo { int count, src_slot, store_slot; };  // slots are 1-based, 0 = none
+
+// Rings the doorbell of every polling CTA: v0 = {seq, w1, w2, w3}; CTA 1 + s also learns about scan s
+// (scans[s], s <= nbase, the last one being the query) and every line carries the viewpoint / grid offset m[4].
+static void res_ring(Resident& R, unsigned seq, unsigned w1, unsigned w2, unsigned w3, const ResScanInfo* scans = nullptr,
+                     int nscans = 0, const double* m = nullptr) {
+  uint32_t mw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (m) memcpy(mw, m, 32);
   for (int k = YSM_RES_POLLERS; k >= 0; k--) {
-    uint64_t* db = reinterpret_cast<uint64_t*>(R.mb + R.o_db + (size_t)k * YSM_RES_DB_STRIDE);
-    __atomic_store_n(&db[1], (uint64_t)w2 | ((uint64_t)w3 << 32), __ATOMIC_RELEASE);
-    __atomic_store_n(&db[0], (uint64_t)seq | ((uint64_t)w1 << 32), __ATOMIC_RELEASE);
+    unsigned char* line = R.mb + R.o_db + (size_t)k * YSM_RES_DB_STRIDE;
+    ResScanInfo si = {0, 0, 0};
+    if (k >= 1 && k - 1 < nscans) si = scans[k - 1];
+    res_put(line, 4, mw[6], mw[7], 0u, seq, 3);
+    res_put(line, 3, mw[3], mw[4], mw[5], seq, 3);
+    res_put(line, 2, mw[0], mw[1], mw[2], seq, 3);
+    res_put(line, 1, seq, (unsigned)si.count, (unsigned)si.src_slot, (unsigned)si.store_slot, 0);
+    res_put(line, 0, seq, w1, w2, w3, 0);
   }
 }
 
@@ -904,6 +928,7 @@ static void res_free(ysm_handle* h) {
   if (R->d_ctl) cudaFree(R->d_ctl);
   if (R->d_cells) cudaFree(R->d_cells);
   if (R->d_qpts) cudaFree(R->d_qpts);
+  if (R->d_cache) cudaFree(R->d_cache);
   if (R->d_resp) cudaFree(R->d_resp);
   if (R->d_cellmax) cudaFree(R->d_cellmax);
   delete R;
@@ -937,6 +962,7 @@ static int res_alloc(ysm_handle* h) {
   CK(cudaMalloc((void**)&R->d_ctl, sizeof(ResReq)));
   CK(cudaMalloc((void**)&R->d_cells, 4 * (size_t)YSM_RES_CELLS_CAP));
   CK(cudaMalloc((void**)&R->d_qpts, 16 * (size_t)YSM_RES_PMAX));
+  CK(cudaMalloc((void**)&R->d_cache, 16 * (size_t)YSM_RES_PMAX * YSM_RES_CACHE_SLOTS));
   const int idle_us = h->prm.resident_idle_us > 0 ? h->prm.resident_idle_us : 2000;
   R->idle_ns = (unsigned long long)idle_us * 1000ull;
   R->G = h->num_sms;
@@ -975,6 +1001,7 @@ static int res_launch(ysm_handle* h, size_t smem, unsigned last_seq) {
   A.cells = R.d_cells;
   A.cells_cap = YSM_RES_CELLS_CAP;
   A.qpts = R.d_qpts;
+  A.cache = R.d_cache;
   A.resp = R.d_resp;
   A.cellmax = R.d_cellmax;
   A.stamp_tab = h->d_stamp_tab;
@@ -1075,12 +1102,13 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   const int fnX = n_steps(crx * 0.5, h->res_eff), fnY = fnX;
   if (nA < 1 || nA > YSM_RES_MAXNA || nAf < 1 || nA * nAf > 4096 || nA > 255 || nAf > 64 || fnX * fnY > 64) return 1;
   if ((long long)nX * nY * nA > (1 << 21) || fnX * fnY * nAf > 4096) return 1;
+  if ((long long)nAf * ((P + 31) / 32) > 32LL * (h->num_sms - 1)) return 1;  // fine-pass items: one per warp
   const int Ppad = align_up(P, 4);
   const size_t tab_bytes = stamp_table_bytes(g.K, g.Wt);
   // shared memory: stamp table | scratch | workers: offsets + lattice / CTA 0: query points, spec, fine offsets, fine sums
   const size_t scratch = res_scratch_bytes(pstride);
-  const size_t worker = (size_t)(((P + 7) & ~7) + nX + nY) * 4;
-  const size_t o_q = 0, o_spec = a16(o_q + 16 * (size_t)P), o_foff = a16(o_spec + 8 * (size_t)(nA + 4 * nA * nAf));
+  const size_t worker = 16 * (size_t)YSM_RES_THREADS + (size_t)(((P + 7) & ~7) + nX + nY) * 4;  // point stash | offsets + lattice
+  const size_t o_q = 0, o_spec = a16(o_q + 16 * (size_t)std::max(P, YSM_RES_THREADS)), o_foff = a16(o_spec + 8 * (size_t)(nA + 4 * nA * nAf));
   const size_t o_fsum = a16(o_foff + 4 * (size_t)nAf * Ppad);
   const size_t tail = a16(o_fsum + 12 * (size_t)(fnX * fnY * nAf + 2));
   size_t need = tab_bytes + scratch + std::max(worker, tail);
@@ -1126,6 +1154,14 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
     while (psplit * 2 * tpc <= 32 && P / (psplit * 2) >= 16) psplit *= 2;
     rq->tpc = tpc; rq->psplit = psplit; rq->task_chunks = (tasks + tpc - 1) / tpc;
   }
+  {
+    // tile lists: coarse-resolution grids have few tiles per CTA but many stamps per tile
+    const int tiles_per_grid = h->tnx * h->tnx;
+    rq->maxt = tiles_per_grid / R.G >= 16 ? YSM_RES_MAXT : YSM_RES_MAXT / 2;
+    rq->cand = YSM_RES_MAXT * YSM_RES_CAND / rq->maxt;
+    rq->tail_warps = 4;
+    rq->pad1 = 0;
+  }
   rq->o_q = (unsigned)o_q; rq->o_spec = (unsigned)o_spec; rq->o_foff = (unsigned)o_foff; rq->o_fsum = (unsigned)o_fsum;
   MatchDev& m = rq->m;
   m.slot = 0; m.base_begin = 0; m.base_end = nbase; m.cells_off = 0; m.gbox_off = 0; m.pad0 = 0;
@@ -1162,20 +1198,62 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
       rq->trig4[a][3] = same ? sa : sin(hn);
     }
   }
-  // points: base scan s at slot s, the query at slot nbase
+  // points: base scan s at mailbox slot s, the query at slot nbase -- unless the device-resident scan store
+  // already holds them (ysm_batch::scan_tag): then nothing is copied and the kernel reads them from HBM.
+  // An untagged or new scan goes through the mailbox; a new TAGGED scan is also kept by the kernel in a free /
+  // least recently used slot, valid once this request has completed.
   double* pts = reinterpret_cast<double*>(R.mb + R.o_pts);
-  for (int k = 0; k < nbase; k++) {
-    const int s = b->base_idx[b->base_ptr[0] + k];
+  ResScanInfo info[YSM_RES_MAXBASE + 1];
+  int pending[YSM_RES_MAXBASE + 1];
+  int npending = 0;
+  const bool use_cache = b->scan_tag != nullptr && nbase + 1 <= YSM_RES_POLLERS;
+  R.use_clock++;
+  for (int k = 0; k <= nbase; k++) {
+    const int s = k < nbase ? b->base_idx[b->base_ptr[0] + k] : q;
     const int c = b->scan_count[s];
     rq->counts[k] = (unsigned short)c;
+    info[k].count = c; info[k].src_slot = 0; info[k].store_slot = 0;
+    const uint64_t tag = use_cache ? b->scan_tag[s] : 0;
+    if (tag != 0 && c > 0) {
+      int hit = -1, victim = -1;
+      for (int j = 0; j < YSM_RES_CACHE_SLOTS; j++) {
+        const Resident::Slot& sl = R.slots[j];
+        if (sl.valid && sl.tag == tag && sl.count == c) { hit = j; break; }
+      }
+      if (hit >= 0) {
+        R.slots[hit].last_use = R.use_clock;
+        info[k].src_slot = hit + 1;
+        h->work[14]++;
+        continue;  // resident: no copy
+      }
+      bool dup = false;  // the same new scan twice in one request: the first occurrence fills the slot
+      for (int j = 0; j < npending; j++) dup = dup || R.slots[pending[j]].tag == tag;
+      if (!dup) {
+        for (int j = 0; j < YSM_RES_CACHE_SLOTS; j++) {
+          const Resident::Slot& sl = R.slots[j];
+          if (sl.last_use == R.use_clock) continue;  // in use by this request
+          if (victim < 0 || !sl.valid || (R.slots[victim].valid && sl.last_use < R.slots[victim].last_use)) {
+            victim = j;
+            if (!sl.valid) break;
+          }
+        }
+        if (victim >= 0) {
+          Resident::Slot& sl = R.slots[victim];
+          sl.tag = tag; sl.count = c; sl.valid = false; sl.last_use = R.use_clock;
+          pending[npending++] = victim;
+          info[k].store_slot = victim + 1;
+        }
+      }
+    }
     if (c) memcpy(pts + 2 * (size_t)k * pstride, b->pool_xy + 2 * (size_t)b->scan_start[s], 16 * (size_t)c);
   }
-  rq->counts[nbase] = (unsigned short)P;
-  memcpy(pts + 2 * (size_t)nbase * pstride, b->pool_xy + 2 * (size_t)b->scan_start[q], 16 * (size_t)P);
   const unsigned ctl_bytes = (unsigned)(offsetof(ResReq, trig4) + 32 * (size_t)nA);
   tr.mark("resident: request staged");
-  res_ring(R, seq, (unsigned)RES_CMD_MATCH | ((unsigned)nbase << 8) | ((unsigned)nA << 16) | ((unsigned)nAf << 24),
-           (unsigned)P | ((unsigned)pstride << 16), ctl_bytes);
+  {
+    const double mf[4] = {m.vpx, m.vpy, m.gox, m.goy};
+    res_ring(R, seq, (unsigned)RES_CMD_MATCH | ((unsigned)nbase << 8) | ((unsigned)nA << 16) | ((unsigned)nAf << 24),
+             (unsigned)P | ((unsigned)pstride << 16), ctl_bytes, info, nbase + 1, mf);
+  }
   if (!R.alive) {
     std::lock_guard<std::mutex> lk(g_res_mu);
     R.scratch = scratch;
@@ -1207,7 +1285,12 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   }
   {
     const int rc = res_await(h, seq, need);
-    if (rc != YSM_OK) return rc;
+    if (rc != YSM_OK) {
+      for (int j = 0; j < YSM_RES_CACHE_SLOTS; j++) R.slots[j].valid = false;  // (the store may be half written)
+      return rc;
+    }
+    // phase A has run to completion for every answered request: the slots it filled are valid now
+    for (int j = 0; j < npending; j++) R.slots[pending[j]].valid = true;
   }
   // ---- read the chunks -------------------------------------------------------------------------------
   const volatile uint32_t* c0 = res_chunk(R, 0);
@@ -1234,6 +1317,7 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
                                   "spec tables in smem", "sweep done (wait)", "coarse reduce", "fine pass"};
     for (int k = 0; k < 8; k++)
       fprintf(stderr, "[ysm-resident] %-26s %8.2f us\n", names[k], (double)(ts[k + 1] - ts[k]) * 1e-3);
+    fprintf(stderr, "[ysm-resident]   SM clock over the request: %.0f MHz\n", (double)(ts[21] - ts[20]) / ((double)(ts[8] - ts[0]) * 1e-3));
     if (has_fine)
       fprintf(stderr, "[ysm-resident]   fine: winner published +%.2f, workers' sums arrived +%.2f, finish %.2f us\n",
               (double)(ts[9] - ts[7]) * 1e-3, (double)(ts[10] - ts[9]) * 1e-3, (double)(ts[8] - ts[10]) * 1e-3);
@@ -1314,7 +1398,7 @@ extern "C" int ysm_debug_ping(ysm_handle* h, int32_t n, double* rtt_us) {
     if (rc != YSM_OK) return rc;
   }
   Resident& R = *h->res;
-  const size_t need = (stamp_table_bytes(h->g.K, h->g.Wt) + res_scratch_bytes(1024) + 8192 + 16383) & ~(size_t)16383;
+  const size_t need = (stamp_table_bytes(h->g.K, h->g.Wt) + res_scratch_bytes(1024) + 16 * (size_t)YSM_RES_THREADS + 8192 + 16383) & ~(size_t)16383;
   if (need > h->res_smem_limit) return fail(h, YSM_EUNSUP, "resident kernel does not fit this configuration");
   if (!R.d_resp) {
     R.resp_cap = 65536; R.cellmax_cap = 4096;

@@ -43,6 +43,8 @@ namespace ysm {
 #define YSM_RES_TS 24        // trace timestamps
 #define YSM_RES_DB_STRIDE 256
 #define YSM_RES_PROF 16      // per-CTA trace timestamps
+#define YSM_RES_PMAX 4096    // point readings per scan
+#define YSM_RES_CACHE_SLOTS 32
 
 enum { RES_CMD_NONE = 0, RES_CMD_MATCH = 1, RES_CMD_QUIT = 2, RES_CMD_PING = 3 };
 enum { RES_ST_OK = 0, RES_ST_FALLBACK = 1, RES_ST_PONG = 2 };
@@ -52,6 +54,7 @@ struct ResReq {
   unsigned seq, cmd;
   int nbase, Pq, pstride, do_refine;
   int nA, nAf, tpc, psplit, task_chunks, trace;
+  int maxt, cand, tail_warps, pad1;  // tiles a CTA can own x stamps per tile (maxt * cand = YSM_RES_MAXT * YSM_RES_CAND)
   // CTA 0's dynamic shared memory (bytes past the stamp table and the scratch every CTA has): query points
   // (double2) | spec tables | fine lookup offsets [nAf][Ppad] | fine sums (u32) + fine responses (f64)
   unsigned o_q, o_spec, o_foff, o_fsum;
@@ -72,9 +75,12 @@ struct ResSpecHdr {
 
 struct ResArgs {
   // mapped host memory
-  const uint4* db;              // doorbells, one per polling CTA, YSM_RES_DB_STRIDE bytes apart (concurrent reads of ONE
-                                // host address are served one PCIe round trip after the other):
-                                // {seq, cmd | nbase << 8 | nA << 16 | nAf << 24, Pq | pstride << 16, ctl bytes}
+  const uint4* db;              // doorbell lines, one per polling CTA, YSM_RES_DB_STRIDE bytes apart (concurrent reads of
+                                // ONE host address are served one PCIe round trip after the other). Five tagged 16-byte
+                                // words, valid together when all carry the same new seq:
+                                //   v0 {seq, cmd | nbase << 8 | nA << 16 | nAf << 24, Pq | pstride << 16, ctl bytes}
+                                //   v1 {seq, points of this CTA's scan, source cache slot + 1 (0: mailbox), slot to fill + 1}
+                                //   v2..v4 {w, w, w, seq}: viewpoint x, y and grid offset x, y as eight 32-bit halves
   const unsigned char* req;     // ResReq
   const double* pts;            // scan s at pts + 2 * s * pstride ([nbase] = query)
   const unsigned char* spec;    // ResSpecHdr | heading[nA] | ftrig4[nA][nAf][4]
@@ -92,6 +98,7 @@ struct ResArgs {
   uint32_t* cells;              // [nbase][pstride] cell of every base point reading (YSM_INVALID_CELL: dropped)
   int cells_cap;
   double* qpts;                 // query point readings
+  double* cache;                // device-resident scan store: YSM_RES_CACHE_SLOTS x YSM_RES_PMAX points
   double* resp;                 // [iy][ix][a] coarse responses
   unsigned long long* cellmax;  // [iy][ix]
   double* passmax;
@@ -191,8 +198,8 @@ __device__ __forceinline__ unsigned res_tile_hash(int t) { return (unsigned)t * 
 
 // ---- phase A: FindValidPoints of one base scan, points pulled from mapped host memory ----
 __device__ __forceinline__ void
-res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int pstride, unsigned char* scratch,
-                int* s_misc, unsigned long long* pf) {
+res_filter_scan(const GridC& g, const ResArgs& A, int s, int pstride, int n_in, int src_slot, int store_slot,
+                const double* mf, unsigned char* scratch, unsigned long long* pf) {
   const int tid = threadIdx.x, T = blockDim.x;
   double* s_px = reinterpret_cast<double*>(scratch);
   double* s_py = s_px + pstride;
@@ -200,56 +207,102 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
   unsigned short* s_ja = s_next + pstride;
   unsigned short* s_jb = s_ja + pstride;
   unsigned char* s_mark = reinterpret_cast<unsigned char*>(s_jb + pstride);
-  double* s_m = reinterpret_cast<double*>(s_misc);  // [4] vpx, vpy, gox, goy; s_misc[8] = n
-  // header fields and points in one PCIe round trip (the point count is only known afterwards: pstride
-  // points are fetched)
-  if (tid == 0) {
-    s_misc[8] = (int)__ldcv(&hreq->counts[s]);
-  } else if (tid >= 32 && tid < 36) {
-    const double* src = tid == 32 ? &hreq->m.vpx : tid == 33 ? &hreq->m.vpy : tid == 34 ? &hreq->m.gox : &hreq->m.goy;
-    s_m[tid - 32] = __ldcv(src);
-  }
-  const double2* src = reinterpret_cast<const double2*>(A.pts + 2 * (size_t)s * pstride);
-  for (int i = tid; i < pstride; i += T) {
-    const double2 w = __ldcv(src + i);
-    s_px[i] = w.x;
-    s_py[i] = w.y;
-    s_mark[i] = i == 0;
+  const int n = min(n_in, pstride);
+  // the scan's point readings: from the device-resident scan store when the host found them there, else
+  // straight from mapped host memory (one PCIe round trip)
+  if (src_slot > 0) {
+    const double2* src = reinterpret_cast<const double2*>(A.cache) + (size_t)(src_slot - 1) * YSM_RES_PMAX;
+    for (int i = tid; i < n; i += T) {
+      const double2 w = __ldcg(src + i);
+      s_px[i] = w.x;
+      s_py[i] = w.y;
+      s_mark[i] = 0;
+    }
+  } else {
+    const double2* src = reinterpret_cast<const double2*>(A.pts + 2 * (size_t)s * pstride);
+    for (int i = tid; i < n; i += T) {
+      const double2 w = __ldcv(src + i);
+      s_px[i] = w.x;
+      s_py[i] = w.y;
+      s_mark[i] = 0;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) pf[9] = res_timer();
-  const int n = min(s_misc[8], pstride);
-  const double vpx = s_m[0], vpy = s_m[1], gox = s_m[2], goy = s_m[3];
+  const double vpx = mf[0], vpy = mf[1], gox = mf[2], goy = mf[3];
   const double msd = 0.1 * 0.1;  // math::Square(0.1)
+  // next[i] = first later point farther than 10 cm from point i (four candidates per step: the loads of a
+  // step are independent)
   for (int i = tid; i < n; i += T) {
     const double fx = s_px[i], fy = s_py[i];
     int j = i + 1;
-    while (j < n) {
-      const double dx = fx - s_px[j], dy = fy - s_py[j];
-      if (dx * dx + dy * dy > msd) break;
-      j++;
+    for (;;) {
+      if (j >= n) { j = n; break; }
+      const int j1 = min(j + 1, n - 1), j2 = min(j + 2, n - 1), j3 = min(j + 3, n - 1);
+      const double x0 = fx - s_px[j], y0 = fy - s_py[j], x1 = fx - s_px[j1], y1 = fy - s_py[j1];
+      const double x2 = fx - s_px[j2], y2 = fy - s_py[j2], x3 = fx - s_px[j3], y3 = fy - s_py[j3];
+      if (x0 * x0 + y0 * y0 > msd) break;
+      if (j + 1 >= n) { j = n; break; }
+      if (x1 * x1 + y1 * y1 > msd) { j += 1; break; }
+      if (j + 2 >= n) { j = n; break; }
+      if (x2 * x2 + y2 * y2 > msd) { j += 2; break; }
+      if (j + 3 >= n) { j = n; break; }
+      if (x3 * x3 + y3 * y3 > msd) { j += 3; break; }
+      j += 4;
     }
     s_next[i] = (unsigned short)j;
-    s_ja[i] = (unsigned short)j;
   }
   __syncthreads();
   if (threadIdx.x == 0) pf[10] = res_timer();
-  // the trigger chain 0 -> next[0] -> ... by pointer doubling (see fv_scan_body)
-  unsigned short* ja = s_ja;
-  unsigned short* jb = s_jb;
-  for (int span = 1; span < n; span <<= 1) {
-    for (int i = tid; i < n; i += T) {
-      const int j = ja[i];
-      if (j < n) {
-        if (s_mark[i]) s_mark[j] = 1;  // benign race: marks only go 0 -> 1 (see fv_scan_body)
-        jb[i] = ja[j];
+  // The trigger chain 0 -> next[0] -> next[next[0]] ... (FindValidPoints' firstPoint sequence), block-wise
+  // over blocks of 32 points (= warps): (1) in-warp pointer doubling (5 shuffle rounds) tells every point
+  // where the chain LEAVES the block if it enters there; (2) one thread hops from block to block through those
+  // exits, which gives every block its entry point; (3) in-warp doubling again spreads the mark from the
+  // entry over the chain's points inside the block.
+  const int nblk = (n + 31) >> 5;
+  const int lane_ = tid & 31;
+  for (int b = tid >> 5; b < nblk; b += T >> 5) {
+    const int i = b * 32 + lane_, bstart = b * 32, bend = min(n, bstart + 32);
+    int cur = i < n ? (int)s_next[i] : n;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+      const int src = cur < bend ? cur - bstart : lane_;
+      const int nxt = __shfl_sync(0xffffffffu, cur, src);
+      if (cur < bend) cur = nxt;
+    }
+    if (i < n) s_ja[i] = (unsigned short)cur;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int e = 0;
+    for (int b = 0; b < nblk; b++) {
+      if (e < n && e < (b + 1) * 32) {
+        s_jb[b] = (unsigned short)e;
+        e = s_ja[e];
       } else {
-        jb[i] = (unsigned short)n;
+        s_jb[b] = 0xFFFFu;  // the chain jumps over this block
       }
     }
-    __syncthreads();
-    unsigned short* t = ja; ja = jb; jb = t;
   }
+  __syncthreads();
+  for (int b = tid >> 5; b < nblk; b += T >> 5) {
+    const int i = b * 32 + lane_, bstart = b * 32, bend = min(n, bstart + 32);
+    const int entry = s_jb[b];
+    int jmp = i < n ? (int)s_next[i] : n;  // 2^r-th successor (absorbing outside the block)
+    bool mk = i == entry;
+    if (mk) s_mark[i] = 1;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+      if (mk && jmp < bend) s_mark[jmp] = 1;
+      __syncwarp();
+      if (i < n) mk = mk || s_mark[i] != 0;
+      const int src = jmp < bend ? jmp - bstart : lane_;
+      const int nxt = __shfl_sync(0xffffffffu, jmp, src);
+      if (jmp < bend) jmp = nxt;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) pf[11] = res_timer();
   // one entry per point reading (YSM_INVALID_CELL: dropped); the smear is a pure max, so phase B may take the
   // cells in any order and no compaction is needed
@@ -279,11 +332,16 @@ res_filter_scan(const GridC& g, const ResArgs& A, const ResReq* hreq, int s, int
     }
     out[j] = cell;
   }
+  if (store_slot > 0) {  // keep the readings for the next requests (the host marks the slot valid afterwards)
+    double2* dst = reinterpret_cast<double2*>(A.cache) + (size_t)(store_slot - 1) * YSM_RES_PMAX;
+    for (int i = tid; i < n; i += T) dst[i] = make_double2(s_px[i], s_py[i]);
+  }
 }
 
 // ---- phase B: the tiles this CTA owns ------------------------------------------------------------------
 __device__ __forceinline__ void
-res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_tile, int* s_cnt, uint32_t* s_steps, int* s_fail) {
+res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int maxt, int cand, int* s_tile, int* s_cnt,
+            uint32_t* s_steps, int* s_fail, const uint32_t (&c_first)[4]) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int h = g.half_kernel;
@@ -292,7 +350,7 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int i = i0 + k * T + tid;
-      c[k] = i < total ? __ldcg(A.cells + i) : YSM_INVALID_CELL;
+      c[k] = i >= total ? YSM_INVALID_CELL : (i0 == 0 ? c_first[k] : __ldcg(A.cells + i));  // (first round: preloaded)
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -306,12 +364,12 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_
           const unsigned hsh = res_tile_hash(t);
           if ((int)((hsh >> 12) % (unsigned)G) != bid) continue;
           bool placed = false;
-          for (int probe = 0; probe < YSM_RES_MAXT && !placed; probe++) {
-            const int sl = (int)((hsh >> 27) + (unsigned)probe) & (YSM_RES_MAXT - 1);
+          for (int probe = 0; probe < maxt && !placed; probe++) {
+            const int sl = (int)((hsh >> 27) + (unsigned)probe) & (maxt - 1);
             const int old = atomicCAS(&s_tile[sl], -1, t);
             if (old == -1 || old == t) {
               const int k2 = atomicAdd(&s_cnt[sl], 1);
-              if (k2 < YSM_RES_CAND) s_steps[sl * YSM_RES_CAND + k2] = stamp_step(c[k], h, g.K, g.Wt, tx * YSM_TILE, ty * YSM_TILE);
+              if (k2 < cand) s_steps[sl * cand + k2] = stamp_step(c[k], h, g.K, g.Wt, tx * YSM_TILE, ty * YSM_TILE);
               else *s_fail = 1;
               placed = true;
             }
@@ -324,8 +382,8 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int* s_
 
 // stamps the owned tiles (up to 8 warps share a tile) and writes each once
 __device__ __forceinline__ void
-res_stamp(const GridC& g, const ResArgs& A, const int* s_tile, const int* s_cnt, const uint32_t* s_steps, int* s_slots,
-          int* s_nt, uint32_t* s_stage, uint32_t lane_tab_s) {
+res_stamp(const GridC& g, const ResArgs& A, int cand, const int* s_tile, const int* s_cnt, const uint32_t* s_steps,
+          int* s_slots, int* s_nt, uint32_t* s_stage, uint32_t lane_tab_s) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   if (warp == 0) {
@@ -343,13 +401,13 @@ res_stamp(const GridC& g, const ResArgs& A, const int* s_tile, const int* s_cnt,
   int slot = 0;
   if (active) {
     slot = s_slots[ti];
-    const int cnt = min(s_cnt[slot], YSM_RES_CAND);
+    const int cnt = min(s_cnt[slot], cand);
     const int per = (cnt + S - 1) / S;
     const int lo = min(cnt, part * per), hi = min(cnt, lo + per);
     uint32_t t[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) t[k] = 0u;
-    tile_scatter_rows(t, s_steps + slot * YSM_RES_CAND + lo, hi - lo, lane_tab_s, g.K);
+    tile_scatter_rows(t, s_steps + slot * cand + lo, hi - lo, lane_tab_s, g.K);
     uint32_t b[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) b[k] = __byte_perm(t[2 * k], t[2 * k + 1], 0x6420);  // u16 lanes -> bytes
@@ -395,7 +453,8 @@ __device__ __forceinline__ void res_clear(const GridC& g, const ResArgs& A, cons
 // ---- phase C: coarse sweep of one (angle, task chunk) ---------------------------------------------------
 // prep: lookup offsets of angle a (ComputeOffsets fused), lattice columns / rows -> shared memory
 __device__ __forceinline__ void
-res_sweep_prep(const GridC& g, const ResReq& rq, const ResArgs& A, int a, int* s_i, int* s_minmax) {
+res_sweep_prep(const GridC& g, const ResReq& rq, const ResArgs& A, int a, int* s_i, int* s_minmax, const double2* s_qp,
+               int n_qp) {
   const PassDev& ps = rq.coarse;
   const TableDev& tb = rq.ctab;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -412,7 +471,7 @@ res_sweep_prep(const GridC& g, const ResReq& rq, const ResArgs& A, int a, int* s
   const double cosine = rq.trig4[a][0], sine = rq.trig4[a][1];
   int mn = 0x7fffffff, mx = (int)0x80000000;
   for (int p = tid; p < ps.P; p += T) {
-    const double2 w = __ldcg(reinterpret_cast<const double2*>(A.qpts) + p);
+    const double2 w = p < n_qp ? s_qp[p] : __ldcg(reinterpret_cast<const double2*>(A.qpts) + p);
     int gx, gy;
     offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
     const int o = gx + gy * g.stride;
@@ -538,19 +597,30 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
   }
   if (lane == 0) s_wmax[warp] = wmax;
   __syncthreads();
-  if (tid == 0) {
-    double m = s_wmax[0];
-    for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
-    atomicMax(reinterpret_cast<unsigned long long*>(A.passmax), (unsigned long long)__double_as_longlong(m));
+  if (warp == 0) {
+    double m = lane < nwarps ? s_wmax[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(0xffffffffu, m, o);
+      m = t > m ? t : m;
+    }
+    if (lane == 0 && m > 0.0)
+      atomicMax(reinterpret_cast<unsigned long long*>(A.passmax), (unsigned long long)__double_as_longlong(m));
   }
   return true;
+}
+
+// The tail runs on a TEAM of a few warps of CTA 0 (named barrier 1): its steps are tiny, and every warp that
+// merely walks through them costs issue slots and barrier time.
+__device__ __forceinline__ void res_team_sync(int team_threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(team_threads) : "memory");
 }
 
 // ---- tail (CTA 0) -----------------------------------------------------------------------------------------
 struct ResTail {
   int list[YSM_RES_TIECAP];
   int sorted[YSM_RES_TIECAP];
-  int count, n, first, status;
+  int count, n, first, status, has_fine, stop;
+  unsigned hi3;
   double acc[4];
   double tmp4[32][4];
   PassOut po[2];
@@ -561,11 +631,11 @@ struct ResTail {
 // L2 round trips): round 1 = best response + the per-cell maxima (kept in registers for A.9), round 2 = the
 // responses of the few cells that can hold a tied pose; ties in storage order, sequential sums.
 // Returns false when a list overflows (the host takes the general path).
-#define YSM_RES_CELLS_PT 4   // lattice cells a thread keeps in registers (more: re-read)
+#define YSM_RES_CELLS_PT 6   // lattice cells a thread keeps in registers (more: re-read)
 __device__ __forceinline__ bool
-res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
+res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S, int T) {
   const PassDev& ps = rq.coarse;
-  const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int ncell = ps.nX * ps.nY;
   if (tid == 0) { S.count = 0; S.n = 0; }
   double cm[YSM_RES_CELLS_PT];
@@ -575,7 +645,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
     cm[k] = c < ncell ? __longlong_as_double((long long)__ldcg(A.cellmax + c)) : -1.0;
   }
   const double best = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(A.passmax)));
-  __syncthreads();
+  res_team_sync(T);
   // cells whose maximum is within the tie tolerance of the best (S.sorted doubles as the cell list)
 #pragma unroll
   for (int k = 0; k < YSM_RES_CELLS_PT; k++) {
@@ -591,7 +661,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
       if (pos < YSM_RES_TIECAP) S.sorted[pos] = c;
     }
   }
-  __syncthreads();
+  res_team_sync(T);
   const int ncand = S.n;
   if (ncand > YSM_RES_TIECAP) return false;
   for (int it = tid; it < ncand * ps.nA; it += T) {
@@ -603,7 +673,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
       if (pos < YSM_RES_TIECAP) S.list[pos] = c * ps.nA + a;
     }
   }
-  __syncthreads();
+  res_team_sync(T);
   const int nt = S.count;
   if (nt > YSM_RES_TIECAP) return false;
   const double startX = -ps.offx, startY = -ps.offy;
@@ -613,7 +683,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
     for (int k = 0; k < nt; k++) rank += (S.list[k] < v);
     S.sorted[rank] = v;
   }
-  __syncthreads();
+  res_team_sync(T);
   if (tid == 0) {
     double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
     for (int e = 0; e < nt; e++) {
@@ -629,14 +699,18 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
     const double cnt = (double)nt;
     PassOut& po = S.po[0];
     po.best = best;
-    po.avg_x = nt > 0 ? sx / cnt : 0.0;
-    po.avg_y = nt > 0 ? sy / cnt : 0.0;
-    po.tx = nt > 0 ? tx / cnt : 0.0;
-    po.ty = nt > 0 ? ty / cnt : 0.0;
+    if (nt == 1) {  // (x / 1.0 == x: skip four f64 divisions on the usual path)
+      po.avg_x = sx; po.avg_y = sy; po.tx = tx; po.ty = ty;
+    } else {
+      po.avg_x = nt > 0 ? sx / cnt : 0.0;
+      po.avg_y = nt > 0 ? sy / cnt : 0.0;
+      po.tx = nt > 0 ? tx / cnt : 0.0;
+      po.ty = nt > 0 ? ty / cnt : 0.0;
+    }
     po.n_ties = nt;
     po.first_idx = nt > 0 ? S.sorted[0] : -1;
   }
-  __syncthreads();
+  res_team_sync(T);
   // ComputePositionalCovariance accumulators (A.9); probs(x, y) = max response over the angles
   double norm = 0.0, axx = 0.0, axy = 0.0, ayy = 0.0;
   if (!(best < YSM_KT_TOLERANCE)) {
@@ -667,7 +741,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
   if (lane == 0) {
     S.tmp4[tid >> 5][0] = norm; S.tmp4[tid >> 5][1] = axx; S.tmp4[tid >> 5][2] = axy; S.tmp4[tid >> 5][3] = ayy;
   }
-  __syncthreads();
+  res_team_sync(T);
   if (tid < 32) {
     const int nw = (int)(T >> 5);
     double v0 = lane < nw ? S.tmp4[lane][0] : 0.0, v1 = lane < nw ? S.tmp4[lane][1] : 0.0;
@@ -680,7 +754,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S) {
     }
     if (lane == 0) { S.po[0].norm = v0; S.po[0].axx = v1; S.po[0].axy = v2; S.po[0].ayy = v3; }
   }
-  __syncthreads();
+  res_team_sync(T);
   return true;
 }
 
@@ -716,10 +790,10 @@ res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsi
   offset_cell(ft, g.scale, pt.x, pt.y, cosine, sine, gx, gy);
   const int o = gx + gy * g.stride;
   const unsigned dsz = (unsigned)g.data_size;
-  for (int c0 = 0; c0 < nxy; c0 += 3) {
-    unsigned v[3];
+  for (int c0 = 0; c0 < nxy; c0 += 9) {  // (3 x 3 cells: one round of independent loads)
+    unsigned v[9];
 #pragma unroll
-    for (int u = 0; u < 3; u++) {
+    for (int u = 0; u < 9; u++) {
       unsigned idx = 0xFFFFFFFFu;
       if (c0 + u < nxy) {
         const int iy = (c0 + u) / f.nX, ix = (c0 + u) - iy * f.nX;
@@ -732,7 +806,7 @@ res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsi
       v[u] = (valid && idx < dsz) ? (unsigned)A.grid[idx] : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < 3; u++) {
+    for (int u = 0; u < 9; u++) {
       const unsigned r = __reduce_add_sync(0xffffffffu, v[u]);
       if (lane == 0 && c0 + u < nxy && r) atomicAdd(A.fsum + (c0 + u) * nAf + a, r);
     }
@@ -743,8 +817,8 @@ res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsi
 // s_fsum: the sums copied to shared memory; s_ft: [nAf][4] trig rows of the winning angle.
 __device__ __forceinline__ bool
 res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& f, const double* s_ft, const unsigned* s_fsum,
-                double* s_fr) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = blockDim.x, nwarps = T >> 5;
+                double* s_fr, int T) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
   const int nAf = f.nA, nxy = f.nX * f.nY, nposes = nxy * nAf;
   double* s_dp = &S.tmp4[0][0];   // [nxy] distance penalty of cell c   (nxy <= 64)
   double* s_ap = &S.tmp4[16][0];  // [nAf] angle penalty of angle a     (nAf <= 64)
@@ -755,7 +829,7 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
   } else if (tid >= 64 && tid < 64 + nAf) {
     s_ap[tid - 64] = penalty_angle(f, pen, tid - 64);
   }
-  __syncthreads();
+  res_team_sync(T);
   double mx = 0.0;
   for (int pose = tid; pose < nposes; pose += T) {
     const int c = pose / nAf, a = pose - c * nAf;
@@ -767,9 +841,9 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
     const double t = __shfl_xor_sync(0xffffffffu, mx, o);
     mx = t > mx ? t : mx;
   }
-  __syncthreads();  // (s_dp / s_ap were read above: tmp4 is reused for the maxima)
+  res_team_sync(T);  // (s_dp / s_ap were read above: tmp4 is reused for the maxima)
   if (lane == 0) S.tmp4[warp][0] = mx;
-  __syncthreads();
+  res_team_sync(T);
   double best = 0.0;
   for (int w = 0; w < nwarps; w++) best = S.tmp4[w][0] > best ? S.tmp4[w][0] : best;
   // ties (few): collected in any order, then rank-sorted into storage order
@@ -778,7 +852,7 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
       const int pos = atomicAdd(&S.count, 1);
       if (pos < YSM_RES_TIECAP) S.sorted[pos] = i;
     }
-  __syncthreads();
+  res_team_sync(T);
   const int nt = S.count;
   if (nt > YSM_RES_TIECAP) return false;
   for (int e = tid; e < nt; e += T) {
@@ -787,7 +861,7 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
     for (int k = 0; k < nt; k++) rank += (S.sorted[k] < v);
     S.list[rank] = v;
   }
-  __syncthreads();
+  res_team_sync(T);
   if (tid == 0) {
     const double startX = -f.offx, startY = -f.offy;
     double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
@@ -804,16 +878,20 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
     const double cnt = (double)nt;
     PassOut& po = S.po[1];
     po.best = best;
-    po.avg_x = nt > 0 ? sx / cnt : 0.0;
-    po.avg_y = nt > 0 ? sy / cnt : 0.0;
-    po.tx = nt > 0 ? tx / cnt : 0.0;
-    po.ty = nt > 0 ? ty / cnt : 0.0;
+    if (nt == 1) {
+      po.avg_x = sx; po.avg_y = sy; po.tx = tx; po.ty = ty;
+    } else {
+      po.avg_x = nt > 0 ? sx / cnt : 0.0;
+      po.avg_y = nt > 0 ? sy / cnt : 0.0;
+      po.tx = nt > 0 ? tx / cnt : 0.0;
+      po.ty = nt > 0 ? ty / cnt : 0.0;
+    }
     po.norm = 0.0; po.axx = 0.0; po.axy = 0.0; po.ayy = 0.0;
     po.n_ties = nt;
     po.first_idx = nt > 0 ? S.list[0] : -1;
     S.first = -1;
   }
-  __syncthreads();
+  res_team_sync(T);
   // ComputeAngularCovariance sums: un-penalised GetResponse at the best cell for every fine angle. The best
   // cell is one of the lattice cells whenever the mean rounds onto one (else: general path).
   if (nt > 0) {
@@ -827,14 +905,14 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
       const int cy = world_to_grid1(f.cy + y, f.goy, g.scale) + g.border;
       if (cx == gx && cy == gy) atomicMax(&S.first, tid);
     }
-    __syncthreads();
+    res_team_sync(T);
     const int cell = S.first;
     if (cell < 0) return false;
     for (int a = tid; a < nAf; a += T) S.angs[a] = (int)s_fsum[cell * nAf + a];
   } else {
     for (int a = tid; a < nAf; a += T) S.angs[a] = 0;
   }
-  __syncthreads();
+  res_team_sync(T);
   return true;
 }
 
@@ -869,11 +947,11 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
   __shared__ int s_nt, s_cmd, s_fail;
   __shared__ int s_io[2];
   __shared__ uint4 s_db;
+  __shared__ __align__(8) unsigned s_line[12];  // this poller's scan: count, source slot, slot to fill, pad, m fields
   __shared__ int s_minmax[8];
   __shared__ __align__(8) int s_misc[16];
   __shared__ double s_wmax[32];
   __shared__ unsigned long long s_ts[YSM_RES_TS];
-  __shared__ unsigned long long s_win;
   __shared__ unsigned long long s_pf[YSM_RES_PROF];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = blockDim.x;
   const int G = (int)gridDim.x, bid = (int)blockIdx.x;
@@ -911,9 +989,19 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       if (tid == 0) {
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
         int c = RES_CMD_NONE;
+        const unsigned char* line = reinterpret_cast<const unsigned char*>(A.db) + (size_t)bid * YSM_RES_DB_STRIDE;
         for (unsigned spins = 1u;; spins++) {
-          d = res_ld_volatile_v4(reinterpret_cast<const unsigned char*>(A.db) + (size_t)bid * YSM_RES_DB_STRIDE);
-          if (d.x != seq_done) { c = (int)(d.y & 0xFFu); break; }
+          // the five tagged words of this CTA's line in ONE round of PCIe reads
+          d = res_ld_volatile_v4(line);
+          const uint4 d1 = res_ld_volatile_v4(line + 16), d2 = res_ld_volatile_v4(line + 32);
+          const uint4 d3 = res_ld_volatile_v4(line + 48), d4 = res_ld_volatile_v4(line + 64);
+          if (d.x != seq_done && d1.x == d.x && d2.w == d.x && d3.w == d.x && d4.w == d.x) {
+            c = (int)(d.y & 0x7Fu);
+            s_line[0] = d1.y; s_line[1] = d1.z; s_line[2] = d1.w;
+            s_line[4] = d2.x; s_line[5] = d2.y; s_line[6] = d2.z; s_line[7] = d3.x;
+            s_line[8] = d3.y; s_line[9] = d3.z; s_line[10] = d4.x; s_line[11] = d4.y;
+            break;
+          }
           if (bid == 0) {
             if ((spins & 7u) == 0u && res_timer() - idle0 > A.idle_ns) {
               c = RES_CMD_QUIT;
@@ -931,7 +1019,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       __syncthreads();
       cmd = s_cmd;
     }
-    if (bid == 0 && tid == 0) s_ts[0] = res_timer();
+    if (bid == 0 && tid == 0) { s_ts[0] = res_timer(); s_ts[20] = (unsigned long long)clock64(); }
     if (threadIdx.x == 0) pf[8] = res_timer();
     if (poller && cmd == RES_CMD_MATCH) {
       const uint4 d = s_db;
@@ -943,14 +1031,34 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         uint4* dst = reinterpret_cast<uint4*>(A.ctl);
         for (int i = tid; i < nvec; i += T) dst[i] = __ldcv(src + i);
       } else {
+        const double* mf = reinterpret_cast<const double*>(s_line + 4);  // viewpoint x, y, grid offset x, y
         for (int s = bid - 1; s <= nbase; s += YSM_RES_POLLERS) {
+          // the poller's own line describes its first scan; a second round (more than 16 scans) asks the
+          // control block in host memory
+          int cnt = (int)s_line[0], src_slot = (int)s_line[1], store_slot = (int)s_line[2];
+          if (s != bid - 1) {
+            if (tid == 0) s_misc[8] = (int)__ldcv(&hreq->counts[s]);
+            __syncthreads();
+            cnt = s_misc[8];
+            src_slot = store_slot = 0;
+          }
           if (s < nbase) {
-            res_filter_scan(g, A, hreq, s, pstride, dyn, s_misc, pf);
+            res_filter_scan(g, A, s, pstride, cnt, src_slot, store_slot, mf, dyn, pf);
           } else {
             const int Pq = (int)(d.z & 0xFFFFu);
-            const double2* src = reinterpret_cast<const double2*>(A.pts + 2 * (size_t)s * pstride);
             double2* dst = reinterpret_cast<double2*>(A.qpts);
-            for (int i = tid; i < Pq; i += T) dst[i] = __ldcv(src + i);
+            if (src_slot > 0) {
+              const double2* src = reinterpret_cast<const double2*>(A.cache) + (size_t)(src_slot - 1) * YSM_RES_PMAX;
+              for (int i = tid; i < Pq; i += T) dst[i] = __ldcg(src + i);
+            } else {
+              const double2* src = reinterpret_cast<const double2*>(A.pts + 2 * (size_t)s * pstride);
+              double2* keep = store_slot > 0 ? reinterpret_cast<double2*>(A.cache) + (size_t)(store_slot - 1) * YSM_RES_PMAX : nullptr;
+              for (int i = tid; i < Pq; i += T) {
+                const double2 w = __ldcv(src + i);
+                dst[i] = w;
+                if (keep) keep[i] = w;
+              }
+            }
           }
           __syncthreads();
         }
@@ -971,13 +1079,20 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
     t1 += (unsigned)G;
     if (!res_barrier(bar1, t1, false, A.abort_flag, s_io, A.stall_ns)) { exit_code = 2; break; }
     RES_TS(2)
-    // control block -> shared memory in ONE round of loads: header, descriptors and the first 32 trig rows
-    // (the usual 21 search angles)
+    // ONE round of loads after the barrier: the control block (header, descriptors, the first 32 trig rows = the
+    // usual 21 search angles) -> shared memory; speculatively, the first 1024 query points -> shared memory and
+    // the first 4096 cell entries -> registers (how many are real is only known once the header is here)
+    double2* s_qp = reinterpret_cast<double2*>(dyn + A.o_off);  // [T] query points (CTA 0: the tail's s_q)
+    int* s_offs = reinterpret_cast<int*>(dyn + A.o_off + 16 * (size_t)YSM_RES_THREADS);
+    uint32_t c_first[4];
     {
       const int hdr4 = (int)(offsetof(ResReq, trig4) / 16);
       const uint4* src = reinterpret_cast<const uint4*>(A.ctl);
       uint4* dst = reinterpret_cast<uint4*>(&s_rq);
       for (int i = tid; i < hdr4 + 64; i += T) dst[i] = __ldcg(src + i);
+      s_qp[tid] = __ldcg(reinterpret_cast<const double2*>(A.qpts) + tid);
+#pragma unroll
+      for (int k = 0; k < 4; k++) c_first[k] = __ldcg(A.cells + tid + k * T);
       __syncthreads();
     }
     const unsigned seq = s_rq.seq;
@@ -1001,8 +1116,29 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
     const PassDev& ps = rq.coarse;
     const int nv = rq.nA * rq.task_chunks;
     int v = bid - 1;
-    // lookup offsets of this CTA's first angle (they do not depend on the grid): before the stamping
-    if (worker && v < nv) res_sweep_prep(g, rq, A, v % rq.nA, reinterpret_cast<int*>(dyn + A.o_off), s_minmax);
+    if (bid == 0 && ps.P > (int)T) {
+      // the tail needs all query points in shared memory (s_q = s_qp, CTA 0 has room for P of them)
+      for (int i = T + tid; i < ps.P; i += T) s_qp[i] = __ldcg(reinterpret_cast<const double2*>(A.qpts) + i);
+    }
+    if (threadIdx.x == 0) pf[1] = res_timer();
+    // ---- phase B: stamp the tiles this CTA owns -------------------------------------------------------
+    {
+      const int total = min(rq.nbase * rq.pstride, A.cells_cap);
+      uint32_t* s_steps = reinterpret_cast<uint32_t*>(dyn);
+      uint32_t* s_stage = s_steps + YSM_RES_MAXT * YSM_RES_CAND;
+      res_collect(g, A, total, G, bid, rq.maxt, rq.cand, s_tile, s_cnt, s_steps, &s_fail, c_first);
+      __syncthreads();
+      if (threadIdx.x == 0) pf[2] = res_timer();
+      res_stamp(g, A, rq.cand, s_tile, s_cnt, s_steps, s_slots, &s_nt, s_stage, lane_tab_s);
+    }
+    if (threadIdx.x == 0) pf[3] = res_timer();
+    RES_TS(3)
+    // ---- barrier 2, split: arrive, do what does not depend on the grid, then wait -----------------
+    t2 += (unsigned)G;
+    __syncthreads();
+    if (tid == 0) res_arrive(bar2, s_fail != 0);
+    // lookup offsets of this CTA's first angle
+    if (worker && v < nv) res_sweep_prep(g, rq, A, v % rq.nA, s_offs, s_minmax, s_qp, (int)T);
     // the fine pass's items of this CTA (fine angle x 32 query points; warp w takes item bid - 1 + w (G - 1)):
     // the points wait in registers
     const int fine_chunks = (ps.P + 31) >> 5, fine_items = rq.do_refine ? rq.nAf * fine_chunks : 0;
@@ -1013,40 +1149,30 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
     if (have_item) {
       const int p = (my_item / rq.nAf) * 32 + lane;
       my_valid = p < ps.P;
-      if (my_valid) my_pt = __ldcg(reinterpret_cast<const double2*>(A.qpts) + p);
+      if (my_valid) my_pt = p < (int)T ? s_qp[p] : __ldcg(reinterpret_cast<const double2*>(A.qpts) + p);
     }
-    if (threadIdx.x == 0) pf[1] = res_timer();
-    // ---- phase B: stamp the tiles this CTA owns -------------------------------------------------------
-    {
-      const int total = min(rq.nbase * rq.pstride, A.cells_cap);
-      uint32_t* s_steps = reinterpret_cast<uint32_t*>(dyn);
-      uint32_t* s_stage = s_steps + YSM_RES_MAXT * YSM_RES_CAND;
-      res_collect(g, A, total, G, bid, s_tile, s_cnt, s_steps, &s_fail);
-      __syncthreads();
-      if (threadIdx.x == 0) pf[2] = res_timer();
-      res_stamp(g, A, s_tile, s_cnt, s_steps, s_slots, &s_nt, s_stage, lane_tab_s);
+    if (tid == 0) {
+      unsigned hi = 0u;
+      s_io[0] = res_wait(bar2, t2, &hi, A.abort_flag, A.stall_ns) ? 1 : 0;
+      s_io[1] = (int)hi;
+      s_fail = 0;
     }
-    if (threadIdx.x == 0) pf[3] = res_timer();
-    RES_TS(3)
-    t2 += (unsigned)G;
-    if (!res_barrier(bar2, t2, s_fail != 0, A.abort_flag, s_io, A.stall_ns)) { exit_code = 2; break; }
+    __syncthreads();
+    if (!s_io[0]) { exit_code = 2; break; }
     RES_TS(4)
     if (threadIdx.x == 0) pf[4] = res_timer();
     const bool failed = (unsigned)s_io[1] != fails2;  // some CTA overflowed its tile lists
     fails2 = (unsigned)s_io[1];
-    __syncthreads();
-    if (tid == 0) s_fail = 0;
-    __syncthreads();
     // ---- phase C: coarse sweep ------------------------------------------------------------------------------
     if (worker && !failed) {
       bool first = true;
       for (; v < nv; v += G - 1) {
         if (!first) {
           __syncthreads();
-          res_sweep_prep(g, rq, A, v % rq.nA, reinterpret_cast<int*>(dyn + A.o_off), s_minmax);
+          res_sweep_prep(g, rq, A, v % rq.nA, s_offs, s_minmax, s_qp, (int)T);
         }
         first = false;
-        if (!res_sweep_run(g, pen, rq, A, v % rq.nA, v / rq.nA, reinterpret_cast<const int*>(dyn + A.o_off), s_minmax,
+        if (!res_sweep_run(g, pen, rq, A, v % rq.nA, v / rq.nA, s_offs, s_minmax,
                            reinterpret_cast<unsigned*>(dyn), s_wmax) && tid == 0)
           s_fail = 1;
       }
@@ -1058,13 +1184,12 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         res_arrive(bar_sweep, s_fail != 0);
         s_fail = 0;
       }
-      // ---- fine pass items: wait for the winner, sum, arrive ---------------------------------------
-      if (rq.do_refine) {
-        if (tid == 0) {
-          unsigned long long w = 0ull;
+      // ---- fine pass items: every warp that holds one waits for the winner, sums, arrives on its own -----
+      if (have_item) {
+        unsigned long long w = 0ull;
+        if (lane == 0) {
           unsigned spins = 0u;
           unsigned long long t0 = 0ull;
-          int ok = 1;
           for (;;) {
             w = res_ld_acquire64(A.win);
             if ((unsigned)(w >> 32) == seq) break;
@@ -1072,18 +1197,18 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
               const unsigned long long now = res_timer();
               if (t0 == 0ull) t0 = now;
               if (now - t0 > A.stall_ns) atomicExch(A.abort_flag, 1);
-              if (res_ld_acquire(reinterpret_cast<const unsigned*>(A.abort_flag)) != 0u) { ok = 0; break; }
+              if (res_ld_acquire(reinterpret_cast<const unsigned*>(A.abort_flag)) != 0u) {
+                w = ((unsigned long long)seq << 32) | YSM_RES_WIN_NOFINE;  // (barrier 3 ends the kernel)
+                break;
+              }
             }
           }
-          s_win = w;
-          s_io[0] = ok;
         }
-        __syncthreads();
-        if (!s_io[0]) { exit_code = 2; break; }
-        const unsigned winw = (unsigned)s_win;
-        if (winw != YSM_RES_WIN_NOFINE && have_item) res_fine_item(g, rq, A, my_item, winw, my_pt, my_valid);
-        __syncthreads();
-        if (tid == 0) res_arrive(bar_fine, false);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        const unsigned winw = (unsigned)w;
+        if (winw != YSM_RES_WIN_NOFINE) res_fine_item(g, rq, A, my_item, winw, my_pt, my_valid);
+        __syncwarp();
+        if (lane == 0) res_arrive(bar_fine, false);
       }
     }
     if (bid == 0) {
@@ -1115,66 +1240,79 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
           }
         }
       }
-      RES_TS(5)
-      t3 += (unsigned)(G - 1);
-      if (tid == 0) {
-        unsigned hi = 0u;
-        s_io[0] = res_wait(bar_sweep, t3, &hi, A.abort_flag, A.stall_ns) ? 1 : 0;
-        s_io[1] = (int)hi;
-      }
       __syncthreads();
-      if (!s_io[0]) { exit_code = 2; break; }
-      if ((unsigned)s_io[1] != fails3) status = RES_ST_FALLBACK;  // (a sweep CTA met a window that can leave the grid)
-      fails3 = (unsigned)s_io[1];
-      RES_TS(6)
-      if (status == RES_ST_OK) {
-        if (!res_reduce_coarse(rq, A, s_tail)) status = RES_ST_FALLBACK;
-      }
-      RES_TS(7)
-      if (rq.do_refine) {
-        // MatchScan goes straight to the fine pass when the coarse pass has ONE winner with a non-zero
-        // response: its centre is the winning lattice pose, the heading the atan2(sin, cos) the host tabulated
-        // for that coarse angle. Otherwise the host reschedules the match (ties, response expansion).
-        const PassOut& po = s_tail.po[0];
-        const bool go = status == RES_ST_OK && po.n_ties == 1 && po.best > YSM_KT_TOLERANCE;
-        const int a = go ? po.first_idx % ps.nA : 0;
-        const int cell = go ? po.first_idx / ps.nA : 0;
-        const int wiy = cell / ps.nX, wix = cell - wiy * ps.nX;
-        if (!go) status = RES_ST_FALLBACK;
-        if (tid == 0) {
-          const unsigned winw = go ? ((unsigned)a | ((unsigned)wix << 8) | ((unsigned)wiy << 20)) : YSM_RES_WIN_NOFINE;
-          res_st_release64(A.win, ((unsigned long long)seq << 32) | winw);
-          PassDev& f = s_rq.fine;
-          f.cx = po.avg_x;
-          f.cy = po.avg_y;
-          f.ch = s_spec[a];
-        }
-        RES_TS(9)
-        t4 += (unsigned)(G - 1);
+      RES_TS(5)
+      // ---- the tail proper: a team of a few warps (named barrier), the other warps wait below ----------
+      const int TT = min((int)T, max(128, rq.tail_warps * 32));
+      t3 += (unsigned)(G - 1);
+      if (rq.do_refine) t4 += (unsigned)fine_items;
+      if (tid == 0) { s_tail.status = status; s_tail.has_fine = 0; s_tail.stop = 0; }
+      if (tid < TT) {
         if (tid == 0) {
           unsigned hi = 0u;
-          s_io[0] = res_wait(bar_fine, t4, &hi, A.abort_flag, A.stall_ns) ? 1 : 0;
+          if (!res_wait(bar_sweep, t3, &hi, A.abort_flag, A.stall_ns)) s_tail.stop = 1;
+          s_tail.hi3 = hi;
+          if (hi != fails3) s_tail.status = RES_ST_FALLBACK;  // (a sweep CTA met a window that can leave the grid)
         }
-        __syncthreads();
-        if (!s_io[0]) { exit_code = 2; break; }
-        RES_TS(10)
-        if (go) {
-          const PassDev& f = s_rq.fine;
-          const int nposes = f.nX * f.nY * f.nA;
-          unsigned* s_fsum = reinterpret_cast<unsigned*>(dyn + A.o_off + rq.o_fsum);
-          double* s_fr = reinterpret_cast<double*>(s_fsum + ((nposes + 1) & ~1));
-          for (int i = tid; i < nposes; i += T) {
-            s_fsum[i] = __ldcg(A.fsum + i);
-            A.fsum[i] = 0u;  // (for the next request)
+        res_team_sync(TT);
+        RES_TS(6)
+        bool stop = s_tail.stop != 0;
+        if (!stop && s_tail.status == RES_ST_OK) {
+          if (!res_reduce_coarse(rq, A, s_tail, TT) && tid == 0) s_tail.status = RES_ST_FALLBACK;
+          res_team_sync(TT);
+        }
+        RES_TS(7)
+        if (!stop && rq.do_refine) {
+          // MatchScan goes straight to the fine pass when the coarse pass has ONE winner with a non-zero
+          // response: its centre is the winning lattice pose, the heading the atan2(sin, cos) the host tabulated
+          // for that coarse angle. Otherwise the host reschedules the match (ties, response expansion).
+          const PassOut& po = s_tail.po[0];
+          const bool go = s_tail.status == RES_ST_OK && po.n_ties == 1 && po.best > YSM_KT_TOLERANCE;
+          const int a = go ? po.first_idx % ps.nA : 0;
+          const int cell = go ? po.first_idx / ps.nA : 0;
+          const int wiy = cell / ps.nX, wix = cell - wiy * ps.nX;
+          res_team_sync(TT);  // (status was read by everyone)
+          if (tid == 0) {
+            const unsigned winw = go ? ((unsigned)a | ((unsigned)wix << 8) | ((unsigned)wiy << 20)) : YSM_RES_WIN_NOFINE;
+            res_st_release64(A.win, ((unsigned long long)seq << 32) | winw);
+            if (!go) s_tail.status = RES_ST_FALLBACK;
+            PassDev& f = s_rq.fine;
+            f.cx = po.avg_x;
+            f.cy = po.avg_y;
+            f.ch = s_spec[a];
+            RES_TS(9)
+            unsigned hi = 0u;
+            if (!res_wait(bar_fine, t4, &hi, A.abort_flag, A.stall_ns)) s_tail.stop = 1;
           }
-          __syncthreads();
-          const double* s_ft = s_spec + rq.nA + (size_t)4 * a * rq.nAf;
-          if (res_fine_finish(g, pen, s_tail, f, s_ft, s_fsum, s_fr)) has_fine = 1;
-          else status = RES_ST_FALLBACK;
+          res_team_sync(TT);
+          RES_TS(10)
+          stop = s_tail.stop != 0;
+          if (go && !stop) {
+            const PassDev& f = s_rq.fine;
+            const int nposes = f.nX * f.nY * f.nA;
+            unsigned* s_fsum = reinterpret_cast<unsigned*>(dyn + A.o_off + rq.o_fsum);
+            double* s_fr = reinterpret_cast<double*>(s_fsum + ((nposes + 1) & ~1));
+            for (int i = tid; i < nposes; i += TT) {
+              s_fsum[i] = __ldcg(A.fsum + i);
+              A.fsum[i] = 0u;  // (for the next request)
+            }
+            res_team_sync(TT);
+            const double* s_ft = s_spec + rq.nA + (size_t)4 * a * rq.nAf;
+            const bool ok = res_fine_finish(g, pen, s_tail, f, s_ft, s_fsum, s_fr, TT);
+            if (tid == 0) {
+              if (ok) s_tail.has_fine = 1;
+              else s_tail.status = RES_ST_FALLBACK;
+            }
+          }
         }
+        RES_TS(8)
+        if (tid == 0) s_ts[21] = (unsigned long long)clock64();
       }
-      RES_TS(8)
       __syncthreads();
+      fails3 = s_tail.hi3;
+      if (s_tail.stop) { exit_code = 2; break; }
+      status = s_tail.status;
+      has_fine = s_tail.has_fine;
       res_publish(A, s_tail, seq, status, has_fine, rq.nAf, rq.trace ? s_ts : nullptr);
       // reset the per-request accumulators for the next request
       const int ncell = ps.nX * ps.nY;

@@ -17,6 +17,14 @@ from . import _capi
 from .matcher import _ERRORS, DEFAULTS, ScanMatcherB200, pack_pool
 
 
+_tag_counter = [0]
+
+
+def _next_tag():
+    _tag_counter[0] += 1
+    return _tag_counter[0]
+
+
 class Pose2(object):
     """karto Pose2(x, y, yaw) (reference serde.py:73, test.py:36)."""
 
@@ -58,6 +66,7 @@ class LocalizedRangeScan(object):
         self.num = num
         self.time = time
         self._points = None
+        self._tag = 0
 
     @property
     def odom_pose(self):
@@ -85,7 +94,13 @@ class LocalizedRangeScan(object):
             c, p = self.config, self._corrected_pose
             self._points = _capi.point_readings(self.ranges, c.min_angle, c.angular_resolution, c.min_range,
                                                 c.range_threshold, p.x, p.y, p.yaw)
+            self._tag = _next_tag()  # names this content (ysm_batch::scan_tag): a new pose makes new readings
         return self._points
+
+    def content_tag(self):
+        """Non-zero id of the current point readings: equal tags <=> same readings (device-resident scan store)."""
+        self.point_readings()
+        return self._tag
 
 
 class ScanMatcherConfig(object):
@@ -130,6 +145,8 @@ class Wrapper(object):
                                   max_grid_bytes=max_grid_bytes, lanes=1)
         self._mt = None
         self._one = {}  # single-query descriptors, keyed by base-set size
+        self._pool = None  # persistent staging pool of the single-query path (regions keyed by content tag)
+        self._region_used = [0] * self.POOL_REGIONS
 
     @property
     def matcher(self):
@@ -145,10 +162,14 @@ class Wrapper(object):
             self._mt = ScanMatcherB200(cfg, device=device, max_slots=max_slots, max_grid_bytes=max_grid_bytes)
         return self._mt
 
+    POOL_REGIONS, REGION_POINTS = 48, 4096  # persistent staging pool of the single-query path
+
     def match_scan(self, query, base_scans, penalty=True, do_fine=False):
         """Wrapper.match_scan(query, base_scans, penalty, do_fine) (reference scan_matching.py:41).
-        Single-query fast path: the descriptor arrays are cached per base-set size, only the
-        point readings are packed per call."""
+        Single-query fast path: the descriptor arrays are cached per base-set size; every scan's point readings
+        sit in a region of a persistent staging pool under their content tag, so the running scans of sequential
+        mapping (graph_slam.py:326) are packed -- and, through ysm_batch::scan_tag, uploaded -- once, not once
+        per match."""
         import ctypes as C
         nb = len(base_scans)
         c = self._one.get(nb)
@@ -157,32 +178,51 @@ class Wrapper(object):
             arr = dict(counts=np.zeros(nb + 1, np.int32), starts=np.zeros(nb + 1, np.int32),
                        qidx=np.zeros(1, np.int32), pose=np.zeros((1, 3), np.float64),
                        bptr=np.array([0, nb], np.int32), bidx=np.arange(1, nb + 1, dtype=np.int32),
-                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), pool=np.zeros((4096, 2), np.float64))
+                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), tags=np.zeros(nb + 1, np.uint64))
             arr["resf"] = arr["res"].view(np.float64).reshape(-1)  # the 128-B record as 16 doubles
             b.n_matches, b.n_scans = 1, nb + 1
             b.scan_start, b.scan_count = arr["starts"].ctypes.data, arr["counts"].ctypes.data
             b.query_scan, b.query_pose = arr["qidx"].ctypes.data, arr["pose"].ctypes.data
             b.base_ptr, b.base_idx = arr["bptr"].ctypes.data, (arr["bidx"].ctypes.data if nb else None)
             b.pool_on_device = 0
-            b.pool_xy = arr["pool"].ctypes.data
+            b.scan_tag = arr["tags"].ctypes.data
             c = self._one[nb] = (b, arr, C.byref(b), arr["res"].ctypes.data)
         b, arr, bref, resp = c
-        pts = [query.point_readings()]
-        pts.extend(s.point_readings() for s in base_scans)
-        counts, starts = arr["counts"], arr["starts"]
-        tot = 0
-        for i, p in enumerate(pts):
-            starts[i] = tot
-            counts[i] = len(p)
-            tot += len(p)
-        pool = arr["pool"]  # persistent staging buffer: its address is written to the descriptor once
-        if tot > len(pool):
-            pool = arr["pool"] = np.zeros((2 * tot, 2), np.float64)
-            b.pool_xy = pool.ctypes.data
-        if tot:
-            np.concatenate(pts, out=pool[:tot])
+        pool = self._pool
+        if pool is None:
+            pool = self._pool = np.zeros((self.POOL_REGIONS * self.REGION_POINTS, 2), np.float64)
+            self._region_of, self._region_tag, self._region_clock = {}, [0] * self.POOL_REGIONS, 0
+        counts, starts, tags = arr["counts"], arr["starts"], arr["tags"]
+        region_of, rp = self._region_of, self.REGION_POINTS
+        self._region_clock += 1
+        clock = self._region_clock
+        scans = [query]
+        scans.extend(base_scans)
+        if len(scans) > self.POOL_REGIONS:
+            return self._match_scan_unpooled(query, base_scans, penalty, do_fine)
+        used = self._region_used
+        for i, sc in enumerate(scans):
+            pts = sc.point_readings()
+            n = len(pts)
+            if n > rp:
+                return self._match_scan_unpooled(query, base_scans, penalty, do_fine)
+            tag = sc._tag
+            r = region_of.get(tag)
+            if r is None:
+                # a region no scan of this call sits in, least recently used first
+                r = min((k for k in range(self.POOL_REGIONS) if used[k] != clock), key=used.__getitem__)
+                region_of.pop(self._region_tag[r], None)
+                region_of[tag] = r
+                self._region_tag[r] = tag
+                if n:
+                    pool[r * rp:r * rp + n] = pts
+            used[r] = clock
+            starts[i] = r * rp
+            counts[i] = n
+            tags[i] = tag
         arr["pose"][0] = query.sensor_pose()
-        b.n_points = tot
+        b.pool_xy = pool.ctypes.data
+        b.n_points = len(pool)
         b.do_penalize, b.do_refine = (1 if penalty else 0), (1 if do_fine else 0)
         m = self._m
         rc = m._lib.ysm_match_batch(m._h, bref, resp, None)
@@ -190,6 +230,18 @@ class Wrapper(object):
             raise _ERRORS.get(rc, RuntimeError)(_capi.last_error(m._h))
         f = arr["resf"]
         return MatchResult(float(f[0]), f[4:13].reshape(3, 3).copy(), Pose2(f[1], f[2], f[3]))
+
+    def _match_scan_unpooled(self, query, base_scans, penalty, do_fine):
+        """Scans too many / too long for the staging pool: pack per call (no content tags)."""
+        pts = [query.point_readings()]
+        pts.extend(s.point_readings() for s in base_scans)
+        pool, starts, counts = pack_pool(pts)
+        nb = len(base_scans)
+        res = self._m.match_pool(pool, starts, counts, np.zeros(1, np.int32), np.array([query.sensor_pose()]),
+                                 np.array([0, nb], np.int32), np.arange(1, nb + 1, dtype=np.int32), penalty, do_fine)
+        r = res[0]
+        return MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
+                           Pose2(float(r["x"]), float(r["y"]), float(r["heading"])))
 
     def match_scan_batch(self, queries, base_sets, penalty=True, do_fine=False):
         """Independent (query, base set) matches in one launch sequence. Scans shared between

@@ -83,7 +83,8 @@ class ScanMatcherB200(object):
         self._lib.ysm_last_work(self._h, v, 16)
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
                          "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
-                         "speculative_fine_passes", "lanes", "latency_kernel_launches", "resident_requests"),
+                         "speculative_fine_passes", "lanes", "latency_kernel_launches", "resident_requests",
+                         "scan_store_hits"),
                         (int(x) for x in v)))
 
     def ping(self, n=1):
@@ -95,7 +96,7 @@ class ScanMatcherB200(object):
         return np.array(out[:], dtype=np.float64)
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
-                   penalty=True, do_fine=False, stream=0, out=None):
+                   penalty=True, do_fine=False, stream=0, out=None, scan_tag=None):
         """Batched Wrapper.match_scan over a pool of scans (see ysm_batch in include/ysm.h).
 
         pool_xy: (n_points, 2) float64 numpy array, or a CUDA tensor already resident in HBM.
@@ -134,6 +135,11 @@ class ScanMatcherB200(object):
         b.base_idx = base_idx.ctypes.data if len(base_idx) else None
         b.do_penalize = int(bool(penalty))
         b.do_refine = int(bool(do_fine))
+        if scan_tag is not None:  # content tags (ysm_batch::scan_tag): tagged scans stay resident on the device
+            scan_tag = np.ascontiguousarray(scan_tag, dtype=np.uint64)
+            if len(scan_tag) != len(scan_start):
+                raise ValueError("scan_tag must have one entry per scan")
+            b.scan_tag = scan_tag.ctypes.data
         if out is None:
             out = np.zeros(n, dtype=_capi.RESULT_DTYPE)
         elif (not isinstance(out, np.ndarray) or out.dtype != _capi.RESULT_DTYPE or out.ndim != 1 or len(out) < n
