@@ -121,6 +121,16 @@ int ysm_point_readings(const double *ranges, int32_t n, double min_angle,
                        double angular_resolution, double min_range, double range_threshold,
                        double x, double y, double heading, double *out_xy, int32_t *n_out);
 
+/* The same for a whole batch of scans in ONE call (host libm on all the host threads the process may use):
+ * scan i takes the range readings of source scan src[i] (ranges[beam_ptr[src[i]] .. beam_ptr[src[i] + 1]), all
+ * sources share one laser) at sensor pose pose[i]. The kept readings are written back to back: scan i owns
+ * out_xy[out_start[i] .. out_start[i] + out_count[i]). out_xy needs room for the sum of the source beam counts;
+ * *n_points receives the total written. */
+int ysm_point_readings_batch(const double *ranges, const int32_t *beam_ptr, int32_t n_src, const int32_t *src,
+                             const double *pose, int32_t n, double min_angle, double angular_resolution,
+                             double min_range, double range_threshold, double *out_xy, int32_t *out_start,
+                             int32_t *out_count, int64_t *n_points);
+
 /* Replaces yag_slam/raytracing.py:90-92 run_raytracing_sweep for n_starts start cells.
  * img: uint8 [h][w] (host, or device if img_on_device); angles in degrees (float64);
  * starts_xy [n_starts][2]; out (host) [n_starts][n_angles][5] float32 rows
@@ -256,7 +266,8 @@ int ysm_debug_ping(ysm_handle *h, int32_t n, double *rtt_us);
  * out[10] fine passes that ran chained on the device behind their coarse pass (latency path),
  * out[11] lanes used by the call, out[12] launches of the single-kernel latency path,
  * out[13] requests served by the resident latency kernel, out[14] scans it took from the device-resident
- * scan store instead of host memory;
+ * scan store instead of host memory, out[15] base points that survived FindValidPoints and the ROI test
+ * (P_valid; counted only with YSM_DEBUG_TIME_KERNELS);
  * fills out[0..n), n <= 16 */
 int ysm_last_work(const ysm_handle *h, int64_t *out, int32_t n);
 

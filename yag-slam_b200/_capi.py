@@ -65,7 +65,7 @@ assert RESULT_DTYPE.itemsize == 128
 
 EXPORTS = [
     "ysm_create", "ysm_create_map", "ysm_destroy", "ysm_last_error", "ysm_get_dims", "ysm_match_batch",
-    "ysm_point_readings", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
+    "ysm_point_readings", "ysm_point_readings_batch", "ysm_raytrace", "ysm_set_debug", "ysm_debug_copy_grid",
     "ysm_debug_copy_kernel", "ysm_debug_copy_offsets", "ysm_launch_count", "ysm_last_kernel_ms", "ysm_last_work",
     "ysm_debug_ping",
     "ysm_occ_create", "ysm_occ_destroy", "ysm_occ_get_info", "ysm_occ_copy_image", "ysm_occ_copy_counts",
@@ -101,6 +101,8 @@ def lib():
     L.ysm_match_batch.argtypes = [vp, C.POINTER(YsmBatch), vp, vp]
     L.ysm_point_readings.restype = C.c_int
     L.ysm_point_readings.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, f64, vp, C.POINTER(i32)]
+    L.ysm_point_readings_batch.restype = C.c_int
+    L.ysm_point_readings_batch.argtypes = [vp, vp, i32, vp, vp, i32, f64, f64, f64, f64, vp, vp, vp, C.POINTER(C.c_int64)]
     L.ysm_raytrace.restype = C.c_int
     L.ysm_raytrace.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, C.c_int, vp]
     L.ysm_set_debug.restype = C.c_int
@@ -163,3 +165,26 @@ def point_readings(ranges, min_angle, angular_resolution, min_range, range_thres
     if rc != YSM_OK:
         raise RuntimeError("ysm_point_readings failed (%d)" % rc)
     return out[:n.value].copy()
+
+
+def point_readings_batch(ranges, beam_ptr, src, pose, min_angle, angular_resolution, min_range, range_threshold):
+    """LocalizedRangeScan::Update for a batch of scans in one call: scan i = source scan src[i] at pose[i].
+    Returns (pool_xy (n_points, 2), starts, counts)."""
+    ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+    beam_ptr = np.ascontiguousarray(beam_ptr, dtype=np.int32)
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(-1, 3)
+    n = len(src)
+    if len(pose) != n:
+        raise ValueError("one pose per scan")
+    cap = int((beam_ptr[1:] - beam_ptr[:-1])[src].sum()) if n else 0
+    out = np.empty((max(cap, 1), 2), dtype=np.float64)
+    starts, counts = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    tot = C.c_int64(0)
+    rc = lib().ysm_point_readings_batch(ranges.ctypes.data, beam_ptr.ctypes.data, len(beam_ptr) - 1, src.ctypes.data,
+                                        pose.ctypes.data, n, float(min_angle), float(angular_resolution),
+                                        float(min_range), float(range_threshold), out.ctypes.data, starts.ctypes.data,
+                                        counts.ctypes.data, C.byref(tot))
+    if rc != YSM_OK:
+        raise RuntimeError("ysm_point_readings_batch failed (%d)" % rc)
+    return out[:tot.value], starts, counts

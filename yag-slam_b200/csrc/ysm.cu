@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <sched.h>
 
 #include <immintrin.h>
 
@@ -772,6 +773,66 @@ extern "C" int ysm_point_readings(const double* ranges, int32_t n, double min_an
   return YSM_OK;
 }
 
+// LocalizedRangeScan::Update for a batch of scans: the same libm loop, spread over host threads
+extern "C" int ysm_point_readings_batch(const double* ranges, const int32_t* beam_ptr, int32_t n_src, const int32_t* src,
+                                        const double* pose, int32_t n, double min_angle, double angular_resolution,
+                                        double min_range, double range_threshold, double* out_xy, int32_t* out_start,
+                                        int32_t* out_count, int64_t* n_points) {
+  if (!ranges || !beam_ptr || !src || !pose || !out_xy || !out_start || !out_count || n < 0 || n_src < 0) return YSM_EINVAL;
+  for (int i = 0; i < n; i++)
+    if (src[i] < 0 || src[i] >= n_src) return YSM_EINVAL;
+  try {
+    // pass 1: how many readings every scan keeps (range test only), then the offsets
+    int64_t tot = 0;
+    for (int i = 0; i < n; i++) {
+      int k = 0;
+      for (int j = beam_ptr[src[i]]; j < beam_ptr[src[i] + 1]; j++) k += (ranges[j] >= min_range && ranges[j] <= range_threshold);
+      if (tot > 0x7fffffffLL - k) return YSM_EUNSUP;
+      out_start[i] = (int32_t)tot;
+      out_count[i] = k;
+      tot += k;
+    }
+    if (n_points) *n_points = tot;
+    // pass 2: the readings, scans dealt to the host threads in contiguous blocks
+    int nthreads = 1;
+    {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      if (sched_getaffinity(0, sizeof(set), &set) == 0) nthreads = std::max(1, CPU_COUNT(&set));
+      nthreads = std::min(nthreads, std::max(1, n / 64));
+    }
+    auto work = [&](int lo, int hi) {
+      for (int i = lo; i < hi; i++) {
+        const double x = pose[3 * (size_t)i], y = pose[3 * (size_t)i + 1], heading = pose[3 * (size_t)i + 2];
+        const int b0 = beam_ptr[src[i]], nb = beam_ptr[src[i] + 1] - b0;
+        double* o = out_xy + 2 * (size_t)out_start[i];
+        for (int j = 0; j < nb; j++) {
+          const double r = ranges[b0 + j];
+          if (!(r >= min_range && r <= range_threshold)) continue;
+          const double angle = heading + min_angle + (double)(uint32_t)j * angular_resolution;
+          o[0] = x + (r * cos(angle));
+          o[1] = y + (r * sin(angle));
+          o += 2;
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) {
+      const int lo = (int)((long long)n * t / nthreads), hi = (int)((long long)n * (t + 1) / nthreads);
+      try {
+        th.emplace_back(work, lo, hi);
+      } catch (const std::exception&) {
+        work(lo, hi);
+      }
+    }
+    work(0, (int)((long long)n / nthreads));
+    for (std::thread& t : th) t.join();
+  } catch (const std::exception&) {
+    return YSM_ENOMEM;
+  }
+  return YSM_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // zero the tiles of the last built wave (its work list is still resident) -- the grids
 // return to all-zero
@@ -1108,8 +1169,9 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   // shared memory: stamp table | scratch | workers: offsets + lattice / CTA 0: query points, spec, fine offsets, fine sums
   const size_t scratch = res_scratch_bytes(pstride);
   const size_t worker = 16 * (size_t)YSM_RES_THREADS + (size_t)(((P + 7) & ~7) + nX + nY) * 4;  // point stash | offsets + lattice
-  const size_t o_q = 0, o_spec = a16(o_q + 16 * (size_t)std::max(P, YSM_RES_THREADS)), o_foff = a16(o_spec + 8 * (size_t)(nA + 4 * nA * nAf));
-  const size_t o_fsum = a16(o_foff + 4 * (size_t)nAf * Ppad);
+  const size_t o_q = 0, o_spec = 16 * (size_t)YSM_RES_THREADS;  // (CTA 0 has the point stash too)
+  const size_t o_foff = 0;                                       // (unused: the workers rotate the points)
+  const size_t o_fsum = a16(o_spec + 8 * (size_t)(nA + 4 * nA * nAf));
   const size_t tail = a16(o_fsum + 12 * (size_t)(fnX * fnY * nAf + 2));
   size_t need = tab_bytes + scratch + std::max(worker, tail);
   need = (need + 16383) & ~(size_t)16383;
@@ -1936,6 +1998,12 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       kt.mark("k_tile_stamp");
       if (timing) CK(cudaEventRecord(h->ev[1], st));
       CK(cudaGetLastError());
+      if (timing) {  // P_valid of the wave (roofline accounting): the cells FindValidPoints + the ROI test kept
+        std::vector<int> cc((size_t)nw);
+        CK(cudaMemcpyAsync(cc.data(), h->d_cellcount.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int v : cc) h->work[15] += v;
+      }
       return YSM_OK;
     };
 

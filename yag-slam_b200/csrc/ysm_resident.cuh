@@ -55,8 +55,8 @@ struct ResReq {
   int nbase, Pq, pstride, do_refine;
   int nA, nAf, tpc, psplit, task_chunks, trace;
   int maxt, cand, tail_warps, pad1;  // tiles a CTA can own x stamps per tile (maxt * cand = YSM_RES_MAXT * YSM_RES_CAND)
-  // CTA 0's dynamic shared memory (bytes past the stamp table and the scratch every CTA has): query points
-  // (double2) | spec tables | fine lookup offsets [nAf][Ppad] | fine sums (u32) + fine responses (f64)
+  // CTA 0's dynamic shared memory (bytes past the stamp table and the scratch every CTA has): point stash |
+  // spec tables | fine sums (u32) + fine responses (f64)   (o_foff: unused)
   unsigned o_q, o_spec, o_foff, o_fsum;
   MatchDev m;
   PassDev coarse, fine;   // fine: everything but the search centre / trig rows (set by the tail)
@@ -1116,10 +1116,6 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
     const PassDev& ps = rq.coarse;
     const int nv = rq.nA * rq.task_chunks;
     int v = bid - 1;
-    if (bid == 0 && ps.P > (int)T) {
-      // the tail needs all query points in shared memory (s_q = s_qp, CTA 0 has room for P of them)
-      for (int i = T + tid; i < ps.P; i += T) s_qp[i] = __ldcg(reinterpret_cast<const double2*>(A.qpts) + i);
-    }
     if (threadIdx.x == 0) pf[1] = res_timer();
     // ---- phase B: stamp the tiles this CTA owns -------------------------------------------------------
     {

@@ -84,7 +84,7 @@ class ScanMatcherB200(object):
         return dict(zip(("lattice_lookups", "sweep_launches", "offset_entries", "poses", "fine_lookups",
                          "base_points", "h2d_bytes", "d2h_bytes", "pruned_sweep_launches", "lookups_issued",
                          "speculative_fine_passes", "lanes", "latency_kernel_launches", "resident_requests",
-                         "scan_store_hits"),
+                         "scan_store_hits", "valid_base_points"),
                         (int(x) for x in v)))
 
     def ping(self, n=1):

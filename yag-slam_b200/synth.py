@@ -213,27 +213,39 @@ def make_scan_log(world, n_scans, n_beams, seed, step=0.25, defects=0.0):
 
 # ---- batched relocalisation (SURVEY.md 8d cfg 5) -------------------------------------------
 def make_relocalisation_batch(world, n_matches, n_beams, n_base, seed, n_log=2000, perturb=(0.2, 0.15),
-                              range_threshold=20.0, path_step=0.25):
+                              range_threshold=20.0, path_step=0.25, n_use=None, readings=None):
     """n_matches independent (query, n_base-scan base set) pairs sampled from an n_log-scan log
     along the loop path: match i takes log scan k_i (uniform in [n_base, n_log)), localises it at
     its true pose + U(+-perturb) and matches it against log scans k_i-n_base .. k_i-1 at their true
     poses. The log's ranges are cast once; only the query point readings are per match.
-    Same dict as make_match_batch (without `points`) plus `log_scan` [n_matches] and `truth`."""
+    n_use: build only the first n_use matches (the SAME matches as the first n_use of the full batch: the random
+    draws do not depend on it). readings: None = the library's batched LocalizedRangeScan::Update
+    (ysm_point_readings_batch), or a callable (ranges, min_angle, angular_resolution, min_range, range_threshold,
+    x, y, heading) -> (k, 2) array, e.g. the oracle's (the CPU reference arm must not load the product library).
+    Same dict as make_match_batch (without `points`) plus `log_scan` [n] and `truth`."""
     rng = np.random.default_rng(seed)
     path = loop_path(n_log, step=path_step)
     lp = laser_params(n_beams, range_threshold)
-    from . import _capi
-    from .matcher import pack_pool
-    ranges = [cast_scan(world, path[k], n_beams, rng) for k in range(n_log)]
-    pts = [_capi.point_readings(ranges[k], lp[0], lp[2], lp[3], lp[5], *path[k]) for k in range(n_log)]
+    ranges = np.stack([cast_scan(world, path[k], n_beams, rng) for k in range(n_log)])
     k = rng.integers(n_base, n_log, size=n_matches)
     d = np.column_stack([rng.uniform(-perturb[0], perturb[0], n_matches), rng.uniform(-perturb[0], perturb[0], n_matches),
                          rng.uniform(-perturb[1], perturb[1], n_matches)])
-    guess = path[k] + d
-    for i in range(n_matches):
-        pts.append(_capi.point_readings(ranges[k[i]], lp[0], lp[2], lp[3], lp[5], *guess[i]))
-    pool, starts, counts = pack_pool(pts)
+    n = n_matches if n_use is None else min(int(n_use), n_matches)
+    k, guess = k[:n], (path[k] + d)[:n]
+    src = np.concatenate([np.arange(n_log), k]).astype(np.int32)  # scans 0 .. n_log-1 = the log, then the queries
+    poses = np.concatenate([path, guess])
+    beam_ptr = (np.arange(n_log + 1) * n_beams).astype(np.int32)
+    if readings is None:
+        from . import _capi
+        pool, starts, counts = _capi.point_readings_batch(ranges.reshape(-1), beam_ptr, src, poses, lp[0], lp[2], lp[3], lp[5])
+    else:
+        from .matcher import pack_pool
+        need = np.zeros(n_log, bool)
+        need[(k[:, None] - n_base + np.arange(n_base)[None, :]).reshape(-1)] = True
+        pts = [readings(ranges[j], lp[0], lp[2], lp[3], lp[5], *path[j]) if need[j] else np.zeros((0, 2)) for j in range(n_log)]
+        pts += [readings(ranges[k[i]], lp[0], lp[2], lp[3], lp[5], *guess[i]) for i in range(n)]
+        pool, starts, counts = pack_pool(pts)
     base_idx = (k[:, None] - n_base + np.arange(n_base)[None, :]).astype(np.int32).reshape(-1)
-    return dict(pool=pool, starts=starts, counts=counts, query_scan=(n_log + np.arange(n_matches)).astype(np.int32),
-                query_pose=np.ascontiguousarray(guess), base_ptr=(np.arange(n_matches + 1) * n_base).astype(np.int32),
+    return dict(pool=pool, starts=starts, counts=counts, query_scan=(n_log + np.arange(n)).astype(np.int32),
+                query_pose=np.ascontiguousarray(guess), base_ptr=(np.arange(n + 1) * n_base).astype(np.int32),
                 base_idx=base_idx, log_scan=k.astype(np.int32), truth=path[k])
