@@ -1659,8 +1659,47 @@ reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* of
       s_n = nt;
       s_first = nt > 0 ? s_sorted[0] : -1;
     }
+  } else if (nt == nposes) {
+    // EVERY pose ties (best == 0: an empty grid, the response-expansion case). The four ordered sums are
+    // independent of each other: four threads of four different warps each run one of them as plain nested
+    // loops in storage order (y, x, angle) -- the same additions in the same order as the CPU loop, without
+    // the per-pose index arithmetic and memory reads of the general path below.
+    __shared__ double s_ht[2 * 128];
+    const bool ht_smem = ps.nA <= 128;
+    if (ht_smem)
+      for (int i = tid; i < 2 * ps.nA; i += blockDim.x) s_ht[i] = htrig[i];
+    __syncthreads();
+    if ((tid & 31) == 0 && tid < 128) {
+      const int which = tid >> 5;
+      double acc = 0.0;
+      if (which == 0) {
+        for (int iy = 0; iy < ps.nY; iy++)
+          for (int ix = 0; ix < ps.nX; ix++) {
+            const double v = ps.cx + (startX + (double)ix * ps.resx);
+            for (int a = 0; a < ps.nA; a++) acc += v;
+          }
+      } else if (which == 1) {
+        for (int iy = 0; iy < ps.nY; iy++) {
+          const double v = ps.cy + (startY + (double)iy * ps.resy);
+          for (int k = 0; k < ps.nX * ps.nA; k++) acc += v;
+        }
+      } else {
+        const int o = which - 2;
+        for (int c = 0; c < ps.nY * ps.nX; c++) {
+          if (ht_smem)
+            for (int a = 0; a < ps.nA; a++) acc += s_ht[2 * a + o];
+          else
+            for (int a = 0; a < ps.nA; a++) acc += htrig[2 * a + o];
+        }
+      }
+      s_acc[which] = acc;
+    }
+    if (tid == 0) {
+      s_n = nt;
+      s_first = 0;
+    }
   } else {
-    // degenerate case (e.g. best == 0: every pose ties): ordered chunks of blockDim poses,
+    // many (not all) poses tie: ordered chunks of blockDim poses,
     // one thread accumulates sequentially so the rounding matches the CPU loop
     double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
     int n = 0, first = -1;

@@ -986,35 +986,42 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
     // ---- wait for the doorbell -----------------------------------------------------------------------
     int cmd = RES_CMD_NONE;
     if (poller) {
-      if (tid == 0) {
-        uint4 d = make_uint4(0u, 0u, 0u, 0u);
-        int c = RES_CMD_NONE;
+      if (warp == 0) {
+        // Lanes 0..4 read the five tagged words of this CTA's line with ONE warp-wide load (one thread's
+        // system-scope loads are served one after the other; five lanes' loads travel together).
         const unsigned char* line = reinterpret_cast<const unsigned char*>(A.db) + (size_t)bid * YSM_RES_DB_STRIDE;
+        int c = RES_CMD_NONE;
         for (unsigned spins = 1u;; spins++) {
-          // the five tagged words of this CTA's line in ONE round of PCIe reads
-          d = res_ld_volatile_v4(line);
-          const uint4 d1 = res_ld_volatile_v4(line + 16), d2 = res_ld_volatile_v4(line + 32);
-          const uint4 d3 = res_ld_volatile_v4(line + 48), d4 = res_ld_volatile_v4(line + 64);
-          if (d.x != seq_done && d1.x == d.x && d2.w == d.x && d3.w == d.x && d4.w == d.x) {
-            c = (int)(d.y & 0x7Fu);
-            s_line[0] = d1.y; s_line[1] = d1.z; s_line[2] = d1.w;
-            s_line[4] = d2.x; s_line[5] = d2.y; s_line[6] = d2.z; s_line[7] = d3.x;
-            s_line[8] = d3.y; s_line[9] = d3.z; s_line[10] = d4.x; s_line[11] = d4.y;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (lane < 5) v = res_ld_volatile_v4(line + 16 * lane);
+          const unsigned tag = lane < 2 ? v.x : v.w;
+          const unsigned tag0 = __shfl_sync(0xffffffffu, tag, 0);
+          const bool fresh = __all_sync(0xffffffffu, lane >= 5 || tag == tag0) && tag0 != seq_done;
+          if (fresh) {
+            if (lane == 0) { s_db = v; c = (int)(v.y & 0x7Fu); }
+            else if (lane == 1) { s_line[0] = v.y; s_line[1] = v.z; s_line[2] = v.w; }
+            else if (lane == 2) { s_line[4] = v.x; s_line[5] = v.y; s_line[6] = v.z; }
+            else if (lane == 3) { s_line[7] = v.x; s_line[8] = v.y; s_line[9] = v.z; }
+            else if (lane == 4) { s_line[10] = v.x; s_line[11] = v.y; }
             break;
           }
-          if (bid == 0) {
-            if ((spins & 7u) == 0u && res_timer() - idle0 > A.idle_ns) {
-              c = RES_CMD_QUIT;
-              res_st_release(A.quit_round, round);
-              break;
+          int quit = 0;
+          if (lane == 0) {
+            if (bid == 0) {
+              if ((spins & 7u) == 0u && res_timer() - idle0 > A.idle_ns) {
+                quit = 1;
+                res_st_release(A.quit_round, round);
+              }
+            } else if ((spins & 3u) == 0u && res_ld_acquire(A.quit_round) == round) {
+              quit = 1;
             }
-          } else if ((spins & 3u) == 0u && res_ld_acquire(A.quit_round) == round) {
-            c = RES_CMD_QUIT;
+          }
+          if (__shfl_sync(0xffffffffu, quit, 0)) {
+            if (lane == 0) { s_db = v; c = RES_CMD_QUIT; }
             break;
           }
         }
-        s_db = d;
-        s_cmd = c;
+        if (lane == 0) s_cmd = c;
       }
       __syncthreads();
       cmd = s_cmd;
