@@ -263,6 +263,9 @@ struct Resident {
   unsigned char* d_small = nullptr;  // barrier counters | quit_round | abort | passmax | winner word (2 KB)
   unsigned* d_fsum = nullptr;        // fine lookup sums
   double* d_spec = nullptr;          // device copy of the spec tables
+  double* d_dp = nullptr;            // distance-penalty tables: coarse lattice [nY][nX], then the fine 3 x 3
+  size_t dp_fine_off = 0;
+  int* d_winrec = nullptr;           // winner record CTA 0 -> fine-pass workers
   unsigned char* d_ctl = nullptr;
   uint32_t* d_cells = nullptr;
   double* d_qpts = nullptr;
@@ -283,7 +286,7 @@ struct Resident {
 };
 #define YSM_RES_PTS_CAP 131072   // points the mailbox holds
 #define YSM_RES_CELLS_CAP 131072
-#define YSM_RES_SPEC_DOUBLES (YSM_RES_MAXNA + 4 * 4096)
+#define YSM_RES_SPEC_DOUBLES (YSM_RES_MAXNA + 5 * 4096)
 
 struct ysm_handle {
   ysm_params prm;
@@ -986,6 +989,8 @@ static void res_free(ysm_handle* h) {
   if (R->d_small) cudaFree(R->d_small);
   if (R->d_fsum) cudaFree(R->d_fsum);
   if (R->d_spec) cudaFree(R->d_spec);
+  if (R->d_dp) cudaFree(R->d_dp);
+  if (R->d_winrec) cudaFree(R->d_winrec);
   if (R->d_ctl) cudaFree(R->d_ctl);
   if (R->d_cells) cudaFree(R->d_cells);
   if (R->d_qpts) cudaFree(R->d_qpts);
@@ -994,6 +999,25 @@ static void res_free(ysm_handle* h) {
   if (R->d_cellmax) cudaFree(R->d_cellmax);
   delete R;
   h->res = nullptr;
+}
+
+// The two halves of CorrelateScan's odometry penalty, evaluated on the host with the same IEEE
+// operations, in the same order, as the device functions penalty_distance / penalty_angle: plain arithmetic
+// (no libm), so host and device agree bit for bit -- and f64 division is the most expensive thing an SM of this
+// machine can be asked to do.
+static double h_penalty_distance(double offx, double resx, double offy, double resy, int ix, int iy, const PenaltyC& pen) {
+  const double x = -offx + (double)ix * resx;
+  const double y = -offy + (double)iy * resy;
+  const double sqd = x * x + y * y;
+  const double dp = 1.0 - (0.2 * sqd / pen.distance_variance_penalty);
+  return dp > pen.minimum_distance_penalty ? dp : pen.minimum_distance_penalty;
+}
+static double h_penalty_angle(double ch, double angle_offset, double angle_res, int a, const PenaltyC& pen) {
+  const double angle = (ch - angle_offset) + (double)a * angle_res;
+  const double da = angle - ch;
+  const double sqa = da * da;
+  const double ap = 1.0 - (0.2 * sqa / pen.angle_variance_penalty);
+  return ap > pen.minimum_angle_penalty ? ap : pen.minimum_angle_penalty;
 }
 
 static int res_alloc(ysm_handle* h) {
@@ -1024,6 +1048,21 @@ static int res_alloc(ysm_handle* h) {
   CK(cudaMalloc((void**)&R->d_cells, 4 * (size_t)YSM_RES_CELLS_CAP));
   CK(cudaMalloc((void**)&R->d_qpts, 16 * (size_t)YSM_RES_PMAX));
   CK(cudaMalloc((void**)&R->d_cache, 16 * (size_t)YSM_RES_PMAX * YSM_RES_CACHE_SLOTS));
+  CK(cudaMalloc((void**)&R->d_winrec, 4096));
+  {
+    // distance-penalty tables: they depend on the matcher's configuration only
+    const double csx = 0.5 * (h->side - 1) * h->res_eff, crx = 2 * h->res_eff;
+    const int nX = n_steps(csx, crx), fnX = n_steps(crx * 0.5, h->res_eff);
+    std::vector<double> dp((size_t)nX * nX + (size_t)fnX * fnX);
+    for (int iy = 0; iy < nX; iy++)
+      for (int ix = 0; ix < nX; ix++) dp[(size_t)iy * nX + ix] = h_penalty_distance(csx, crx, csx, crx, ix, iy, h->pen);
+    R->dp_fine_off = (size_t)nX * nX;
+    for (int iy = 0; iy < fnX; iy++)
+      for (int ix = 0; ix < fnX; ix++)
+        dp[R->dp_fine_off + (size_t)iy * fnX + ix] = h_penalty_distance(crx * 0.5, h->res_eff, crx * 0.5, h->res_eff, ix, iy, h->pen);
+    CK(cudaMalloc((void**)&R->d_dp, dp.size() * 8));
+    CK(cudaMemcpy(R->d_dp, dp.data(), dp.size() * 8, cudaMemcpyHostToDevice));
+  }
   const int idle_us = h->prm.resident_idle_us > 0 ? h->prm.resident_idle_us : 2000;
   R->idle_ns = (unsigned long long)idle_us * 1000ull;
   R->G = h->num_sms;
@@ -1055,10 +1094,12 @@ static int res_launch(ysm_handle* h, size_t smem, unsigned last_seq) {
   A.bars = (unsigned long long*)R.d_small;  // 5 counters, 128 bytes apart
   A.quit_round = (unsigned*)(R.d_small + 1024);
   A.abort_flag = (int*)(R.d_small + 1088);
-  A.passmax = (double*)(R.d_small + 1152);
   A.win = (unsigned long long*)(R.d_small + 1216);
   A.fsum = R.d_fsum;
   A.spec_dev = R.d_spec;
+  A.dp_coarse = R.d_dp;
+  A.dp_fine = R.d_dp + R.dp_fine_off;
+  A.winrec = R.d_winrec;
   A.cells = R.d_cells;
   A.cells_cap = YSM_RES_CELLS_CAP;
   A.qpts = R.d_qpts;
@@ -1161,9 +1202,9 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   const int nA = n_steps(a_off, a_res), nAf = n_steps(fo, fr);
   const int nX = n_steps(csx, crx), nY = nX;
   const int fnX = n_steps(crx * 0.5, h->res_eff), fnY = fnX;
-  if (nA < 1 || nA > YSM_RES_MAXNA || nAf < 1 || nA * nAf > 4096 || nA > 255 || nAf > 64 || fnX * fnY > 64) return 1;
+  if (nA < 1 || nA > YSM_RES_MAXNA || nAf < 1 || nA * nAf > 4096 || nA > 255 || nAf > 64 || fnX * fnY > 32) return 1;
   if ((long long)nX * nY * nA > (1 << 21) || fnX * fnY * nAf > 4096) return 1;
-  if ((long long)nAf * ((P + 31) / 32) > 32LL * (h->num_sms - 1)) return 1;  // fine-pass items: one per warp
+  if ((long long)nAf * ((P + 31) / 32) > (long long)(YSM_RES_THREADS / 32) * (h->num_sms - 1)) return 1;  // fine-pass items: one per warp
   const int Ppad = align_up(P, 4);
   const size_t tab_bytes = stamp_table_bytes(g.K, g.Wt);
   // shared memory: stamp table | scratch | workers: offsets + lattice / CTA 0: query points, spec, fine offsets, fine sums
@@ -1171,8 +1212,9 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
   const size_t worker = 16 * (size_t)YSM_RES_THREADS + (size_t)(((P + 7) & ~7) + nX + nY) * 4;  // point stash | offsets + lattice
   const size_t o_q = 0, o_spec = 16 * (size_t)YSM_RES_THREADS;  // (CTA 0 has the point stash too)
   const size_t o_foff = 0;                                       // (unused: the workers rotate the points)
-  const size_t o_fsum = a16(o_spec + 8 * (size_t)(nA + 4 * nA * nAf));
-  const size_t tail = a16(o_fsum + 12 * (size_t)(fnX * fnY * nAf + 2));
+  const size_t o_fsum = a16(o_spec + 8 * (size_t)(nA + 5 * nA * nAf));
+  const size_t o_cm = a16(o_fsum + 12 * (size_t)(fnX * fnY * nAf + 2));
+  const size_t tail = a16(o_cm + 8 * (size_t)std::min(nX * nY, YSM_RES_CM_SMEM));
   size_t need = tab_bytes + scratch + std::max(worker, tail);
   need = (need + 16383) & ~(size_t)16383;
   if (need > h->res_smem_limit) return 1;
@@ -1211,9 +1253,10 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
     // sweep shape: CTAs per angle x tasks per CTA x point slices = the machine (32 warps per CTA)
     const int nxc = (nX + 31) / 32, tasks = nY * nxc;
     const int cpa = std::max(1, (R.G - 1) / nA);
-    int tpc = std::min(32, (tasks + cpa - 1) / cpa);
+    const int nwarps = YSM_RES_THREADS / 32;
+    int tpc = std::min(nwarps, (tasks + cpa - 1) / cpa);
     int psplit = 1;
-    while (psplit * 2 * tpc <= 32 && P / (psplit * 2) >= 16) psplit *= 2;
+    while (psplit * 2 * tpc <= nwarps && P / (psplit * 2) >= 16) psplit *= 2;
     rq->tpc = tpc; rq->psplit = psplit; rq->task_chunks = (tasks + tpc - 1) / tpc;
   }
   {
@@ -1225,6 +1268,7 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
     rq->pad1 = 0;
   }
   rq->o_q = (unsigned)o_q; rq->o_spec = (unsigned)o_spec; rq->o_foff = (unsigned)o_foff; rq->o_fsum = (unsigned)o_fsum;
+  rq->o_cm = (unsigned)o_cm;
   MatchDev& m = rq->m;
   m.slot = 0; m.base_begin = 0; m.base_end = nbase; m.cells_off = 0; m.gbox_off = 0; m.pad0 = 0;
   m.vpx = pose[0]; m.vpy = pose[1]; m.gox = gox; m.goy = goy;
@@ -1258,6 +1302,7 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
       rq->trig4[a][0] = ca; rq->trig4[a][1] = sa;
       rq->trig4[a][2] = same ? ca : cos(hn);
       rq->trig4[a][3] = same ? sa : sin(hn);
+      rq->ap[a] = b->do_penalize ? h_penalty_angle(pose[2], a_off, a_res, a, h->pen) : 1.0;
     }
   }
   // points: base scan s at mailbox slot s, the query at slot nbase -- unless the device-resident scan store
@@ -1340,6 +1385,8 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
         e[0] = ca; e[1] = sa;
         e[2] = same ? ca : cos(hn);
         e[3] = same ? sa : sin(hn);
+        // the fine pass's angle penalty, should this coarse angle win (its search centre heading is `heading`)
+        ft[4 * (size_t)nA * nAf + (size_t)a * nAf + f] = b->do_penalize ? h_penalty_angle(heading, fo, fr, f, h->pen) : 1.0;
       }
     }
     __atomic_store_n(reinterpret_cast<uint32_t*>(R.mb + R.o_spec), seq, __ATOMIC_RELEASE);
@@ -1392,6 +1439,22 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
       for (int c = 1; c < R.G; c++) v.push_back((double)(int64_t)(pf[(size_t)c * YSM_RES_PROF + k + 1] - pf[(size_t)c * YSM_RES_PROF + k]) * 1e-3);
       std::sort(v.begin(), v.end());
       fprintf(stderr, "[ysm-resident]   workers %-26s min %6.2f  med %6.2f  max %6.2f us\n", pn[k], v.front(), v[v.size() / 2], v.back());
+    }
+    {
+      // inside the sweep (pf[4] barrier-2 exit, [13] penalties done, [14] row sums done, [15] responses stored, [5] end)
+      // and inside the stamp (pf[2] start, [16] slots known, [17] scattered + staged, [18] barrier, [3] written)
+      static const int seq[3][5] = {{4, 13, 14, 15, 5}, {2, 16, 17, 18, 3}, {4, 19, 20, 13, 14}};
+      static const char* nm[3][4] = {{"sweep: penalties", "sweep: row sums", "sweep: combine + response", "sweep: block max"},
+                                     {"stamp: slot list", "stamp: scatter + stage", "stamp: barrier", "stamp: combine + write"},
+                                     {"sweep: barrier exit -> entry", "sweep: setup", "sweep: dp load issue", "sweep: row sums"}};
+      for (int q = 0; q < 3; q++)
+        for (int k = 0; k < 4; k++) {
+          std::vector<double> v;
+          for (int c = 1; c < R.G; c++)
+            v.push_back((double)(int64_t)(pf[(size_t)c * YSM_RES_PROF + seq[q][k + 1]] - pf[(size_t)c * YSM_RES_PROF + seq[q][k]]) * 1e-3);
+          std::sort(v.begin(), v.end());
+          fprintf(stderr, "[ysm-resident]     %-28s min %6.2f  med %6.2f  max %6.2f us\n", nm[q][k], v.front(), v[v.size() / 2], v.back());
+        }
     }
     {
       const uint64_t* f1 = pf + (size_t)1 * YSM_RES_PROF;  // CTA 1: base scan 0

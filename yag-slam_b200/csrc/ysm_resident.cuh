@@ -32,7 +32,9 @@
 
 namespace ysm {
 
+#ifndef YSM_RES_THREADS
 #define YSM_RES_THREADS 1024
+#endif
 #define YSM_RES_MAXBASE 64
 #define YSM_RES_POLLERS 16   // CTAs 1..16 poll the doorbell too (they own the scans of phase A)
 #define YSM_RES_MAXT 32      // tiles one CTA can own per request
@@ -42,9 +44,10 @@ namespace ysm {
 #define YSM_RES_CHUNKS 256   // 16-byte result chunks
 #define YSM_RES_TS 24        // trace timestamps
 #define YSM_RES_DB_STRIDE 256
-#define YSM_RES_PROF 16      // per-CTA trace timestamps
+#define YSM_RES_PROF 24      // per-CTA trace timestamps
 #define YSM_RES_PMAX 4096    // point readings per scan
 #define YSM_RES_CACHE_SLOTS 32
+#define YSM_RES_CM_SMEM 4096 // coarse lattice cells whose maxima the tail keeps in shared memory
 
 enum { RES_CMD_NONE = 0, RES_CMD_MATCH = 1, RES_CMD_QUIT = 2, RES_CMD_PING = 3 };
 enum { RES_ST_OK = 0, RES_ST_FALLBACK = 1, RES_ST_PONG = 2 };
@@ -58,10 +61,12 @@ struct ResReq {
   // CTA 0's dynamic shared memory (bytes past the stamp table and the scratch every CTA has): point stash |
   // spec tables | fine sums (u32) + fine responses (f64)   (o_foff: unused)
   unsigned o_q, o_spec, o_foff, o_fsum;
+  unsigned o_cm, pad2[3];          // ... | per-cell maxima of the coarse pass (f64, up to YSM_RES_CM_SMEM cells)
   MatchDev m;
   PassDev coarse, fine;   // fine: everything but the search centre / trig rows (set by the tail)
   TableDev ctab, ftab;
   unsigned short counts[YSM_RES_MAXBASE + 12];  // point readings of base scan s; [nbase] = query
+  double ap[YSM_RES_MAXNA];                     // angle penalty of every coarse angle (host: plain IEEE arithmetic)
   double trig4[YSM_RES_MAXNA][4];              // per coarse angle: cos, sin, cos / sin of the normalised heading
 };
 static_assert(sizeof(ResReq) % 16 == 0, "ResReq must be a multiple of 16 bytes");
@@ -101,7 +106,9 @@ struct ResArgs {
   double* cache;                // device-resident scan store: YSM_RES_CACHE_SLOTS x YSM_RES_PMAX points
   double* resp;                 // [iy][ix][a] coarse responses
   unsigned long long* cellmax;  // [iy][ix]
-  double* passmax;
+  const double* dp_coarse;      // distance penalty of every coarse lattice cell [nY][nX] (depends on the configuration only)
+  const double* dp_fine;        // ... of the fine pass's 3 x 3 cells
+  int* winrec;                  // winner record for the fine items: flat index of the 3 x 3 cells | (cos, sin) rows as doubles at +16 ints
   const uint16_t* stamp_tab;
   uint8_t* grid;                // slot 0
   unsigned last_seq;
@@ -383,7 +390,7 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int max
 // stamps the owned tiles (up to 8 warps share a tile) and writes each once
 __device__ __forceinline__ void
 res_stamp(const GridC& g, const ResArgs& A, int cand, const int* s_tile, const int* s_cnt, const uint32_t* s_steps,
-          int* s_slots, int* s_nt, uint32_t* s_stage, uint32_t lane_tab_s) {
+          int* s_slots, int* s_nt, uint32_t* s_stage, uint32_t lane_tab_s, unsigned long long* pf) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   if (warp == 0) {
@@ -394,6 +401,7 @@ res_stamp(const GridC& g, const ResArgs& A, int cand, const int* s_tile, const i
   }
   __syncthreads();
   const int nt = *s_nt;
+  if (threadIdx.x == 0) { pf[16] = res_timer(); pf[17] = pf[18] = pf[16]; }
   if (nt == 0) return;  // CTA-uniform
   const int S = max(1, min(8, nwarps / nt));
   const int ti = warp / S, part = warp - ti * S;
@@ -416,7 +424,9 @@ res_stamp(const GridC& g, const ResArgs& A, int cand, const int* s_tile, const i
     st4[lane * 2 + (0 ^ sw)] = make_uint4(b[0], b[1], b[2], b[3]);
     st4[lane * 2 + (1 ^ sw)] = make_uint4(b[4], b[5], b[6], b[7]);
   }
+  if (threadIdx.x == 0) pf[17] = res_timer();
   __syncthreads();
+  if (threadIdx.x == 0) pf[18] = res_timer();
   if (active) {
     const int tile = s_tile[slot];
     const int ty = tile / tnx, tx = tile - ty * tnx;
@@ -542,9 +552,10 @@ __device__ __forceinline__ unsigned res_sweep_row(const uint8_t* gp, const unsig
 // general path's business
 __device__ __forceinline__ bool
 res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResArgs& A, int a, int chunk, const int* s_i,
-              const int* s_minmax, unsigned* s_part, double* s_wmax) {
+              const int* s_minmax, unsigned* s_part, unsigned long long* pf) {
   const PassDev& ps = rq.coarse;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) pf[19] = res_timer();
   const int pc4 = (ps.P + 7) & ~7;
   const unsigned* s_off = reinterpret_cast<const unsigned*>(s_i);
   const int* s_col = s_i + pc4;
@@ -562,21 +573,25 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
   const int plen = (((np + psplit - 1) / psplit) + 3) & ~3;
   const int pb = min(np, slice * plen), pe = min(np, pb + plen);
   const int iters = (task1 - task0 + ntw - 1) / ntw;  // CTA-uniform
-  const double ap = ps.penalize ? penalty_angle(ps, pen, a) : 1.0;
-  double wmax = 0.0;
+  const double ap = rq.ap[a];
+  if (threadIdx.x == 0) pf[20] = res_timer();
   for (int it = 0; it < iters; it++) {
     const int task = task0 + wtask + it * ntw;
     const bool tv = wtask < ntw && task < task1;
     const int iy = tv ? task / nxc : 0, xc = tv ? task - iy * nxc : 0;
     const int ix = (xc << 5) + lane;
     const bool active = tv && ix < ps.nX;
-    // the penalty does not depend on the sum: its divisions overlap the lookups
-    const double dpap = (ps.penalize && active && slice == 0) ? penalty_distance(ps, pen, ix, iy) * ap : 1.0;
+    // the odometry penalty of the pose: distance part from the per-configuration table, angle part from the
+    // request (both made by the host with the same IEEE operations as CorrelateScan); the load overlaps the lookups
+    double dp = 1.0;
+    if (ps.penalize && active && slice == 0) dp = __ldg(A.dp_coarse + (size_t)iy * ps.nX + ix);
+    if (threadIdx.x == 0) pf[13] = res_timer();
     unsigned sum = 0;
     if (tv) {
       const int base = s_row[iy] + s_col[active ? ix : 0] + minoff;
       sum = res_sweep_row(A.grid + base, s_off + pb, pe - pb);
     }
+    if (threadIdx.x == 0) pf[14] = res_timer();
     if (psplit > 1) {
       s_part[warp * 32 + lane] = sum;
       __syncthreads();
@@ -585,26 +600,11 @@ res_sweep_run(const GridC& g, const PenaltyC& pen, const ResReq& rq, const ResAr
       __syncthreads();
     }
     if (active && slice == 0) {
-      const double rr = response_from(ps, sum, dpap);
+      const double rr = response_from(ps, sum, dp * ap);
       A.resp[((size_t)iy * ps.nX + ix) * ps.nA + a] = rr;
       atomicMax(A.cellmax + (size_t)iy * ps.nX + ix, (unsigned long long)__double_as_longlong(rr));
-      wmax = rr > wmax ? rr : wmax;
     }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double t = __shfl_xor_sync(0xffffffffu, wmax, o);
-    wmax = t > wmax ? t : wmax;
-  }
-  if (lane == 0) s_wmax[warp] = wmax;
-  __syncthreads();
-  if (warp == 0) {
-    double m = lane < nwarps ? s_wmax[lane] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) {
-      const double t = __shfl_xor_sync(0xffffffffu, m, o);
-      m = t > m ? t : m;
-    }
-    if (lane == 0 && m > 0.0)
-      atomicMax(reinterpret_cast<unsigned long long*>(A.passmax), (unsigned long long)__double_as_longlong(m));
+    if (threadIdx.x == 0) pf[15] = res_timer();
   }
   return true;
 }
@@ -627,35 +627,35 @@ struct ResTail {
   int angs[YSM_RES_MAXNA];
 };
 
-// CorrelateScan epilogue of the coarse pass (reduce_body's logic, restated for one CTA with few dependent
-// L2 round trips): round 1 = best response + the per-cell maxima (kept in registers for A.9), round 2 = the
-// responses of the few cells that can hold a tied pose; ties in storage order, sequential sums.
-// Returns false when a list overflows (the host takes the general path).
-#define YSM_RES_CELLS_PT 6   // lattice cells a thread keeps in registers (more: re-read)
+// CorrelateScan epilogue of the coarse pass (reduce_body's logic, restated for a small team with few dependent
+// L2 round trips), in two steps so that the winner can be published to the fine-pass workers in between:
+//   res_reduce_winner  per-cell maxima -> shared memory, best response = their maximum, the responses of the
+//                      few cells that can hold a tied pose, ties in storage order, sequential sums
+//   res_reduce_cov     ComputePositionalCovariance accumulators (A.9) from the maxima in shared memory
+// res_reduce_winner returns false when a list overflows (the host takes the general path).
 __device__ __forceinline__ bool
-res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S, int T) {
+res_reduce_winner(const ResReq& rq, const ResArgs& A, ResTail& S, int T, double* s_cm) {
   const PassDev& ps = rq.coarse;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int ncell = ps.nX * ps.nY;
   if (tid == 0) { S.count = 0; S.n = 0; }
-  double cm[YSM_RES_CELLS_PT];
-#pragma unroll
-  for (int k = 0; k < YSM_RES_CELLS_PT; k++) {
-    const int c = tid + k * T;
-    cm[k] = c < ncell ? __longlong_as_double((long long)__ldcg(A.cellmax + c)) : -1.0;
-  }
-  const double best = __longlong_as_double((long long)__ldcg(reinterpret_cast<const unsigned long long*>(A.passmax)));
-  res_team_sync(T);
-  // cells whose maximum is within the tie tolerance of the best (S.sorted doubles as the cell list)
-#pragma unroll
-  for (int k = 0; k < YSM_RES_CELLS_PT; k++) {
-    if (cm[k] >= best - YSM_KT_TOLERANCE) {  // (cells past the lattice hold -1)
-      const int pos = atomicAdd(&S.n, 1);
-      if (pos < YSM_RES_TIECAP) S.sorted[pos] = tid + k * T;
-    }
-  }
-  for (int c = tid + YSM_RES_CELLS_PT * T; c < ncell; c += T) {
+  double mx = 0.0;
+  for (int c = tid; c < ncell; c += T) {
     const double m = __longlong_as_double((long long)__ldcg(A.cellmax + c));
+    if (c < YSM_RES_CM_SMEM) s_cm[c] = m;
+    mx = m > mx ? m : mx;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = t > mx ? t : mx;
+  }
+  if (lane == 0) S.tmp4[warp][0] = mx;
+  res_team_sync(T);
+  double best = 0.0;  // (responses are >= 0; CorrelateScan's -1 initial value never survives)
+  for (int w = 0; w < nwarps; w++) best = S.tmp4[w][0] > best ? S.tmp4[w][0] : best;
+  // cells whose maximum is within the tie tolerance of the best (S.sorted doubles as the cell list)
+  for (int c = tid; c < ncell; c += T) {
+    const double m = c < YSM_RES_CM_SMEM ? s_cm[c] : __longlong_as_double((long long)__ldcg(A.cellmax + c));
     if (m >= best - YSM_KT_TOLERANCE) {
       const int pos = atomicAdd(&S.n, 1);
       if (pos < YSM_RES_TIECAP) S.sorted[pos] = c;
@@ -707,15 +707,27 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S, int T) {
       po.tx = nt > 0 ? tx / cnt : 0.0;
       po.ty = nt > 0 ? ty / cnt : 0.0;
     }
+    po.norm = 0.0; po.axx = 0.0; po.axy = 0.0; po.ayy = 0.0;
     po.n_ties = nt;
     po.first_idx = nt > 0 ? S.sorted[0] : -1;
   }
   res_team_sync(T);
-  // ComputePositionalCovariance accumulators (A.9); probs(x, y) = max response over the angles
+  return true;
+}
+
+__device__ __forceinline__ void
+res_reduce_cov(const ResReq& rq, const ResArgs& A, ResTail& S, int T, const double* s_cm) {
+  const PassDev& ps = rq.coarse;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ncell = ps.nX * ps.nY;
+  const double best = S.po[0].best;
+  const double startX = -ps.offx, startY = -ps.offy;
+  // probs(x, y) = max response over the angles
   double norm = 0.0, axx = 0.0, axy = 0.0, ayy = 0.0;
   if (!(best < YSM_KT_TOLERANCE)) {
     const double dx = S.po[0].avg_x - ps.cx, dy = S.po[0].avg_y - ps.cy;
-    auto add_cell = [&](int c, double pm) {
+    for (int c = tid; c < ncell; c += T) {
+      const double pm = c < YSM_RES_CM_SMEM ? s_cm[c] : __longlong_as_double((long long)__ldcg(A.cellmax + c));
       if (pm >= (best - 0.1)) {
         const int iy = c / ps.nX, ix = c - iy * ps.nX;
         const double x = startX + (double)ix * ps.resx;
@@ -725,12 +737,7 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S, int T) {
         axy += ((x - dx) * (y - dy) * pm);
         ayy += ((y - dy) * (y - dy) * pm);
       }
-    };
-#pragma unroll
-    for (int k = 0; k < YSM_RES_CELLS_PT; k++)
-      if (tid + k * T < ncell) add_cell(tid + k * T, cm[k]);
-    for (int c = tid + YSM_RES_CELLS_PT * T; c < ncell; c += T)
-      add_cell(c, __longlong_as_double((long long)__ldcg(A.cellmax + c)));
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     norm += __shfl_xor_sync(0xffffffffu, norm, o);
@@ -755,7 +762,6 @@ res_reduce_coarse(const ResReq& rq, const ResArgs& A, ResTail& S, int T) {
     if (lane == 0) { S.po[0].norm = v0; S.po[0].axx = v1; S.po[0].axy = v2; S.po[0].ayy = v3; }
   }
   res_team_sync(T);
-  return true;
 }
 
 // ---- fine CorrelateScan at the coarse winner, spread over the machine ------------------------------------
@@ -772,20 +778,19 @@ __device__ __forceinline__ void res_fine_centre(const PassDev& ps, int ix, int i
   cy = (0.0 + (ps.cy + (-ps.offy + (double)iy * ps.resy))) / 1.0;
 }
 
-// one warp, one item
+// one warp, one item. The winner record (written by CTA 0 before it released the winner word) holds what does not
+// depend on the item: the flat grid index of each of the 3 x 3 lattice cells, then the (cos, sin) of every fine angle.
 __device__ __forceinline__ void
-res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsigned winw, double2 pt, bool valid) {
-  const PassDev& ps = rq.coarse;
+res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, double2 pt, bool valid) {
   const PassDev& f = rq.fine;
   const TableDev& ft = rq.ftab;
   const int lane = threadIdx.x & 31;
   const int nAf = f.nA, nxy = f.nX * f.nY;
   const int a = item % nAf;  // fine angle (the chunk of points came with `pt`)
-  const int wa = (int)(winw & 0xFFu), wix = (int)((winw >> 8) & 0xFFFu), wiy = (int)(winw >> 20);
-  double cx, cy;
-  res_fine_centre(ps, wix, wiy, cx, cy);
-  const double* row = A.spec_dev + rq.nA + 4 * ((size_t)wa * nAf + a);
-  const double cosine = __ldcg(row), sine = __ldcg(row + 1);
+  const double* rows = reinterpret_cast<const double*>(A.winrec + 64);
+  const double cosine = __ldcg(rows + 2 * a), sine = __ldcg(rows + 2 * a + 1);
+  int cb = 0;
+  if (lane < nxy) cb = __ldcg(A.winrec + lane);  // (nxy <= 32: one cell base per lane, handed round by shuffles)
   int gx, gy;
   offset_cell(ft, g.scale, pt.x, pt.y, cosine, sine, gx, gy);
   const int o = gx + gy * g.stride;
@@ -794,15 +799,8 @@ res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsi
     unsigned v[9];
 #pragma unroll
     for (int u = 0; u < 9; u++) {
-      unsigned idx = 0xFFFFFFFFu;
-      if (c0 + u < nxy) {
-        const int iy = (c0 + u) / f.nX, ix = (c0 + u) - iy * f.nX;
-        const double x = -f.offx + (double)ix * f.resx;
-        const double y = -f.offy + (double)iy * f.resy;
-        const int bx = world_to_grid1(cx + x, f.gox, g.scale) + g.border;
-        const int by = world_to_grid1(cy + y, f.goy, g.scale) + g.border;
-        idx = (unsigned)(bx + by * g.stride + o);
-      }
+      const int base = __shfl_sync(0xffffffffu, cb, (c0 + u) & 31);
+      const unsigned idx = c0 + u < nxy ? (unsigned)(base + o) : 0xFFFFFFFFu;
       v[u] = (valid && idx < dsz) ? (unsigned)A.grid[idx] : 0u;
     }
 #pragma unroll
@@ -816,24 +814,18 @@ res_fine_item(const GridC& g, const ResReq& rq, const ResArgs& A, int item, unsi
 // CTA 0, after the workers' sums: responses, max / ties (storage order), angular covariance sums.
 // s_fsum: the sums copied to shared memory; s_ft: [nAf][4] trig rows of the winning angle.
 __device__ __forceinline__ bool
-res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& f, const double* s_ft, const unsigned* s_fsum,
-                double* s_fr, int T) {
+res_fine_finish(const GridC& g, const ResArgs& A, ResTail& S, const PassDev& f, const double* s_ft, const double* s_fap,
+                const unsigned* s_fsum, double* s_fr, int T) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
   const int nAf = f.nA, nxy = f.nX * f.nY, nposes = nxy * nAf;
-  double* s_dp = &S.tmp4[0][0];   // [nxy] distance penalty of cell c   (nxy <= 64)
-  double* s_ap = &S.tmp4[16][0];  // [nAf] angle penalty of angle a     (nAf <= 64)
+  // odometry penalty: distance part from the per-configuration table (A.dp_fine), angle part from the spec
+  // tables (s_fap: the host evaluated it for this winner's heading)
   if (tid == 0) S.count = 0;
-  if (tid < nxy) {
-    const int iy = tid / f.nX, ix = tid - iy * f.nX;
-    s_dp[tid] = penalty_distance(f, pen, ix, iy);
-  } else if (tid >= 64 && tid < 64 + nAf) {
-    s_ap[tid - 64] = penalty_angle(f, pen, tid - 64);
-  }
   res_team_sync(T);
   double mx = 0.0;
   for (int pose = tid; pose < nposes; pose += T) {
     const int c = pose / nAf, a = pose - c * nAf;
-    const double rr = response_from(f, s_fsum[pose], s_dp[c] * s_ap[a]);
+    const double rr = response_from(f, s_fsum[pose], f.penalize ? __ldg(A.dp_fine + c) * s_fap[a] : 1.0);
     s_fr[pose] = rr;
     mx = rr > mx ? rr : mx;
   }
@@ -841,7 +833,6 @@ res_fine_finish(const GridC& g, const PenaltyC& pen, ResTail& S, const PassDev& 
     const double t = __shfl_xor_sync(0xffffffffu, mx, o);
     mx = t > mx ? t : mx;
   }
-  res_team_sync(T);  // (s_dp / s_ap were read above: tmp4 is reused for the maxima)
   if (lane == 0) S.tmp4[warp][0] = mx;
   res_team_sync(T);
   double best = 0.0;
@@ -1132,7 +1123,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       res_collect(g, A, total, G, bid, rq.maxt, rq.cand, s_tile, s_cnt, s_steps, &s_fail, c_first);
       __syncthreads();
       if (threadIdx.x == 0) pf[2] = res_timer();
-      res_stamp(g, A, rq.cand, s_tile, s_cnt, s_steps, s_slots, &s_nt, s_stage, lane_tab_s);
+      res_stamp(g, A, rq.cand, s_tile, s_cnt, s_steps, s_slots, &s_nt, s_stage, lane_tab_s, pf);
     }
     if (threadIdx.x == 0) pf[3] = res_timer();
     RES_TS(3)
@@ -1176,7 +1167,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         }
         first = false;
         if (!res_sweep_run(g, pen, rq, A, v % rq.nA, v / rq.nA, s_offs, s_minmax,
-                           reinterpret_cast<unsigned*>(dyn), s_wmax) && tid == 0)
+                           reinterpret_cast<unsigned*>(dyn), pf) && tid == 0)
           s_fail = 1;
       }
     }
@@ -1209,7 +1200,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         }
         w = __shfl_sync(0xffffffffu, w, 0);
         const unsigned winw = (unsigned)w;
-        if (winw != YSM_RES_WIN_NOFINE) res_fine_item(g, rq, A, my_item, winw, my_pt, my_valid);
+        if (winw != YSM_RES_WIN_NOFINE) res_fine_item(g, rq, A, my_item, my_pt, my_valid);
         __syncwarp();
         if (lane == 0) res_arrive(bar_fine, false);
       }
@@ -1219,7 +1210,7 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       int status = failed ? RES_ST_FALLBACK : RES_ST_OK;
       int has_fine = 0;
       double* s_spec = reinterpret_cast<double*>(dyn + A.o_off + rq.o_spec);
-      const int spec_doubles = rq.nA + 4 * rq.nA * rq.nAf;
+      const int spec_doubles = rq.nA + 5 * rq.nA * rq.nAf;  // headings | trig rows | fine angle penalties
       if (rq.do_refine && !failed) {
         if (tid == 0) {
           const unsigned long long t0 = res_timer();
@@ -1260,30 +1251,52 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
         res_team_sync(TT);
         RES_TS(6)
         bool stop = s_tail.stop != 0;
+        double* s_cm = reinterpret_cast<double*>(dyn + A.o_off + rq.o_cm);
         if (!stop && s_tail.status == RES_ST_OK) {
-          if (!res_reduce_coarse(rq, A, s_tail, TT) && tid == 0) s_tail.status = RES_ST_FALLBACK;
+          if (!res_reduce_winner(rq, A, s_tail, TT, s_cm) && tid == 0) s_tail.status = RES_ST_FALLBACK;
           res_team_sync(TT);
         }
         RES_TS(7)
+        const bool coarse_ok = !stop && s_tail.status == RES_ST_OK;
+        bool go = false;
+        int a = 0;
         if (!stop && rq.do_refine) {
           // MatchScan goes straight to the fine pass when the coarse pass has ONE winner with a non-zero
           // response: its centre is the winning lattice pose, the heading the atan2(sin, cos) the host tabulated
           // for that coarse angle. Otherwise the host reschedules the match (ties, response expansion).
           const PassOut& po = s_tail.po[0];
-          const bool go = s_tail.status == RES_ST_OK && po.n_ties == 1 && po.best > YSM_KT_TOLERANCE;
-          const int a = go ? po.first_idx % ps.nA : 0;
-          const int cell = go ? po.first_idx / ps.nA : 0;
-          const int wiy = cell / ps.nX, wix = cell - wiy * ps.nX;
-          res_team_sync(TT);  // (status was read by everyone)
+          go = coarse_ok && po.n_ties == 1 && po.best > YSM_KT_TOLERANCE;
+          a = go ? po.first_idx % ps.nA : 0;
+          PassDev& f = s_rq.fine;
+          if (go) {
+            // the winner record for the workers: flat index of the 3 x 3 cells, (cos, sin) of the fine angles
+            const int nxy = f.nX * f.nY;
+            if (tid < nxy) {
+              const int iy = tid / f.nX, ix = tid - iy * f.nX;
+              const double x = -f.offx + (double)ix * f.resx;
+              const double y = -f.offy + (double)iy * f.resy;
+              const int bx = world_to_grid1(po.avg_x + x, f.gox, g.scale) + g.border;
+              const int by = world_to_grid1(po.avg_y + y, f.goy, g.scale) + g.border;
+              A.winrec[tid] = bx + by * g.stride;
+            } else if (tid >= 32 && tid < 32 + 2 * rq.nAf) {
+              const int k = tid - 32, fa = k >> 1;
+              reinterpret_cast<double*>(A.winrec + 64)[k] = s_spec[rq.nA + 4 * ((size_t)a * rq.nAf + fa) + (k & 1)];
+            }
+          }
+          res_team_sync(TT);  // (record written, status read by everyone)
           if (tid == 0) {
-            const unsigned winw = go ? ((unsigned)a | ((unsigned)wix << 8) | ((unsigned)wiy << 20)) : YSM_RES_WIN_NOFINE;
-            res_st_release64(A.win, ((unsigned long long)seq << 32) | winw);
+            res_st_release64(A.win, ((unsigned long long)seq << 32) | (go ? (unsigned)a : YSM_RES_WIN_NOFINE));
             if (!go) s_tail.status = RES_ST_FALLBACK;
-            PassDev& f = s_rq.fine;
             f.cx = po.avg_x;
             f.cy = po.avg_y;
             f.ch = s_spec[a];
-            RES_TS(9)
+          }
+          RES_TS(9)
+        }
+        // the A.9 accumulators, while the workers sum the fine pass
+        if (coarse_ok) res_reduce_cov(rq, A, s_tail, TT, s_cm);
+        if (!stop && rq.do_refine) {
+          if (tid == 0) {
             unsigned hi = 0u;
             if (!res_wait(bar_fine, t4, &hi, A.abort_flag, A.stall_ns)) s_tail.stop = 1;
           }
@@ -1301,7 +1314,8 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
             }
             res_team_sync(TT);
             const double* s_ft = s_spec + rq.nA + (size_t)4 * a * rq.nAf;
-            const bool ok = res_fine_finish(g, pen, s_tail, f, s_ft, s_fsum, s_fr, TT);
+            const double* s_fap = s_spec + rq.nA + (size_t)4 * rq.nA * rq.nAf + (size_t)a * rq.nAf;
+            const bool ok = res_fine_finish(g, A, s_tail, f, s_ft, s_fap, s_fsum, s_fr, TT);
             if (tid == 0) {
               if (ok) s_tail.has_fine = 1;
               else s_tail.status = RES_ST_FALLBACK;
@@ -1320,7 +1334,6 @@ k_match_resident(GridC g, PenaltyC pen, ResArgs A) {
       // reset the per-request accumulators for the next request
       const int ncell = ps.nX * ps.nY;
       for (int i = tid; i < ncell; i += T) A.cellmax[i] = 0ull;
-      if (tid == 0) *A.passmax = 0.0;
     }
     // ---- barrier 3: the fine pass has read the grid; zero the tiles this CTA stamped ----------------
     t5 += (unsigned)G;
