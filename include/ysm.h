@@ -86,6 +86,15 @@ typedef struct ysm_batch {
                                   single-query path keeps tagged scans in a device-resident store, so the running scans
                                   of sequential mapping (graph_slam.py:326) are uploaded once, not once per match.
                                   0 = untagged (always uploaded). */
+  const int32_t *scan_raw_count; /* [n_scans] host, or NULL: RAW range readings of every scan (before the min_range /
+                                  range_threshold filter). Karto's MatchScan returns early only for a scan without any
+                                  range reading; a query with beams but no in-range reading goes through the whole
+                                  schedule with an empty lookup table: GetResponse returns 0 for every pose, so every
+                                  pose ties in every pass (all response expansions run) and the result is the ordered
+                                  average of the search lattices -- response 0, a pose equal to the search centre up to
+                                  rounding, covariance 500 / 500 / 4 coarse_res^2 (1000 fine_res^2 after a fine pass).
+                                  That schedule has no grid lookup at all; the library's host runtime evaluates it.
+                                  NULL: every scan without point readings is taken to have no beams (early return). */
 } ysm_batch;
 
 /* 128-byte result record (what Wrapper.match_scan returns: response, best_pose, covariance). */

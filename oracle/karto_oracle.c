@@ -552,14 +552,29 @@ static double correlate_scan(ko_matcher *m, const double *qpts, int nq, const do
 static int match_schedule(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
                           int do_penalize, int do_refine, double *out);
 
+/* n_raw = number of RAW range readings of the query scan. Karto's early return tests that count
+ * (pScan->GetNumberOfRangeReadings() == 0), not the number of filtered point readings: a scan with beams but
+ * none inside [min_range, range_threshold] runs the schedule on an empty lookup table, GetResponse divides
+ * 0.0 by (0 * 100), every response is NaN, nothing compares equal to the best response (-1) and CorrelateScan
+ * throws "Unable to find best position" (rc != 0 here). */
+int ko_match_raw(ko_matcher *m, const double *query_pts, int nq, int n_raw, const double *query_pose,
+                 const double *base_pts, const int *base_counts, int nbase, int do_penalize,
+                 int do_refine, double *out);
+
 int ko_match(ko_matcher *m, const double *query_pts, int nq, const double *query_pose,
              const double *base_pts, const int *base_counts, int nbase, int do_penalize,
              int do_refine, double *out) {
+  return ko_match_raw(m, query_pts, nq, nq, query_pose, base_pts, base_counts, nbase, do_penalize, do_refine, out);
+}
+
+int ko_match_raw(ko_matcher *m, const double *query_pts, int nq, int n_raw, const double *query_pose,
+                 const double *base_pts, const int *base_counts, int nbase, int do_penalize,
+                 int do_refine, double *out) {
   double cov[9];
   memset(cov, 0, sizeof(cov));
   cov[0] = cov[4] = cov[8] = 1.0; /* Matrix3 default-constructs... the wrapper hands in identity */
   m->last_num_passes = 0;
-  if (nq == 0) {
+  if (n_raw == 0 || (nq == 0 && n_raw < 0)) {
     out[0] = 0.0;
     out[1] = query_pose[0]; out[2] = query_pose[1]; out[3] = query_pose[2];
     cov[0] = MAX_VARIANCE;

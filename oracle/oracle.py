@@ -67,6 +67,8 @@ def lib():
         L.ko_find_valid_points.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_uint8)]
         L.ko_match.restype = C.c_int
         L.ko_match.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, ip, C.c_int, C.c_int, C.c_int, dp]
+        L.ko_match_raw.restype = C.c_int
+        L.ko_match_raw.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, dp, dp, ip, C.c_int, C.c_int, C.c_int, dp]
         L.ko_create_map.restype = C.c_void_p
         L.ko_create_map.argtypes = [C.POINTER(KoParams), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
                                     C.c_double]
@@ -200,15 +202,16 @@ class KartoOracle:
                                  float(angle_offset), float(angle_res))
         return self.lookup()
 
-    def match(self, query_pts, query_pose, base_pts_list, do_penalize=True, do_refine=False):
-        """Returns (response, (x, y, heading), cov 3x3)."""
+    def match(self, query_pts, query_pose, base_pts_list, do_penalize=True, do_refine=False, n_raw=None):
+        """Returns (response, (x, y, heading), cov 3x3). n_raw: RAW range readings of the query (default: as
+        many as point readings); beams without any in-range reading raise like Karto."""
         q = np.ascontiguousarray(query_pts, dtype=np.float64).reshape(-1, 2)
         pose = np.ascontiguousarray(query_pose, dtype=np.float64)
         cat, counts = self._pack(base_pts_list)
         out = np.zeros(13, dtype=np.float64)
         qq = q if len(q) else np.zeros((1, 2))
-        rc = lib().ko_match(self._h, _dp(qq), len(q), _dp(pose), _dp(cat), _ip(counts), len(counts),
-                            int(do_penalize), int(do_refine), _dp(out))
+        rc = lib().ko_match_raw(self._h, _dp(qq), len(q), len(q) if n_raw is None else int(n_raw), _dp(pose), _dp(cat),
+                                _ip(counts), len(counts), int(do_penalize), int(do_refine), _dp(out))
         if rc != 0:
             raise RuntimeError("Mapper FATAL ERROR - Unable to find best position")
         return float(out[0]), (float(out[1]), float(out[2]), float(out[3])), out[4:].reshape(3, 3).copy()

@@ -47,7 +47,7 @@ def _header_struct_fields(name):
 def test_struct_layouts_match_header():
     assert C.sizeof(_capi.YsmParams) == 11 * 8 + 4 + 4 + 8 + 4 + 4
     assert C.sizeof(_capi.YsmDims) == 10 * 4 + 8
-    assert C.sizeof(_capi.YsmBatch) == 4 + 4 + 8 + 7 * 8 + 4 * 4 + 8
+    assert C.sizeof(_capi.YsmBatch) == 4 + 4 + 8 + 7 * 8 + 4 * 4 + 8 + 8
     assert _capi.RESULT_DTYPE.itemsize == 128
     for cls, name in ((_capi.YsmParams, "ysm_params"), (_capi.YsmBatch, "ysm_batch"), (_capi.YsmDims, "ysm_dims"),
                       (_capi.YsmOccScans, "ysm_occ_scans"), (_capi.YsmOccInfo, "ysm_occ_info"),

@@ -649,3 +649,43 @@ def test_exact_candidate_lists_equal_the_searched_build(world):
             assert (ga == gb).all()
         assert max(int(ga.max()) for ga in grids[0]) == 100  # (a degenerate match has an empty grid)
         _assert_parity(recs[0], scenarios.oracle_results(cfg, b, True, True), "candidate lists")
+
+
+def test_beams_without_an_in_range_reading(world):
+    """Karto's MatchScan returns early only for a scan WITHOUT range readings. A query that has beams but none
+    inside [min_range, range_threshold] runs the whole schedule on an empty lookup table: every pose of every
+    pass ties at response 0 (all three response expansions, then the fine pass). ysm_batch::scan_raw_count carries
+    the raw beam count; the result must equal the oracle's run of that schedule, bit for bit."""
+    import scenarios
+    from oracle.oracle import KartoOracle
+    from yag_slam_b200 import karto_compat as kc
+    from yag_slam_b200 import synth
+    from yag_slam_b200.matcher import pack_pool
+    rng = np.random.default_rng(9)
+    base = synth.scan_points(world, (0.0, 0.0, 0.0), 360, rng)
+    pool, starts, counts = pack_pool([np.zeros((0, 2)), base])
+    one = (np.array([0], np.int32), np.array([[1.0, -2.0, 0.3]]), np.array([0, 1], np.int32), np.array([1], np.int32))
+    for cfg in (None, LOOP, dict(use_response_expansion=False)):
+        m = _matcher(cfg, max_slots=2)
+        o = KartoOracle(cfg)
+        for fine in (False, True):
+            out = m.match_pool(pool, starts, counts, *one, True, fine, scan_raw_count=np.array([360, 360], np.int32))
+            r, p, cov = o.match(np.zeros((0, 2)), (1.0, -2.0, 0.3), [base], True, fine, n_raw=360)
+            _assert_parity(out, np.concatenate([[r], p, cov.reshape(-1)]), "beams without readings %r fine=%s" % (cfg, fine))
+            assert out["n_passes"][0] == (4 if (cfg or {}).get("use_response_expansion", True) else 1) + int(fine)
+            # no beams at all (or no raw counts given): MatchScan's early return
+            for raw in (np.array([0, 360], np.int32), None):
+                e = m.match_pool(pool, starts, counts, *one, True, fine, scan_raw_count=raw)
+                assert e["response"][0] == 0.0 and (e["x"][0], e["y"][0], e["heading"][0]) == (1.0, -2.0, 0.3)
+                assert e["cov"][0][0] == 500.0 and e["n_passes"][0] == 0
+        m.close()
+    # through the reference-facing wrapper: every beam beyond the range threshold
+    lp = synth.laser_params(360)
+    cfg = kc.LaserScanConfig(lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], "")
+    b = kc.LocalizedRangeScan(cfg, synth.cast_scan(world, (0.0, 0.0, 0.0), 360, rng), kc.Pose2(0, 0, 0), kc.Pose2(0, 0, 0), 0, 0.0)
+    q = kc.LocalizedRangeScan(cfg, np.full(360, 25.0), kc.Pose2(1.0, -2.0, 0.3), kc.Pose2(1.0, -2.0, 0.3), 1, 0.0)
+    w = kc.Wrapper(kc.ScanMatcherConfig())
+    res = w.match_scan(q, [b], True, True)
+    r, p, cov = KartoOracle(None).match(np.zeros((0, 2)), (1.0, -2.0, 0.3), [b.point_readings()], True, True, n_raw=360)
+    assert res.response == r and (res.best_pose.x, res.best_pose.y, res.best_pose.yaw) == tuple(p)
+    assert np.allclose(res.covariance, cov, rtol=1e-12)

@@ -35,7 +35,8 @@ class YsmBatch(C.Structure):
         ("pool_xy", C.c_void_p), ("scan_start", C.c_void_p), ("scan_count", C.c_void_p),
         ("query_scan", C.c_void_p), ("query_pose", C.c_void_p), ("base_ptr", C.c_void_p),
         ("base_idx", C.c_void_p), ("do_penalize", C.c_int32), ("do_refine", C.c_int32),
-        ("pool_on_device", C.c_int32), ("_pad", C.c_int32), ("scan_tag", C.c_void_p)]
+        ("pool_on_device", C.c_int32), ("_pad", C.c_int32), ("scan_tag", C.c_void_p),
+        ("scan_raw_count", C.c_void_p)]
 
 
 class YsmOccScans(C.Structure):

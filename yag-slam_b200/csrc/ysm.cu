@@ -1548,6 +1548,72 @@ extern "C" int ysm_debug_ping(ysm_handle* h, int32_t n, double* rtt_us) {
   return YSM_OK;
 }
 
+// MatchScan for a query scan that has range readings but not one point reading: the
+// lookup table is empty, GetResponse returns 0 for every pose ("if (nPoints == 0) return response"), so in
+// every CorrelateScan pass all poses tie with the best response 0 and the result is the ordered average of the
+// whole search lattice; response expansion (if enabled) widens the angle window three times, a fine pass
+// follows when asked. There is not a single grid lookup in this schedule -- nothing for the GPU to do -- so the
+// host runtime walks the lattices in Karto's storage order (y, x, angle) with the same additions.
+static void zero_point_schedule(const ysm_handle* h, const double* pose, bool do_refine, MatchState& s) {
+  auto tie_average = [](const double* center, double offx, double offy, double resx, double resy, double angle_offset,
+                        double angle_res, double* mean) {
+    const int nX = n_steps(offx, resx), nY = n_steps(offy, resy), nA = n_steps(angle_offset, angle_res);
+    const double startX = -offx, startY = -offy, start_angle = center[2] - angle_offset;
+    std::vector<double> hc((size_t)nA), hs((size_t)nA);
+    for (int a = 0; a < nA; a++) {
+      const double hn = h_normalize_angle(start_angle + (double)(uint32_t)a * angle_res);
+      hc[a] = cos(hn);
+      hs[a] = sin(hn);
+    }
+    double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+    for (int iy = 0; iy < nY; iy++) {
+      const double ny = center[1] + (startY + (double)(uint32_t)iy * resy);
+      for (int ix = 0; ix < nX; ix++) {
+        const double nx = center[0] + (startX + (double)(uint32_t)ix * resx);
+        for (int a = 0; a < nA; a++) {
+          sx += nx;
+          sy += ny;
+          tx += hc[a];
+          ty += hs[a];
+        }
+      }
+    }
+    const double cnt = (double)((long long)nX * nY * nA);
+    mean[0] = sx / cnt;
+    mean[1] = sy / cnt;
+    mean[2] = atan2(ty / cnt, tx / cnt);
+    return nX * nY * nA;
+  };
+  const double csx = 0.5 * (h->side - 1) * h->res_eff, crx = 2 * h->res_eff;
+  double angle_offset = h->prm.coarse_search_angle_offset;
+  double mean[3] = {pose[0], pose[1], pose[2]};
+  int passes = 0, ties = 0;
+  for (int stage = 0; stage < 4; stage++) {
+    ties = tie_average(pose, csx, csx, crx, crx, angle_offset, h->prm.coarse_angle_resolution, mean);
+    passes++;
+    if (!h->prm.use_response_expansion || stage == 3) break;
+    angle_offset += 20 * KT_PI_180;  // (best == 0: the next response expansion)
+  }
+  memset(s.cov, 0, sizeof(s.cov));
+  s.cov[0] = MAX_VARIANCE;  // ComputePositionalCovariance with best < KT_TOLERANCE
+  s.cov[4] = MAX_VARIANCE;
+  s.cov[8] = 4 * h_square(h->prm.coarse_angle_resolution);
+  if (do_refine) {
+    double fmean[3];
+    ties = tie_average(mean, crx * 0.5, crx * 0.5, h->res_eff, h->res_eff, 0.5 * h->prm.coarse_angle_resolution,
+                       h->prm.fine_search_angle_resolution, fmean);
+    passes++;
+    mean[0] = fmean[0]; mean[1] = fmean[1]; mean[2] = fmean[2];
+    s.cov[8] = 1000 * h_square(h->prm.fine_search_angle_resolution);  // ComputeAngularCovariance with norm == 0
+  }
+  s.mean[0] = mean[0]; s.mean[1] = mean[1]; s.mean[2] = mean[2];
+  s.best = 0.0;
+  s.n_passes = passes;
+  s.n_ties = ties;
+  s.status = YSM_OK;
+  s.stage = 5;
+}
+
 // --------------------------------------------------------------------------------------------
 static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, cudaStream_t st) {
   if (!h || !b || !out) return YSM_EINVAL;
@@ -1701,7 +1767,11 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       work_cap += std::min<long long>((long long)tiles_per_grid, mc * tiles_per_stamp);
       m.vpx = s.pose[0]; m.vpy = s.pose[1];
       m.gox = s.gox; m.goy = s.goy;
-      if (s.P == 0) {
+      if (s.P == 0 && b->scan_raw_count && b->scan_raw_count[s.q] > 0) {
+        // Beams, but none inside [min_range, range_threshold]: Karto does NOT return early (it tests the number
+        // of RANGE readings) -- see zero_point_schedule.
+        zero_point_schedule(h, s.pose, b->do_refine != 0, s);
+      } else if (s.P == 0) {
         // scan has no readings (MatchScan early return)
         s.stage = 5;
         s.cov[0] = MAX_VARIANCE;
@@ -2720,49 +2790,61 @@ extern "C" int ysm_debug_copy_offsets(ysm_handle* h, int32_t match, int32_t* out
 }
 
 // --------------------------------------------------------------------------------------------
-// run_raytracing_sweep (reference yag_slam/raytracing.py:90-92) for many start cells
+// run_raytracing_sweep (reference yag_slam/raytracing.py:90-92) for many start cells.
+// The reference's caller does one sweep per centroid (yag_slam/splicing.py:90-94): no allocation on the call --
+// a per-device workspace (map copy, trig table, starts, rays, pinned staging) grows on demand and is reused.
+namespace {
+struct RayWorkspace {
+  std::mutex mu;
+  DevBuf img, cs, starts, out;
+  PinBuf h_in;  // cos/sin table + starts, staged for one async copy
+};
+RayWorkspace g_ray_ws[64];
+}  // namespace
+
 extern "C" int ysm_raytrace(const uint8_t* img, int32_t hh, int32_t ww, int32_t img_on_device,
                             const double* angles_deg, int32_t n_angles, const double* starts_xy,
                             int32_t n_starts, float* out, int device, void* stream) {
   if (!img || !angles_deg || !starts_xy || !out || hh < 3 || ww < 3 || n_angles < 0 || n_starts < 0)
     return fail(nullptr, YSM_EINVAL, "ysm_raytrace: bad argument");
   if (n_angles == 0 || n_starts == 0) return YSM_OK;
+  if (device < 0 || device >= 64) return fail(nullptr, YSM_EINVAL, "ysm_raytrace: bad device index");
   const long long n_rays = (long long)n_angles * n_starts;
   if (n_rays > 0x7fffffffLL / 5) return fail(nullptr, YSM_EUNSUP, "ysm_raytrace: too many rays in one call");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(nullptr, YSM_ECUDA, cudaGetErrorString(e));
-  ysm_quiesce_device(device);
-  std::vector<double> cs((size_t)2 * n_angles);
-  for (int a = 0; a < n_angles; a++) {
-    const double ang = angles_deg[a] * (3.141592653589793 / 180.0);  // np.deg2rad
-    cs[2 * a] = cos(ang);
-    cs[2 * a + 1] = sin(ang);
-  }
-  uint8_t* d_img = nullptr;
-  double *d_cs = nullptr, *d_starts = nullptr;
-  float* d_out = nullptr;
-  int rc = YSM_OK;
+  RayWorkspace& W = g_ray_ws[device];
+  std::lock_guard<std::mutex> lk(W.mu);
+  const size_t in_bytes = ((size_t)2 * n_angles + (size_t)2 * n_starts) * 8;
+  const bool grow = (!img_on_device && (size_t)hh * ww > W.img.cap) || (size_t)2 * n_angles * 8 > W.cs.cap ||
+                    (size_t)n_starts * 16 > W.starts.cap || (size_t)n_rays * 20 > W.out.cap || in_bytes > W.h_in.cap;
+  if (grow) ysm_quiesce_device(device);  // (allocations below must not wait for a resident latency kernel)
   do {
-    if (!img_on_device) {
-      if ((e = cudaMalloc((void**)&d_img, (size_t)hh * ww)) != cudaSuccess) break;
-      if ((e = cudaMemcpyAsync(d_img, img, (size_t)hh * ww, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if (!img_on_device && (e = W.img.ensure((size_t)hh * ww)) != cudaSuccess) break;
+    if ((e = W.cs.ensure((size_t)2 * n_angles * 8)) != cudaSuccess) break;
+    if ((e = W.starts.ensure((size_t)n_starts * 16)) != cudaSuccess) break;
+    if ((e = W.out.ensure((size_t)n_rays * 20)) != cudaSuccess) break;
+    if ((e = W.h_in.ensure(in_bytes)) != cudaSuccess) break;
+    double* cs = (double*)W.h_in.p;
+    for (int a = 0; a < n_angles; a++) {
+      const double ang = angles_deg[a] * (3.141592653589793 / 180.0);  // np.deg2rad
+      cs[2 * a] = cos(ang);
+      cs[2 * a + 1] = sin(ang);
     }
-    if ((e = cudaMalloc((void**)&d_cs, cs.size() * 8)) != cudaSuccess) break;
-    if ((e = cudaMalloc((void**)&d_starts, (size_t)n_starts * 16)) != cudaSuccess) break;
-    if ((e = cudaMalloc((void**)&d_out, (size_t)n_rays * 5 * 4)) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync(d_cs, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync(d_starts, starts_xy, (size_t)n_starts * 16, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-    k_raywalk<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(img_on_device ? img : d_img, hh, ww, d_cs, n_angles,
-                                                                d_starts, (int)n_rays, d_out);
+    memcpy(cs + 2 * (size_t)n_angles, starts_xy, (size_t)n_starts * 16);
+    if (!img_on_device &&
+        (e = cudaMemcpyAsync(W.img.p, img, (size_t)hh * ww, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(W.cs.p, cs, (size_t)2 * n_angles * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(W.starts.p, cs + 2 * (size_t)n_angles, (size_t)n_starts * 16, cudaMemcpyHostToDevice, st)) !=
+        cudaSuccess) break;
+    k_raywalk<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(img_on_device ? img : (const uint8_t*)W.img.p, hh, ww,
+                                                                (const double*)W.cs.p, n_angles, (const double*)W.starts.p,
+                                                                (int)n_rays, (float*)W.out.p);
     if ((e = cudaGetLastError()) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync(out, d_out, (size_t)n_rays * 5 * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(out, W.out.p, (size_t)n_rays * 5 * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
     e = cudaStreamSynchronize(st);
   } while (0);
-  if (e != cudaSuccess) rc = fail(nullptr, YSM_ECUDA, std::string("ysm_raytrace: ") + cudaGetErrorString(e));
-  if (d_img) cudaFree(d_img);
-  if (d_cs) cudaFree(d_cs);
-  if (d_starts) cudaFree(d_starts);
-  if (d_out) cudaFree(d_out);
-  return rc;
+  if (e != cudaSuccess) return fail(nullptr, YSM_ECUDA, std::string("ysm_raytrace: ") + cudaGetErrorString(e));
+  return YSM_OK;
 }

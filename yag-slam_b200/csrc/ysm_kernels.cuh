@@ -103,15 +103,6 @@ __device__ __forceinline__ uint32_t vmax4_lt128(uint32_t a, uint32_t b) {
 // memory pointer chase), then every segment [t_k, t_k+1) is kept iff the side test ss >= 0
 // (parallel). Output: the match's occupied cells in Karto's processing order.
 // ---------------------------------------------------------------------------------------------
-__device__ unsigned long long g_fv_ts[16];  // developer tracing: %globaltimer inside find_valid (CTA 0, thread 0)
-__device__ int g_fv_trace = 0;
-#define YSM_FVTS(k)                                                        \
-  if (g_fv_trace && vbx == 0 && threadIdx.x == 0) {                        \
-    unsigned long long t_;                                                 \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                 \
-    g_fv_ts[k] = t_;                                                       \
-  }
-
 // warp-aggregated bump of the 16-bit counter of tile t (t < 0: this lane has none): lanes naming the same
 // tile are served by ONE shared-memory atomic; returns this lane's slot = old counter value + its rank
 __device__ __forceinline__ unsigned tile_counter_bump(unsigned* s_cnt, int t, int lane) {
@@ -168,7 +159,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
   // dependent loads are LDS instead of L2 round trips
   double* s_px = reinterpret_cast<double*>(smem_raw + (((size_t)nwarps * 4 * pmax + 16 * (size_t)nbase_max + 4 * (size_t)nbitw + 15) & ~(size_t)15)) + (size_t)warp * 2 * pmax;
   double* s_py = s_px + pmax;
-  YSM_FVTS(0)
   for (int i = threadIdx.x; i < nbitw; i += blockDim.x) s_bits[i] = 0u;
   if (threadIdx.x == 0) s_tile_total = 0;
   __syncthreads();
@@ -194,7 +184,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     }
   }
   __syncthreads();
-  YSM_FVTS(1)
   for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
     const int off = s_dir[2 * nbase_max + b];
     const int n = s_dir[b];
@@ -221,7 +210,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
         s_next[i] = (unsigned short)j;
       }
       __syncwarp();
-      YSM_FVTS(2)
       int ntrig = 0;
       if (lane == 0) {
         int t = 0;
@@ -232,7 +220,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       }
       ntrig = __shfl_sync(0xffffffffu, ntrig, 0);
       __syncwarp();
-      YSM_FVTS(3)
       for (int k = lane; k < ntrig - 1; k += 32) {
         const int f = s_trig[k], c = s_trig[k + 1];
         const double fx = YSM_PX(f), fy = YSM_PY(f);
@@ -267,10 +254,8 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     for (int o = 16; o > 0; o >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
     if (lane == 0) s_scan_emit[b] = emitted;
     __syncwarp();
-    YSM_FVTS(4)
   }
   __syncthreads();
-  YSM_FVTS(5)
   // ordered compaction (scan order, then point order)
   for (int b = warp; b < nbase && warp < nwarps; b += nwarps) {
     int dst = 0;
@@ -287,7 +272,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       dst += __popc(bal);
     }
   }
-  YSM_FVTS(6)
   int tot = 0;
   for (int b = 0; b < nbase; b++) tot += s_scan_emit[b];
   if (threadIdx.x == 0) cell_count[vbx] = tot;
@@ -420,7 +404,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       work[pos++] = make_int2(vbx, i * 4 + (bit >> 3));
     }
   }
-  YSM_FVTS(7)
   // bounding box of every group of 32 consecutive cells (scan order keeps them spatially close)
   __threadfence_block();
   const uint32_t* mcells = cells + m.cells_off;
@@ -440,7 +423,6 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     }
     if (lane == 0) gbox[m.gbox_off + (g0 >> 5)] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   }
-  YSM_FVTS(8)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -178,7 +178,8 @@ class Wrapper(object):
             arr = dict(counts=np.zeros(nb + 1, np.int32), starts=np.zeros(nb + 1, np.int32),
                        qidx=np.zeros(1, np.int32), pose=np.zeros((1, 3), np.float64),
                        bptr=np.array([0, nb], np.int32), bidx=np.arange(1, nb + 1, dtype=np.int32),
-                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), tags=np.zeros(nb + 1, np.uint64))
+                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), tags=np.zeros(nb + 1, np.uint64),
+                       raw=np.zeros(nb + 1, np.int32))
             arr["resf"] = arr["res"].view(np.float64).reshape(-1)  # the 128-B record as 16 doubles
             b.n_matches, b.n_scans = 1, nb + 1
             b.scan_start, b.scan_count = arr["starts"].ctypes.data, arr["counts"].ctypes.data
@@ -186,6 +187,7 @@ class Wrapper(object):
             b.base_ptr, b.base_idx = arr["bptr"].ctypes.data, (arr["bidx"].ctypes.data if nb else None)
             b.pool_on_device = 0
             b.scan_tag = arr["tags"].ctypes.data
+            b.scan_raw_count = arr["raw"].ctypes.data
             c = self._one[nb] = (b, arr, C.byref(b), arr["res"].ctypes.data)
         b, arr, bref, resp = c
         pool = self._pool
@@ -221,6 +223,7 @@ class Wrapper(object):
             counts[i] = n
             tags[i] = tag
         arr["pose"][0] = query.sensor_pose()
+        arr["raw"][0] = len(query.ranges)  # (Karto tests the RAW reading count for its early return)
         b.pool_xy = pool.ctypes.data
         b.n_points = len(pool)
         b.do_penalize, b.do_refine = (1 if penalty else 0), (1 if do_fine else 0)
@@ -237,8 +240,10 @@ class Wrapper(object):
         pts.extend(s.point_readings() for s in base_scans)
         pool, starts, counts = pack_pool(pts)
         nb = len(base_scans)
+        raw = np.array([len(query.ranges)] + [len(s.ranges) for s in base_scans], np.int32)
         res = self._m.match_pool(pool, starts, counts, np.zeros(1, np.int32), np.array([query.sensor_pose()]),
-                                 np.array([0, nb], np.int32), np.arange(1, nb + 1, dtype=np.int32), penalty, do_fine)
+                                 np.array([0, nb], np.int32), np.arange(1, nb + 1, dtype=np.int32), penalty, do_fine,
+                                 scan_raw_count=raw)
         r = res[0]
         return MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
                            Pose2(float(r["x"]), float(r["y"]), float(r["heading"])))
@@ -262,8 +267,9 @@ class Wrapper(object):
             base_ptr.append(len(base_idx))
         pool, starts, counts = pack_pool([s.point_readings() for s in scans])
         poses = np.array([q.sensor_pose() for q in queries], dtype=np.float64).reshape(-1, 3)
+        raw = np.array([len(s.ranges) for s in scans], np.int32)
         res = self.batch_matcher(len(qidx)).match_pool(pool, starts, counts, qidx, poses, base_ptr, base_idx, penalty,
-                                                       do_fine)
+                                                       do_fine, scan_raw_count=raw)
         return [MatchResult(float(r["response"]), r["cov"].reshape(3, 3).copy(),
                             Pose2(float(r["x"]), float(r["y"]), float(r["heading"]))) for r in res]
 

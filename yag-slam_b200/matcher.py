@@ -96,7 +96,7 @@ class ScanMatcherB200(object):
         return np.array(out[:], dtype=np.float64)
 
     def match_pool(self, pool_xy, scan_start, scan_count, query_scan, query_pose, base_ptr, base_idx,
-                   penalty=True, do_fine=False, stream=0, out=None, scan_tag=None):
+                   penalty=True, do_fine=False, stream=0, out=None, scan_tag=None, scan_raw_count=None):
         """Batched Wrapper.match_scan over a pool of scans (see ysm_batch in include/ysm.h).
 
         pool_xy: (n_points, 2) float64 numpy array, or a CUDA tensor already resident in HBM.
@@ -140,6 +140,11 @@ class ScanMatcherB200(object):
             if len(scan_tag) != len(scan_start):
                 raise ValueError("scan_tag must have one entry per scan")
             b.scan_tag = scan_tag.ctypes.data
+        if scan_raw_count is not None:  # raw beams per scan: Karto's "beams but no in-range reading" case raises
+            scan_raw_count = np.ascontiguousarray(scan_raw_count, dtype=np.int32)
+            if len(scan_raw_count) != len(scan_start):
+                raise ValueError("scan_raw_count must have one entry per scan")
+            b.scan_raw_count = scan_raw_count.ctypes.data
         if out is None:
             out = np.zeros(n, dtype=_capi.RESULT_DTYPE)
         elif (not isinstance(out, np.ndarray) or out.dtype != _capi.RESULT_DTYPE or out.ndim != 1 or len(out) < n
