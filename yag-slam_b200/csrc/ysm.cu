@@ -2334,7 +2334,12 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       // ---- K2 offsets (tables of the passes the host scheduled) ------------------------------------
       if (pl.cmax_elems > 0) CK(cudaMemsetAsync(h->d_cellmax.p, 0, pl.cmax_elems * 8, st));
       const int ntab_host = spec ? pl.first_spec_table : (int)pl.tab.size();
-      {
+      // The pruned sweep computes its own lookup offsets (ComputeOffsets fused): the tables are only needed by
+      // the unpruned lattice sweep, the fine sweep / angular covariance, and the offset introspection of tests.
+      const bool will_prune = !pl.pa.empty() && !(h->debug & YSM_DEBUG_NO_PRUNE) &&
+                              (long long)pl.pa.size() * ((pl.max_lat_ny + 27) / 28) * ((pl.max_lat_nx + 31) / 32) >= h->num_sms * 2;
+      const bool need_tables = !will_prune || nhostfine > 0 || (h->debug & YSM_DEBUG_KEEP_GRIDS);
+      if (need_tables) {
         int maxwork = 1;
         for (int t = 0; t < ntab_host; t++) maxwork = std::max(maxwork, pl.tab[t].nA * (pl.tab[t].Ppad / 4));
         dim3 grid((maxwork + 255) / 256, (unsigned)ntab_host);
