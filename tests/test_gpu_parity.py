@@ -630,23 +630,24 @@ def scenarios_scan_points(world, pose, P, rng, sense_at=None):
 
 
 def test_exact_candidate_lists_equal_the_searched_build(world):
-    """The grid build with exact per-tile candidate lists (k_find_valid's 16-bit counters / cursors)
-    gives byte-identical grids and identical records to the build that searches the cell list per tile
-    (YSM_DEBUG_NO_CANDLISTS), on the sequential and the loop configuration."""
+    """The grid build with exact per-tile candidate lists (k_find_valid's 16-bit counters / cursors), stamped by
+    k_tile_stamp_lists (per-column-group / per-tile-half step lists) or by k_tile_stamp's per-candidate loop
+    (YSM_DEBUG_NO_HALF_LISTS), gives byte-identical grids and identical records to the build that searches the
+    cell list per tile (YSM_DEBUG_NO_CANDLISTS), on the sequential and the loop configuration."""
     import scenarios
     from yag_slam_b200 import _capi
     for cfg, nb, P in ((None, 10, 720), (LOOP, 10, 360), (dict(resolution=0.02, smear_deviation=0.05), 4, 360)):
         b = scenarios.make_batch(world, 40, P, nb, 91, perturb=(0.1, 0.05), degenerate_frac=0.1)
         grids, recs = [], []
-        for flags in (0, _capi.DEBUG_NO_CANDLISTS):
+        for flags in (0, _capi.DEBUG_NO_HALF_LISTS, _capi.DEBUG_NO_CANDLISTS):
             m = _matcher(cfg, max_slots=48, lanes=1)
             m.set_debug(flags | _capi.DEBUG_KEEP_GRIDS)
             recs.append(_run(m, b, True, True).copy())
             grids.append([m.debug_grid(i) for i in (0, 7, 39)])
             m.close()
-        assert recs[0].tobytes() == recs[1].tobytes()
-        for ga, gb in zip(*grids):
-            assert (ga == gb).all()
+        assert recs[0].tobytes() == recs[1].tobytes() == recs[2].tobytes()
+        for ga, gb, gc in zip(*grids):
+            assert (ga == gb).all() and (ga == gc).all()
         assert max(int(ga.max()) for ga in grids[0]) == 100  # (a degenerate match has an empty grid)
         _assert_parity(recs[0], scenarios.oracle_results(cfg, b, True, True), "candidate lists")
 

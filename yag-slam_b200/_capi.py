@@ -16,6 +16,7 @@ PARAM_FIELDS = [
 
 YSM_OK, YSM_EINVAL, YSM_ECUDA, YSM_ENOMEM, YSM_EMATCH, YSM_EUNSUP = 0, -1, -2, -3, -4, -5
 DEBUG_KEEP_GRIDS, DEBUG_TIME_KERNELS, DEBUG_NO_PRUNE, DEBUG_NO_SPECULATE, DEBUG_NO_MEGA, DEBUG_NO_CANDLISTS = 1, 2, 4, 8, 16, 32
+DEBUG_NO_HALF_LISTS = 64
 
 
 class YsmParams(C.Structure):

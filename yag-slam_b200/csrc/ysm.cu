@@ -304,6 +304,8 @@ struct ysm_handle {
   int tnx = 0, rm_words = 0;
   uint8_t* d_kernel = nullptr;
   uint16_t* d_stamp_tab = nullptr;  // pre-shifted stamp rows of k_tile_stamp: u16 [8][K][Wt]
+  double* d_dpc = nullptr;          // coarse distance-penalty table [nY][nX] of k_sweep_pruned (made at the first batch)
+  int dpc_nx = 0;
   std::vector<uint8_t> h_kernel;
   std::string err;
   int debug = 0;
@@ -419,6 +421,7 @@ static cudaError_t init_kernel_attrs(int device) {
   cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e != cudaSuccess) return e;
   const void* fns[] = {(const void*)k_find_valid,    (const void*)k_stamp_order, (const void*)k_tile_stamp,
+                       (const void*)k_tile_stamp_lists,
                        (const void*)k_sweep_pruned,  (const void*)k_sweep_lattice, (const void*)k_match_small,
                        (const void*)k_match_resident};
   for (const void* fn : fns) {
@@ -700,6 +703,7 @@ extern "C" void ysm_destroy(ysm_handle* h) {
   if (h->d_issued) cudaFree(h->d_issued);
   if (h->d_kernel) cudaFree(h->d_kernel);
   if (h->d_stamp_tab) cudaFree(h->d_stamp_tab);
+  if (h->d_dpc) cudaFree(h->d_dpc);
   DevBuf* bufs[] = {&h->d_pool, &h->d_scan_start, &h->d_scan_count, &h->d_base_idx, &h->d_matches,
                     &h->d_cells, &h->d_ptcell, &h->d_cellcount, &h->d_gbox, &h->d_work, &h->d_workcount,
                     &h->d_tables, &h->d_passes,
@@ -1691,6 +1695,17 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
   const int tiles_per_stamp = tps1 * tps1;
   const double csx = 0.5 * (h->side - 1) * h->res_eff;
   const double crx = 2 * h->res_eff;
+  if (!h->d_dpc) {
+    // distance half of the odometry penalty for the coarse lattice: it depends on the matcher's configuration
+    // only, and its f64 division per pose is the dearest thing in the sweep's epilogue
+    const int nX = n_steps(csx, crx);
+    std::vector<double> dp((size_t)nX * nX);
+    for (int iy = 0; iy < nX; iy++)
+      for (int ix = 0; ix < nX; ix++) dp[(size_t)iy * nX + ix] = h_penalty_distance(csx, crx, csx, crx, ix, iy, h->pen);
+    CK(cudaMalloc((void**)&h->d_dpc, dp.size() * 8));
+    CK(cudaMemcpy(h->d_dpc, dp.data(), dp.size() * 8, cudaMemcpyHostToDevice));
+    h->dpc_nx = nX;
+  }
   const int S = h->static_grid ? 4096 : h->slots;  // matches per wave
   const int nAf = n_steps(0.5 * h->prm.coarse_angle_resolution, h->prm.fine_search_angle_resolution);
 
@@ -2121,6 +2136,14 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       const size_t ksmem = tile_stamp_smem(g.K, g.Wt, 8);
       if (ksmem > 200 * 1024) return fail(h, YSM_EUNSUP, "smear kernel too large for the stamping kernel");
       const long long ctas = std::max<long long>(1, std::min<long long>(work_cap, (long long)h->num_sms * 8));
+      const size_t lsmem = tile_stamp_lists_smem(g.K, g.Wt, 8);
+      if (use_cand && stamp_lists_fit(g.K, g.Wt) && lsmem <= 100 * 1024 && !(h->debug & YSM_DEBUG_NO_HALF_LISTS)) {
+        // throughput form: per-column-group, per-tile-half step lists
+        const long long lctas = std::max<long long>(1, std::min<long long>((work_cap + 7) / 8, (long long)h->num_sms * 4));
+        k_tile_stamp_lists<<<(unsigned)lctas, 256, lsmem, st>>>(g, d_matches, (const int2*)h->d_work.p, d_workcount,
+                                                                h->d_stamp_tab, h->d_grids, h->d_rowmask, h->rm_words,
+                                                                (const uint32_t*)h->d_cand.p, (const uint2*)h->d_wcand.p);
+      } else
       k_tile_stamp<<<(unsigned)ctas, 256, ksmem, st>>>(g, d_matches, (const uint32_t*)h->d_cells.p,
                                                        (const int*)h->d_cellcount.p, (const uint2*)h->d_gbox.p,
                                                        (const int2*)h->d_work.p, d_workcount, h->d_stamp_tab, h->d_grids,
@@ -2352,19 +2375,22 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       if (!pl.pa.empty()) {
         const int npa = (int)pl.pa.size();
         const int target = h->num_sms * 2;
-        const int nrg = (pl.max_lat_ny + 27) / 28, rows_per_cta = (pl.max_lat_ny + nrg - 1) / nrg;
+        static const int sweep_rows = getenv("YSM_SWEEP_ROWS") ? std::max(1, std::min(28, atoi(getenv("YSM_SWEEP_ROWS")))) : 28;
+        const int nrg = (pl.max_lat_ny + sweep_rows - 1) / sweep_rows, rows_per_cta = (pl.max_lat_ny + nrg - 1) / nrg;
         const int nxc = (pl.max_lat_nx + 31) / 32, cw = (pl.max_lat_nx + nxc - 1) / nxc;
         const bool pruned = !(h->debug & YSM_DEBUG_NO_PRUNE) && (long long)npa * nrg * nxc >= target;
         if (pruned) {
           // throughput form: zero-row pruning, offsets fused (k_sweep_pruned)
-          int PB = (int)((96 * 1024 / 4 / (2 + rows_per_cta)) & ~31);
+          // shared memory per CTA decides the L1 the lookups get: 2 CTAs x 82 KB leave 60 KB of L1, 2 x 41 KB 156 KB
+          static const int sweep_kb = getenv("YSM_SWEEP_SMEM_KB") ? atoi(getenv("YSM_SWEEP_SMEM_KB")) : 96;
+          int PB = (int)((sweep_kb * 1024 / 4 / (2 + rows_per_cta)) & ~31);
           PB = std::max(32, std::min(PB, (pl.max_lat_P + 31) & ~31));
           const size_t smem = (size_t)(2 + rows_per_cta) * PB * 4;
           dim3 grid(npa, nrg * nxc, 1);
           k_sweep_pruned<<<grid, 32 * rows_per_cta, smem, st>>>(g, h->pen, d_pass, d_pa, d_tab, d_trig, d_pool, h->d_grids,
                                                                h->d_rowmask, h->rm_words, h->tnx, (double*)h->d_sums.p,
                                                                d_pmax, (unsigned long long*)h->d_cellmax.p, rows_per_cta, cw, PB,
-                                                               timing ? h->d_issued : nullptr);
+                                                               timing ? h->d_issued : nullptr, h->d_dpc, h->dpc_nx);
           h->work[8]++;
         } else {
           // one warp per lattice row-task; small batches: fewer row-tasks per CTA and several warps

@@ -917,6 +917,208 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
                   (int)blockIdx.x, (int)gridDim.x, dsm_ts, 1, cand, wcand);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1b (throughput form)  k_tile_stamp_lists: the same register-tile stamping for tiles whose exact
+// candidate lists k_find_valid made, with the step loop rebuilt around what ncu showed for k_tile_stamp
+// (r02p: half of all instructions were the per-candidate group tests / reconvergence, and only 12 of 32
+// lanes were live in the max instructions because a K-row stamp crosses ~13 of a tile's 32 rows):
+//   * a candidate is expanded into one step per 8-column group it overlaps, kept in a list of that group,
+//     so a group's loop names its four tile registers statically and carries no group test;
+//   * the tile is treated as two 16-row halves with their own lists: lanes 0-15 walk the upper half's
+//     list while lanes 16-31 walk the lower half's, so a stamp that only reaches one half costs the other
+//     half nothing (steps per group = max of the two lengths instead of their sum);
+//   * a step is one word: bits 31..16 = byte offset of tile row 0's window in the stamp table (biased to be
+//     non-negative), bits 15..0 = which of the half's 16 rows the stamp crosses; the lane's row bit
+//     selects between the stamp's window and 16 zero bytes for one LDS.128 + four VIMNMX.U16x2, no branch.
+// Results are identical to k_tile_stamp (a pure max; tests/test_gpu_parity.py compares grid bytes).
+// ---------------------------------------------------------------------------------------------
+#define YSM_HL_CAP 48  // steps per (column group, tile half) list between flushes; multiple of 4
+
+__host__ __device__ __forceinline__ int stamp_lists_bias(int Wt) { return 31 * Wt + 8; }  // cells; multiple of 8
+// does every step offset fit 16 bits?
+__host__ __device__ __forceinline__ bool stamp_lists_fit(int K, int Wt) {
+  return 2 * ((8 * K - 1) * Wt + 56 + stamp_lists_bias(Wt)) <= 65535;
+}
+__host__ __device__ __forceinline__ size_t tile_stamp_lists_smem(int K, int Wt, int nwarps) {
+  return stamp_table_bytes(K, Wt) + (size_t)nwarps * (8 * YSM_HL_CAP * 4);
+}
+
+// t0..t3 = max(t0..t3, the 8 cells of this lane's row of step w); a lane whose row the stamp does not cross
+// reads 16 zero bytes (zaddr: the left margin of the table's first row) instead of branching around the
+// load -- ptxas then pairs two steps into VIMNMX3.U16x2 (7.25 instructions per step)
+__device__ __forceinline__ void half_step(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t& t3, uint32_t w,
+                                          uint32_t tab_s, uint32_t lanebit, uint32_t zaddr) {
+  const uint32_t saddr = (w & lanebit) ? tab_s + (w >> 16) : zaddr;
+  uint32_t a, b, c, d;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr));
+  t0 = __vmaxu2(t0, a);
+  t1 = __vmaxu2(t1, b);
+  t2 = __vmaxu2(t2, c);
+  t3 = __vmaxu2(t3, d);
+}
+
+__device__ __forceinline__ void half_group_run(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t& t3,
+                                               const uint32_t* __restrict__ lp, int n4, uint32_t tab_s, uint32_t lanebit,
+                                               uint32_t zaddr) {
+#pragma unroll 1
+  for (int k = 0; k < n4; k += 4) {
+    const uint4 ww = *reinterpret_cast<const uint4*>(lp + k);
+    half_step(t0, t1, t2, t3, ww.x, tab_s, lanebit, zaddr);
+    half_step(t0, t1, t2, t3, ww.y, tab_s, lanebit, zaddr);
+    half_step(t0, t1, t2, t3, ww.z, tab_s, lanebit, zaddr);
+    half_step(t0, t1, t2, t3, ww.w, tab_s, lanebit, zaddr);
+  }
+}
+
+// run and empty the warp's eight lists (nU / nL: four byte counters each, one per column group)
+__device__ __forceinline__ void half_lists_flush(uint32_t (&t)[16], uint32_t* wl, uint32_t& nU, uint32_t& nL,
+                                                 uint32_t tab_s, uint32_t lanebit, uint32_t zaddr, int lane) {
+  // pad the shorter list of every group with null steps up to the common length (multiple of 4)
+#pragma unroll
+  for (int gq = 0; gq < 4; gq++) {
+    const int a = (int)((nU >> (8 * gq)) & 0xFFu), b = (int)((nL >> (8 * gq)) & 0xFFu);
+    const int n4 = (max(a, b) + 3) & ~3;
+    if (a + lane < n4) wl[(2 * gq) * YSM_HL_CAP + a + lane] = 0u;  // n4 - a <= 32 + 3: at most two rounds
+    if (a + 32 + lane < n4) wl[(2 * gq) * YSM_HL_CAP + a + 32 + lane] = 0u;
+    if (b + lane < n4) wl[(2 * gq + 1) * YSM_HL_CAP + b + lane] = 0u;
+    if (b + 32 + lane < n4) wl[(2 * gq + 1) * YSM_HL_CAP + b + 32 + lane] = 0u;
+  }
+  __syncwarp();
+  const uint32_t* lp = wl + (lane >> 4) * YSM_HL_CAP;
+#pragma unroll
+  for (int gq = 0; gq < 4; gq++) {
+    const int a = (int)((nU >> (8 * gq)) & 0xFFu), b = (int)((nL >> (8 * gq)) & 0xFFu);
+    const int n4 = (max(a, b) + 3) & ~3;
+    half_group_run(t[4 * gq], t[4 * gq + 1], t[4 * gq + 2], t[4 * gq + 3], lp + (2 * gq) * YSM_HL_CAP, n4,
+                   tab_s + 16u * gq, lanebit, zaddr);
+  }
+  __syncwarp();
+  nU = 0u;
+  nL = 0u;
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_tile_stamp_lists(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
+                   const int* __restrict__ work_count, const uint16_t* __restrict__ stamp_tab,
+                   uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask, int rm_words,
+                   const uint32_t* __restrict__ cand, const uint2* __restrict__ wcand) {
+  extern __shared__ __align__(16) unsigned char dsm_tl[];
+  const int K = g.K, Wt = g.Wt, h = g.half_kernel;
+  const int ntab4 = (int)(stamp_table_bytes(K, Wt) / 16);
+  uint4* s_tab4 = reinterpret_cast<uint4*>(dsm_tl);
+  for (int t = threadIdx.x; t < ntab4; t += blockDim.x) s_tab4[t] = __ldg(reinterpret_cast<const uint4*>(stamp_tab) + t);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  uint32_t* wl = reinterpret_cast<uint32_t*>(s_tab4 + ntab4) + (size_t)warp * (8 * YSM_HL_CAP);  // lists; staging tile at the end
+  const int bias = stamp_lists_bias(Wt);
+  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(dsm_tl) + (uint32_t)(lane * Wt * 2) - (uint32_t)(2 * bias);
+  const uint32_t lanebit = 1u << (lane & 15);
+  const uint32_t zaddr = (uint32_t)__cvta_generic_to_shared(dsm_tl);  // cells 0..7 of table row 0: zeros
+  const uint32_t ltmask = (1u << lane) - 1u;
+  const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
+  const int nwork = *work_count;
+  const int nwarps_total = (int)gridDim.x * wpb;
+  int wi = (int)blockIdx.x * wpb + warp;
+  int2 wk = make_int2(0, 0);
+  uint2 wc = make_uint2(0u, 0u);
+  uint32_t c0 = 0u;
+  int slot = 0;
+  if (wi < nwork) {
+    wk = work[wi];
+    wc = wcand[wi];
+    slot = matches[wk.x].slot;
+    if (lane < (int)wc.y) c0 = cand[wc.x + lane];
+  }
+  for (; wi < nwork; wi += nwarps_total) {
+    // the next tile's descriptors are fetched under this tile's work
+    const int nxt = wi + nwarps_total;
+    int2 wk_n = make_int2(0, 0);
+    uint2 wc_n = make_uint2(0u, 0u);
+    if (nxt < nwork) {
+      wk_n = work[nxt];
+      wc_n = wcand[nxt];
+    }
+    const int ty = wk.y / tnx, tx = wk.y - ty * tnx;
+    const int x0t = tx * YSM_TILE, y0t = ty * YSM_TILE;
+    const uint32_t* cl = cand + wc.x;
+    const int cnt = (int)wc.y;
+    uint32_t t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = 0u;
+    uint32_t nU = 0u, nL = 0u;
+    const uint32_t dummy = (uint32_t)x0t | ((uint32_t)y0t << 16);  // lanes past the list: in-range arithmetic, no steps
+    uint32_t c = c0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      if (i0 && i0 + lane < cnt) c = cl[i0 + lane];
+      if (i0 + lane >= cnt) c = dummy;
+      // candidate -> steps
+      const int ax = (int)(c & 0xFFFFu), ay = (int)(c >> 16);
+      const int xr = ax - h - x0t;    // tile column of the stamp's first column: [-(K-1), 31]
+      const int dy = y0t - (ay - h);  // stamp row that lands on tile row 0: [-31, K-1]
+      const int a = xr & 7;
+      const int q = (a * K + dy) * Wt + 24 + a - xr + bias;  // > 0, multiple of 8
+      const int g0 = max(0, xr) >> 3, g1 = min(31, xr + K - 1) >> 3;
+      uint32_t gmask = ((2u << g1) - 1u) & ~((1u << g0) - 1u);
+      if (i0 + lane >= cnt) gmask = 0u;
+      const int rlo = max(0, -dy), rhi = min(31, K - 1 - dy);
+      const uint32_t rows = (0xFFFFFFFFu >> (31 - rhi)) & (0xFFFFFFFFu << rlo);
+      const uint32_t wU = ((uint32_t)(2 * q) << 16) | (rows & 0xFFFFu), wL = ((uint32_t)(2 * q) << 16) | (rows >> 16);
+      const bool up = (rows & 0xFFFFu) != 0u, lo = (rows >> 16) != 0u;
+#pragma unroll
+      for (int gq = 0; gq < 4; gq++) {
+        const bool ing = (gmask >> gq) & 1u;
+        const unsigned bu = __ballot_sync(0xffffffffu, ing && up), bl = __ballot_sync(0xffffffffu, ing && lo);
+        if (ing && up) wl[(2 * gq) * YSM_HL_CAP + ((nU >> (8 * gq)) & 0xFFu) + __popc(bu & ltmask)] = wU;
+        if (ing && lo) wl[(2 * gq + 1) * YSM_HL_CAP + ((nL >> (8 * gq)) & 0xFFu) + __popc(bl & ltmask)] = wL;
+        nU += (uint32_t)__popc(bu) << (8 * gq);
+        nL += (uint32_t)__popc(bl) << (8 * gq);
+      }
+      // another chunk could overflow a list (a counter above CAP - 32): run what is there
+      if (i0 + 32 < cnt && (((nU + 0x6F6F6F6Fu) | (nL + 0x6F6F6F6Fu)) & 0x80808080u))
+        half_lists_flush(t, wl, nU, nL, tab_s, lanebit, zaddr, lane);
+    }
+    int slot_n = 0;
+    if (nxt < nwork) {
+      slot_n = matches[wk_n.x].slot;
+      if (lane < (int)wc_n.y) c0 = cand[wc_n.x + lane];
+    }
+    half_lists_flush(t, wl, nU, nL, tab_s, lanebit, zaddr, lane);
+    // lane r's row as bytes -> this warp's staging tile (16-byte chunks swizzled: conflict-free both ways)
+    {
+      uint32_t b[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) b[k] = __byte_perm(t[2 * k], t[2 * k + 1], 0x6420);  // u16 lanes -> bytes
+      const int sw = (lane >> 2) & 1;
+      uint4* st4 = reinterpret_cast<uint4*>(wl);
+      st4[lane * 2 + (0 ^ sw)] = make_uint4(b[0], b[1], b[2], b[3]);
+      st4[lane * 2 + (1 ^ sw)] = make_uint4(b[4], b[5], b[6], b[7]);
+    }
+    __syncwarp();
+    // the tile is written exactly once
+    uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes);
+    const int dr = lane >> 3, wd = lane & 7;
+    const int gw = (x0t >> 2) + wd;
+    uint32_t rows_nz = 0u;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int r = k * 4 + dr, row = y0t + r;
+      const uint32_t v = wl[r * 8 + 4 * ((wd >> 2) ^ (k & 1)) + (wd & 3)];
+      const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+      // all-zero rows are not written (the slot is all-zero between matches; 8 lanes = one 32-byte sector)
+      if ((nz & (0xFFu << (8 * dr))) && row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        if (nz & (0xFFu << (8 * d))) rows_nz |= 1u << (k * 4 + d);
+    }
+    if (lane == 0) rowmask[(size_t)slot * rm_words + wk.y] = rows_nz;
+    __syncwarp();
+    wk = wk_n;
+    wc = wc_n;
+    slot = slot_n;
+  }
+}
+
 // zero the tiles a wave touched (the slot grids are kept all-zero between matches). A warp takes 32
 // work items at a time: the (match, tile) pairs and their slots are fetched lane-parallel (no
 // dependent-load chain per tile), then each tile is zeroed with four 8-byte stores per lane
@@ -1314,34 +1516,55 @@ __device__ __forceinline__ unsigned sweep_list_checked(const uint8_t* __restrict
   return sum;
 }
 
+// CTA constants of k_sweep_pruned, made once by warp 0 (r02p: with every warp deriving them itself the
+// prologue was 19 % of the kernel's instructions)
+struct SweepCta {
+  PassDev ps;
+  TableDev tb;
+  double cosine, sine;
+  double ap;  // odometry angle penalty of this CTA's search angle
+  int regular, sx, sy, xspan, yspan;
+};
+
 __global__ void __launch_bounds__(896, 2)
 k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const PassAngle* __restrict__ pa_list,
                const TableDev* __restrict__ tables, const double* __restrict__ trig,
                const double* __restrict__ pool, const uint8_t* __restrict__ grids,
                const uint32_t* __restrict__ rowmask, int rm_words, int tnx, double* __restrict__ resp,
                double* __restrict__ passmax, unsigned long long* __restrict__ cellmax, int rows_per_cta, int cw,
-               int PB, unsigned long long* __restrict__ issued) {
+               int PB, unsigned long long* __restrict__ issued, const double* __restrict__ dpen, int dpen_nx) {
+  // dpen: the matcher's coarse distance-penalty table [nY][nX] (host-made with the device's own IEEE operations;
+  // every coarse pass of a handle shares the lattice), used when a pass has exactly that lattice width
   extern __shared__ __align__(16) uint32_t s_u[];
-  __shared__ double s_wmax[32];
+  __shared__ __align__(16) SweepCta s_c;
+  __shared__ unsigned long long s_cmax;
   __shared__ int s_col[32], s_row[32];
   __shared__ unsigned s_issued;
   __shared__ int s_nsurv;
-  if (threadIdx.x == 0) s_issued = 0u;
   const PassAngle pa = pa_list[blockIdx.x];
-  const PassDev ps = passes[pa.pass];
-  const int nxc = (ps.nX + cw - 1) / cw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(passes + pa.pass);
+    if (threadIdx.x < sizeof(PassDev) / 4) reinterpret_cast<uint32_t*>(&s_c.ps)[threadIdx.x] = __ldg(src + threadIdx.x);
+    if (threadIdx.x == 0) {
+      s_issued = 0u;
+      s_cmax = 0ull;
+    }
+  }
+  __syncthreads();
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + s_c.ps.table);
+    if (threadIdx.x < sizeof(TableDev) / 4) reinterpret_cast<uint32_t*>(&s_c.tb)[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+  const int nX = s_c.ps.nX, nY = s_c.ps.nY;
+  const int nxc = (nX + cw - 1) / cw;
   const int rg = blockIdx.y / nxc, xc = blockIdx.y - rg * nxc;
   const int iy0 = rg * rows_per_cta, ix0 = xc * cw;
-  if (iy0 >= ps.nY || ix0 >= ps.nX) return;
-  const int nr = min(rows_per_cta, ps.nY - iy0), nxl = min(cw, ps.nX - ix0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  uint2* s_pm = reinterpret_cast<uint2*>(s_u);
-  uint32_t* s_list = s_u + 2 * PB + (size_t)warp * PB;  // warp-private
-  const TableDev tb = tables[ps.table];
-  const double cosine = trig[2 * (tb.trig_off + pa.a)], sine = trig[2 * (tb.trig_off + pa.a) + 1];
-  const double* qpts = pool + 2 * (size_t)tb.q_start;
+  if (iy0 >= nY || ix0 >= nX) return;  // block-uniform
+  const int nr = min(rows_per_cta, nY - iy0), nxl = min(cw, nX - ix0);
   // lattice cells of this CTA, exactly as CorrelateScan rounds them (A.7)
-  if (threadIdx.x < 32) {
+  if (warp == 0) {
+    const PassDev& ps = s_c.ps;
     if (lane < nxl) {
       const double x = -ps.offx + (double)(ix0 + lane) * ps.resx;
       s_col[lane] = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
@@ -1350,20 +1573,35 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
       const double y = -ps.offy + (double)(iy0 + lane) * ps.resy;
       s_row[lane] = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
     }
+    __syncwarp();
+    // pruning needs a regular lattice (step 1 or 2 cells): col(i) = col(0) + i*sx, row(i) = row(0) + i*sy
+    const int sx = nxl > 1 ? s_col[1] - s_col[0] : 1, sy = nr > 1 ? s_row[1] - s_row[0] : 1;
+    bool regular = (sx == 1 || sx == 2) && (sy == 1 || sy == 2);
+    if (lane < nxl) regular = regular && s_col[lane] == s_col[0] + lane * sx;
+    if (lane < nr) regular = regular && s_row[lane] == s_row[0] + lane * sy;
+    regular = __all_sync(0xffffffffu, regular);
+    if (lane == 0) {
+      s_c.regular = regular ? 1 : 0;
+      s_c.sx = sx;
+      s_c.sy = sy;
+      s_c.xspan = s_col[nxl - 1] - s_col[0];
+      s_c.yspan = s_row[nr - 1] - s_row[0];
+      s_c.ap = penalty_angle(ps, pen, pa.a);
+    }
   }
   __syncthreads();
-  // pruning needs a regular lattice (step 1 or 2 cells): col(i) = col(0) + i*sx, row(i) = row(0) + i*sy
-  const int sx = nxl > 1 ? s_col[1] - s_col[0] : 1, sy = nr > 1 ? s_row[1] - s_row[0] : 1;
-  bool regular = (sx == 1 || sx == 2) && (sy == 1 || sy == 2);
-  if (lane < nxl) regular = regular && s_col[lane] == s_col[0] + lane * sx;
-  if (lane < nr) regular = regular && s_row[lane] == s_row[0] + lane * sy;
-  regular = __all_sync(0xffffffffu, regular);  // every warp evaluates the same 32 entries
-  // window of this CTA for a point at cell offset (gx, gy): columns xa .. xa + xspan, rows ya .. ya + yspan
-  const int xa0 = s_col[0], ya0 = s_row[0];
-  const int xspan = s_col[nxl - 1] - s_col[0], yspan = s_row[nr - 1] - s_row[0];
-  const uint32_t* rm = rowmask + (size_t)ps.slot * rm_words;
+  if (threadIdx.x == 0) {
+    const int ti = 2 * (s_c.tb.trig_off + pa.a);
+    s_c.cosine = trig[ti];
+    s_c.sine = trig[ti + 1];
+  }
+  uint2* s_pm = reinterpret_cast<uint2*>(s_u);
+  uint32_t* s_list = s_u + 2 * PB + (size_t)warp * PB;  // warp-private
+  const int P = s_c.ps.P;
+  const int slot = s_c.ps.slot;
+  const uint32_t* rm = rowmask + (size_t)slot * rm_words;
   const uint32_t rows_all = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
-  const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+  const uint8_t* grid = grids + (size_t)slot * g.grid_bytes;
   const unsigned dsz = (unsigned)g.data_size;
   const bool row_warp = warp < nr;
   const bool active = row_warp && lane < nxl;
@@ -1374,50 +1612,67 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const uint8_t* gp = grid + (base - (long long)dsz);
   const bool lo32 = __all_sync(0xffffffffu, (reinterpret_cast<unsigned long long>(gp) & 0xFFFFFFFFull) + 2ull * dsz <
                                                0x100000000ull);
-  for (int pb = 0; pb < ps.P; pb += PB) {
-    const int nb = min(PB, ps.P - pb);
-    __syncthreads();  // the previous batch's s_pm is still being read; s_nsurv reset below
+  for (int pb = 0; pb < P; pb += PB) {
+    const int nb = min(PB, P - pb);
+    __syncthreads();  // the previous batch's s_pm is still being read; s_nsurv reset below; s_c complete
     if (threadIdx.x == 0) s_nsurv = 0;
     __syncthreads();
     // ---- A: offsets + per-point row masks; points that can see a non-zero cell survive ----------
     int ok = 1;
-    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
-      const int i = i0 + threadIdx.x;
-      uint32_t mask = 0u;
-      int flat = 0;
-      if (i < nb) {
-        const double2 w = *reinterpret_cast<const double2*>(qpts + 2 * (size_t)(pb + i));
-        int gx, gy;
-        offset_cell(tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
-        flat = gx + gy * g.stride;
-        const int xa = xa0 + gx, ya = ya0 + gy;
-        mask = rows_all;
-        if (regular && xa >= 0 && ya >= 0 && xa + xspan < g.width && ya + yspan < g.height) {
-          const int txa = xa >> 5, txb = (xa + xspan) >> 5, tya = ya >> 5, tyb = (ya + yspan) >> 5;
-          uint32_t m[3] = {0u, 0u, 0u};
-#pragma unroll
-          for (int j = 0; j < 3; j++) {
-            if (tya + j <= tyb) {
-              const uint32_t* r = rm + (size_t)(tya + j) * tnx;
+    {
+      const double* qpts = pool + 2 * (size_t)s_c.tb.q_start;
+      const double cosine = s_c.cosine, sine = s_c.sine;
+      const int regular = s_c.regular, sy = s_c.sy, xspan = s_c.xspan, yspan = s_c.yspan;
+      const int xa0 = s_col[0], ya0 = s_row[0];
+      for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        uint32_t mask = 0u;
+        int flat = 0;
+        if (i < nb) {
+          const double2 w = *reinterpret_cast<const double2*>(qpts + 2 * (size_t)(pb + i));
+          int gx, gy;
+          offset_cell(s_c.tb, g.scale, w.x, w.y, cosine, sine, gx, gy);
+          flat = gx + gy * g.stride;
+          const int xa = xa0 + gx, ya = ya0 + gy;
+          mask = rows_all;
+          if (regular && xa >= 0 && ya >= 0 && xa + xspan < g.width && ya + yspan < g.height) {
+            const int txa = xa >> 5, txb = (xa + xspan) >> 5, tya = ya >> 5, tyb = (ya + yspan) >> 5;
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u;
+            {
+              const uint32_t* r = rm + (size_t)tya * tnx;
               uint32_t v = __ldg(r + txa);
               if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
               if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
-              m[j] = v;
+              m0 = v;
             }
+            if (tya + 1 <= tyb) {
+              const uint32_t* r = rm + (size_t)(tya + 1) * tnx;
+              uint32_t v = __ldg(r + txa);
+              if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
+              if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
+              m1 = v;
+            }
+            if (tya + 2 <= tyb) {
+              const uint32_t* r = rm + (size_t)(tya + 2) * tnx;
+              uint32_t v = __ldg(r + txa);
+              if (txa + 1 <= txb) v |= __ldg(r + txa + 1);
+              if (txa + 2 <= txb) v |= __ldg(r + txa + 2);
+              m2 = v;
+            }
+            const int sft = ya & 31;
+            const unsigned long long lo = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+            const unsigned long long S = sft ? ((lo >> sft) | ((unsigned long long)m2 << (64 - sft))) : lo;
+            mask = (sy == 2 ? even_bits64(S) : (uint32_t)S) & rows_all;
+          } else {
+            ok = 0;  // window may leave the grid: all rows, and Karto's flat bounds check for this batch
           }
-          const int sft = ya & 31;
-          const unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
-          const unsigned long long S = sft ? ((lo >> sft) | ((unsigned long long)m[2] << (64 - sft))) : lo;
-          mask = (sy == 2 ? even_bits64(S) : (uint32_t)S) & rows_all;
-        } else {
-          ok = 0;  // window may leave the grid: all rows, and Karto's flat bounds check for this batch
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (mask) s_pm[wbase + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)flat, mask);
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
-      int wbase = 0;
-      if (lane == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (mask) s_pm[wbase + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)flat, mask);
     }
     const int safe = __syncthreads_and(ok);
     const int nsurv = s_nsurv;
@@ -1442,24 +1697,29 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
       __syncwarp();
     }
   }
-  double wmax = 0.0;
+  // ---- epilogue: normalise, penalise, store; CTA maximum through the responses' bit patterns (>= 0) ----------
+  unsigned long long bits = 0ull;
   if (active) {
+    const PassDev& ps = s_c.ps;
     const int ix = ix0 + lane, iy = iy0 + warp;
-    const double rr = response_of(ps, pen, sum, ix, iy, pa.a);
-    resp[ps.sums_off + ((size_t)iy * ps.nX + ix) * ps.nA + pa.a] = rr;
+    double rr = (double)sum / (double)((unsigned)P * 100u);
+    if (ps.penalize && !kt_double_equal(rr, 0.0)) {
+      const double dp = (dpen && dpen_nx == nX) ? __ldg(dpen + (size_t)iy * nX + ix) : penalty_distance(ps, pen, ix, iy);
+      rr *= (dp * s_c.ap);
+    }
+    resp[ps.sums_off + ((size_t)iy * nX + ix) * ps.nA + pa.a] = rr;
     cell_max_update(cellmax, ps, ix, iy, rr);
-    wmax = rr;
+    bits = (unsigned long long)__double_as_longlong(rr);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double t = __shfl_xor_sync(0xffffffffu, wmax, o);
-    wmax = t > wmax ? t : wmax;
+  {
+    const unsigned hi = (unsigned)(bits >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? (unsigned)bits : 0u);
+    if (lane == 0 && row_warp) atomicMax(&s_cmax, ((unsigned long long)mhi << 32) | mlo);
   }
-  if (lane == 0) s_wmax[warp] = wmax;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double m = s_wmax[0];
-    for (int w = 1; w < nwarps; w++) m = s_wmax[w] > m ? s_wmax[w] : m;
-    pass_max_update(passmax, pa.pass, m);
+    atomicMax(reinterpret_cast<unsigned long long*>(passmax + pa.pass), s_cmax);
     if (issued) atomicAdd(issued, (unsigned long long)s_issued);  // lookups actually performed (bench accounting)
   }
 }
