@@ -259,6 +259,7 @@ int64_t ysm_launch_count(const ysm_handle *h);
 #define YSM_DEBUG_NO_MEGA 16     /* latency path: separate kernels instead of the single cooperative kernel */
 #define YSM_DEBUG_NO_CANDLISTS 32 /* grid build: search the cell list per tile instead of exact per-tile candidate lists (A/B checks) */
 #define YSM_DEBUG_NO_HALF_LISTS 64 /* grid build: k_tile_stamp's per-candidate step loop instead of k_tile_stamp_lists (A/B checks) */
+#define YSM_DEBUG_NO_FINE9 128 /* fine pass: k_sweep_points (a warp per pose) instead of k_sweep_fine9 (A/B checks) */
 int ysm_last_kernel_ms(const ysm_handle *h, double *sweep_ms, double *build_ms, double *reduce_ms,
                        double *total_ms);
 

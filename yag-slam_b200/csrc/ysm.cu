@@ -231,6 +231,7 @@ struct PassPlan {
   size_t off_elems = 0, sums_elems = 0, cmax_elems = 0;
   int ang_elems = 0;
   int max_lat_P = 0, max_lat_nx = 0, max_lat_ny = 0, max_lat_tasks = 0, max_fine_poses = 0;
+  bool fine_not9 = false;  // some fine pass is not a 3 x 3 lattice (k_sweep_points instead of k_sweep_fine9)
   int first_spec_table = -1;
   void clear() {
     tab.clear(); pass.clear(); ph.clear(); pa.clear(); fine.clear(); spec_fine.clear(); trig.clear();
@@ -238,6 +239,7 @@ struct PassPlan {
     off_elems = sums_elems = cmax_elems = 0;
     ang_elems = 0;
     max_lat_P = max_lat_nx = max_lat_ny = max_lat_tasks = max_fine_poses = 0;
+    fine_not9 = false;
     first_spec_table = -1;
   }
 };
@@ -435,6 +437,7 @@ static cudaError_t init_kernel_attrs(int device) {
   return cudaSuccess;
 }
 
+static int debug_env_or();
 static int create_one(const ysm_params* p, int device, ysm_handle** out, int roi_override = 0) {
   if (!p || !out) return fail(nullptr, YSM_EINVAL, "null argument");
   *out = nullptr;
@@ -559,6 +562,7 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out, int roi
     delete h;
     return fail(nullptr, YSM_ECUDA, msg);
   }
+  h->debug = debug_env_or();
   *out = h;
   return YSM_OK;
 }
@@ -731,8 +735,15 @@ extern "C" int ysm_get_dims(const ysm_handle* h, ysm_dims* out) {
   return YSM_OK;
 }
 
+static int debug_env_or() {
+  static const int v = getenv("YSM_DEBUG_OR") ? atoi(getenv("YSM_DEBUG_OR")) : 0;
+  return v;
+}
+
 extern "C" int ysm_set_debug(ysm_handle* h, int32_t flags) {
   if (!h) return YSM_EINVAL;
+  // YSM_DEBUG_OR: developer A/B switch (read once), ORed into every set_debug / create: e.g. 64 | 128
+  flags |= debug_env_or();
   h->debug = flags;
   for (ysm_handle* sub : h->lanes) sub->debug = flags;
   return YSM_OK;
@@ -1912,7 +1923,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         pl.spec_of.push_back(-1);
         pl.spec_h.push_back(-1);
         if (!ph.fine) {
-          for (int a = 0; a < ph.nA; a++) pl.pa.push_back(PassAngle{pid, a});
+          for (int a = 0; a < ph.nA; a++) pl.pa.push_back(PassAngle{pid, a, tid, pl.tab[tid].trig_off + a});
           h->work[0] += (int64_t)ph.nX * ph.nY * ph.nA * s.P;
           pl.max_lat_P = std::max(pl.max_lat_P, s.P);
           pl.max_lat_nx = std::max(pl.max_lat_nx, ph.nX);
@@ -1928,6 +1939,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
           pl.fine.push_back(pid);
           h->work[4] += (int64_t)(ph.nX * ph.nY + 1) * ph.nA * s.P;
           pl.max_fine_poses = std::max(pl.max_fine_poses, ph.nX * ph.nY * ph.nA);
+          if (ph.nX != 3 || ph.nY != 3) pl.fine_not9 = true;
         }
       }
       if (spec) {
@@ -2009,6 +2021,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
           PassDev& c2 = pl.pass[pid];
           c2.spec = fid; c2.spec_nAf = nAf; c2.spec_h_off = h_off; c2.spec_trig_off = t_off; c2.spec_htrig_off = ht_off;
           pl.max_fine_poses = std::max(pl.max_fine_poses, fd.nX * fd.nY * nAf);
+          if (fd.nX != 3 || fd.nY != 3) pl.fine_not9 = true;
         }
       }
       return YSM_OK;
@@ -2424,6 +2437,10 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       if (timing) CK(cudaEventRecord(h->ev[3], st));
       if (nhostfine > 0) {
         dim3 grid((pl.max_fine_poses + 7) / 8, (unsigned)nhostfine);
+        if (!pl.fine_not9 && nhostfine >= 64 && !(h->debug & YSM_DEBUG_NO_FINE9))  // waves of 3 x 3 fine passes: a warp per (pass, angle), nine cells per offset
+          k_sweep_fine9<<<(unsigned)nhostfine, 32 * std::min(12, std::max(1, nAf)), 0, st>>>(
+              g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids, (double*)h->d_sums.p, d_pmax);
+        else
         k_sweep_points<<<grid, 256, 0, st>>>(g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
                                              (double*)h->d_sums.p, d_pmax);
         h->launches++;

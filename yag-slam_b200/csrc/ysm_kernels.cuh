@@ -932,7 +932,7 @@ k_tile_stamp(GridC g, const MatchDev* __restrict__ matches, const uint32_t* __re
 //     selects between the stamp's window and 16 zero bytes for one LDS.128 + four VIMNMX.U16x2, no branch.
 // Results are identical to k_tile_stamp (a pure max; tests/test_gpu_parity.py compares grid bytes).
 // ---------------------------------------------------------------------------------------------
-#define YSM_HL_CAP 48  // steps per (column group, tile half) list between flushes; multiple of 4
+#define YSM_HL_CAP 96  // steps per (column group, tile half) list between flushes; multiple of 4
 
 __host__ __device__ __forceinline__ int stamp_lists_bias(int Wt) { return 31 * Wt + 8; }  // cells; multiple of 8
 // does every step offset fit 16 bits?
@@ -978,10 +978,8 @@ __device__ __forceinline__ void half_lists_flush(uint32_t (&t)[16], uint32_t* wl
   for (int gq = 0; gq < 4; gq++) {
     const int a = (int)((nU >> (8 * gq)) & 0xFFu), b = (int)((nL >> (8 * gq)) & 0xFFu);
     const int n4 = (max(a, b) + 3) & ~3;
-    if (a + lane < n4) wl[(2 * gq) * YSM_HL_CAP + a + lane] = 0u;  // n4 - a <= 32 + 3: at most two rounds
-    if (a + 32 + lane < n4) wl[(2 * gq) * YSM_HL_CAP + a + 32 + lane] = 0u;
-    if (b + lane < n4) wl[(2 * gq + 1) * YSM_HL_CAP + b + lane] = 0u;
-    if (b + 32 + lane < n4) wl[(2 * gq + 1) * YSM_HL_CAP + b + 32 + lane] = 0u;
+    for (int k = a + lane; k < n4; k += 32) wl[(2 * gq) * YSM_HL_CAP + k] = 0u;
+    for (int k = b + lane; k < n4; k += 32) wl[(2 * gq + 1) * YSM_HL_CAP + k] = 0u;
   }
   __syncwarp();
   const uint32_t* lp = wl + (lane >> 4) * YSM_HL_CAP;
@@ -1075,7 +1073,7 @@ k_tile_stamp_lists(GridC g, const MatchDev* __restrict__ matches, const int2* __
         nL += (uint32_t)__popc(bl) << (8 * gq);
       }
       // another chunk could overflow a list (a counter above CAP - 32): run what is there
-      if (i0 + 32 < cnt && (((nU + 0x6F6F6F6Fu) | (nL + 0x6F6F6F6Fu)) & 0x80808080u))
+      if (i0 + 32 < cnt && (((nU + 0x3F3F3F3Fu) | (nL + 0x3F3F3F3Fu)) & 0x80808080u))
         half_lists_flush(t, wl, nU, nL, tab_s, lanebit, zaddr, lane);
     }
     int slot_n = 0;
@@ -1085,31 +1083,32 @@ k_tile_stamp_lists(GridC g, const MatchDev* __restrict__ matches, const int2* __
     }
     half_lists_flush(t, wl, nU, nL, tab_s, lanebit, zaddr, lane);
     // lane r's row as bytes -> this warp's staging tile (16-byte chunks swizzled: conflict-free both ways)
+    uint32_t rows_nz;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
     {
       uint32_t b[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) b[k] = __byte_perm(t[2 * k], t[2 * k + 1], 0x6420);  // u16 lanes -> bytes
+      rows_nz = __ballot_sync(0xffffffffu, ((b[0] | b[1]) | (b[2] | b[3]) | (b[4] | b[5]) | (b[6] | b[7])) != 0u);
       const int sw = (lane >> 2) & 1;
       uint4* st4 = reinterpret_cast<uint4*>(wl);
       st4[lane * 2 + (0 ^ sw)] = make_uint4(b[0], b[1], b[2], b[3]);
       st4[lane * 2 + (1 ^ sw)] = make_uint4(b[4], b[5], b[6], b[7]);
     }
     __syncwarp();
-    // the tile is written exactly once
-    uint32_t* gout = reinterpret_cast<uint32_t*>(grids + (size_t)slot * g.grid_bytes);
-    const int dr = lane >> 3, wd = lane & 7;
-    const int gw = (x0t >> 2) + wd;
-    uint32_t rows_nz = 0u;  // bit r: row r of this tile holds a non-zero cell (the sweep skips the others)
+    // the tile is written exactly once: four lanes per row (8 bytes each: the row stride is a multiple of 8), eight
+    // rows per store instruction; all-zero rows are not written (the slot is all-zero between matches)
+    {
+      uint2* gout = reinterpret_cast<uint2*>(grids + (size_t)slot * g.grid_bytes);
+      const int stride8 = g.stride4 >> 1;
+      const int dr = lane >> 2, wd = lane & 3;
+      const int gw = (x0t >> 3) + wd;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int r = k * 4 + dr, row = y0t + r;
-      const uint32_t v = wl[r * 8 + 4 * ((wd >> 2) ^ (k & 1)) + (wd & 3)];
-      const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
-      // all-zero rows are not written (the slot is all-zero between matches; 8 lanes = one 32-byte sector)
-      if ((nz & (0xFFu << (8 * dr))) && row < g.height && gw < g.stride4) gout[(size_t)row * g.stride4 + gw] = v;
-#pragma unroll
-      for (int d = 0; d < 4; d++)
-        if (nz & (0xFFu << (8 * d))) rows_nz |= 1u << (k * 4 + d);
+      for (int k = 0; k < 4; k++) {
+        const int r = k * 8 + dr, row = y0t + r;
+        if (((rows_nz >> r) & 1u) && row < g.height && gw < stride8)
+          gout[(size_t)row * stride8 + gw] =
+              *reinterpret_cast<const uint2*>(wl + r * 8 + 4 * ((wd >> 1) ^ ((r >> 2) & 1)) + 2 * (wd & 1));
+      }
     }
     if (lane == 0) rowmask[(size_t)slot * rm_words + wk.y] = rows_nz;
     __syncwarp();
@@ -1216,6 +1215,8 @@ k_offsets(GridC g, const TableDev* __restrict__ tables, const double* __restrict
 // ---------------------------------------------------------------------------------------------
 struct PassAngle {
   int pass, a;
+  int table;   // = passes[pass].table      (copies: a sweep CTA fetches its pass, its table and its angle's
+  int trig_i;  // = tables[table].trig_off + a   cos/sin in ONE round of loads instead of a chain of three)
 };
 
 // GetResponse normalisation + the odometry penalty of CorrelateScan for the
@@ -1544,18 +1545,20 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const PassAngle pa = pa_list[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(passes + pa.pass);
-    if (threadIdx.x < sizeof(PassDev) / 4) reinterpret_cast<uint32_t*>(&s_c.ps)[threadIdx.x] = __ldg(src + threadIdx.x);
+    // pass, table and the angle's cos / sin in one round of loads
+    const int nps = (int)(sizeof(PassDev) / 4), ntb = (int)(sizeof(TableDev) / 4);
+    for (int i = threadIdx.x; i < nps + ntb + 2; i += blockDim.x) {
+      if (i < nps) reinterpret_cast<uint32_t*>(&s_c.ps)[i] = __ldg(reinterpret_cast<const uint32_t*>(passes + pa.pass) + i);
+      else if (i < nps + ntb) reinterpret_cast<uint32_t*>(&s_c.tb)[i - nps] = __ldg(reinterpret_cast<const uint32_t*>(tables + pa.table) + (i - nps));
+      else if (i == nps + ntb) s_c.cosine = trig[2 * pa.trig_i];
+      else s_c.sine = trig[2 * pa.trig_i + 1];
+    }
     if (threadIdx.x == 0) {
       s_issued = 0u;
       s_cmax = 0ull;
     }
   }
   __syncthreads();
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + s_c.ps.table);
-    if (threadIdx.x < sizeof(TableDev) / 4) reinterpret_cast<uint32_t*>(&s_c.tb)[threadIdx.x] = __ldg(src + threadIdx.x);
-  }
   const int nX = s_c.ps.nX, nY = s_c.ps.nY;
   const int nxc = (nX + cw - 1) / cw;
   const int rg = blockIdx.y / nxc, xc = blockIdx.y - rg * nxc;
@@ -1590,11 +1593,6 @@ k_sweep_pruned(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ti = 2 * (s_c.tb.trig_off + pa.a);
-    s_c.cosine = trig[ti];
-    s_c.sine = trig[ti + 1];
-  }
   uint2* s_pm = reinterpret_cast<uint2*>(s_u);
   uint32_t* s_list = s_u + 2 * PB + (size_t)warp * PB;  // warp-private
   const int P = s_c.ps.P;
@@ -1772,6 +1770,81 @@ k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
   const TableDev tb = tables[ps.table];
   sweep_points_body(g, pen, ps, tb, pid, (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)), offsets, grids,
                     resp, passmax);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3' (3 x 3 form)  the fine pass of the throughput path: its lattice is 3 x 3 cells, so a warp takes one
+// (pass, angle): every lane reads a point's lookup offset ONCE and sums the nine cells around it (k_sweep_points
+// read the offset once per pose and kept one pose per warp: nine times the table traffic, 99 short dependent
+// chains per match). One CTA per fine pass; nine REDUX per warp, lanes 0-8 finish their pose.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384)
+k_sweep_fine9(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
+              const TableDev* __restrict__ tables, const int* __restrict__ offsets,
+              const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax) {
+  __shared__ PassDev s_ps;
+  __shared__ int s_out_off, s_ppad;
+  const int pid = pass_ids[blockIdx.x];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(passes + pid);
+    if (threadIdx.x < sizeof(PassDev) / 4) reinterpret_cast<uint32_t*>(&s_ps)[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const TableDev* tb = tables + s_ps.table;
+    s_out_off = tb->out_off;
+    s_ppad = tb->Ppad;
+  }
+  __syncthreads();
+  const PassDev& ps = s_ps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // the nine lattice cells, rounded exactly as CorrelateScan rounds them (A.7)
+  int cb[9];
+#pragma unroll
+  for (int iy = 0; iy < 3; iy++) {
+    const double y = -ps.offy + (double)iy * ps.resy;
+    const int gy = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
+#pragma unroll
+    for (int ix = 0; ix < 3; ix++) {
+      const double x = -ps.offx + (double)ix * ps.resx;
+      const int gx = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+      cb[iy * 3 + ix] = gx + gy * g.stride;
+    }
+  }
+  const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
+  const unsigned dsz = (unsigned)g.data_size;
+  const int P = ps.P, nA = ps.nA;
+  for (int a = warp; a < nA; a += nwarps) {
+    const int* goff = offsets + s_out_off + (size_t)a * s_ppad;
+    unsigned sum[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) sum[k] = 0u;
+    for (int p = lane; p < P; p += 32) {
+      const int o = __ldg(goff + p);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const unsigned idx = (unsigned)(cb[k] + o);
+        if (idx < dsz) sum[k] += (unsigned)__ldg(grid + idx);  // Karto's IsUpTo(index, dataSize)
+      }
+    }
+    unsigned mine = 0u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const unsigned t = __reduce_add_sync(0xffffffffu, sum[k]);
+      if (lane == k) mine = t;
+    }
+    unsigned long long bits = 0ull;
+    if (lane < 9) {
+      const int iy = lane / 3, ix = lane - iy * 3;
+      const double rr = response_of(ps, pen, mine, ix, iy, a);
+      resp[ps.sums_off + (iy * 3 + ix) * nA + a] = rr;
+      bits = (unsigned long long)__double_as_longlong(rr);
+    }
+    const unsigned hi = (unsigned)(bits >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? (unsigned)bits : 0u);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(passmax + pid), ((unsigned long long)mhi << 32) | mlo);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
