@@ -529,6 +529,11 @@ static int create_one(const ysm_params* p, int device, ysm_handle** out, int roi
   long long slots = budget / g.grid_bytes;
   if (p->max_slots > 0 && slots > p->max_slots) slots = p->max_slots;
   if (slots > 8192) slots = 8192;
+  {
+    // developer A/B: waves a multiple of YSM_WAVE_ALIGN matches (k_find_valid runs one CTA per match)
+    static const int wave_align = getenv("YSM_WAVE_ALIGN") ? atoi(getenv("YSM_WAVE_ALIGN")) : 0;
+    if (wave_align > 0 && slots > wave_align) slots -= slots % wave_align;
+  }
   if (slots < 1) {
     delete h;
     return fail(nullptr, YSM_ENOMEM, "not enough device memory for one correlation grid");
@@ -2106,6 +2111,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       if (use_cand) {
         CK(h->d_cand.ensure(std::max<size_t>(16, (size_t)cells_total * tiles_per_stamp * 4)));
         CK(h->d_wcand.ensure(std::max<size_t>(16, (size_t)work_cap * 8)));
+        CK(h->d_gbox.ensure(std::max<size_t>(8, (size_t)cells_total * 4)));  // second half of the cells' list ranks
       }
       if (h->static_grid) {  // the map grid is resident: nothing to build
         if (timing) CK(cudaEventRecord(h->ev[1], st));

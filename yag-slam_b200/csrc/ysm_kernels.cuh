@@ -281,6 +281,8 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
     // (touched tiles, candidates), then work items + list offsets, then the fill
     const int tps1 = stamp_tiles_axis;  // tiles a stamp can span per axis
     const uint32_t* mc = cells + m.cells_off;
+    uint32_t* rank01 = pt_cell + m.cells_off;                                // (tps1 == 2)
+    uint32_t* rank23 = reinterpret_cast<uint32_t*>(gbox) + m.cells_off;      // sized for it by the host in this path
     __syncthreads();  // the compacted cells (global, written by this CTA) are complete
     for (int i0 = 0; i0 < tot; i0 += (int)blockDim.x) {  // count pass (block-uniform trip count)
       const int i = i0 + (int)threadIdx.x;
@@ -299,6 +301,12 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
         for (int k = 0; k < 4; k++)
           t4[k] = (i < tot && ty0 + (k >> 1) <= ty1 && tx0 + (k & 1) <= tx1) ? (ty0 + (k >> 1)) * tnx + tx0 + (k & 1) : -1;
         tile_counter_bump4(s_bits, t4, lane, sl);
+        // the slot a cell got in each tile's count IS its rank in that tile's list: kept (the point scratch and
+        // the bounding-box buffer are free in this path) so the fill pass needs no second round of match / atomics
+        if (i < tot) {
+          rank01[i] = (sl[0] & 0xFFFFu) | (sl[1] << 16);
+          rank23[i] = (sl[2] & 0xFFFFu) | (sl[3] << 16);
+        }
       } else {
         for (int dy = 0; dy < tps1; dy++)
           for (int dx = 0; dx < tps1; dx++) {
@@ -365,15 +373,18 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
       const int tx0 = (ax - g.half_kernel) / YSM_TILE, tx1 = (ax + g.half_kernel) / YSM_TILE;
       const int ty0 = (ay - g.half_kernel) / YSM_TILE, ty1 = (ay + g.half_kernel) / YSM_TILE;
       if (tps1 == 2) {
-        int t4[4];
-        unsigned sl[4];
+        if (i < tot) {
+          const uint32_t r01 = rank01[i], r23 = rank23[i];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          t4[k] = (i < tot && ty0 + (k >> 1) <= ty1 && tx0 + (k & 1) <= tx1) ? (ty0 + (k >> 1)) * tnx + tx0 + (k & 1) : -1;
-        tile_counter_bump4(s_bits, t4, lane, sl);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (t4[k] >= 0) cand[cbase + sl[k]] = c;
+          for (int k = 0; k < 4; k++) {
+            if (ty0 + (k >> 1) <= ty1 && tx0 + (k & 1) <= tx1) {
+              const int t = (ty0 + (k >> 1)) * tnx + tx0 + (k & 1);
+              const unsigned off = (s_bits[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;  // the tile's list offset (read-only now)
+              const unsigned rk = ((k < 2 ? r01 : r23) >> (16 * (k & 1))) & 0xFFFFu;
+              cand[cbase + off + rk] = c;
+            }
+          }
+        }
       } else {
         for (int dy = 0; dy < tps1; dy++)
           for (int dx = 0; dx < tps1; dx++) {
