@@ -404,7 +404,7 @@ def run_ours(args, rank, world, local_rank):
             "reduce_share": snap["reduce_ms"] / max(snap["total_ms"], 1e-9),
         },
         "roofline_build": {
-            "kernel": "k_find_valid + k_tile_stamp (AddScans/FindValidPoints/SmearPoint)", "bound": "hbm",
+            "kernel": "k_find_valid + k_tile_stamp_lists (AddScans/FindValidPoints/SmearPoint)", "bound": "hbm",
             "achieved": stamp_achieved, "peak": peak, "unit": "GB/s",
             "frac": (stamp_achieved / peak) if stamp_achieved else None,
             "algorithmic_bytes": "2 B x P_valid x K^2 (K = %d); P_valid = %d of %d base points survive FindValidPoints "

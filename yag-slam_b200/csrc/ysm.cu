@@ -2565,7 +2565,6 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     }
 
     tr.mark("host finalize");
-    kt.dump();
     // ---- results + clear ------------------------------------------------------------------------
     for (int i = 0; i < nw; i++) {
       const MatchState& s = states[i];
@@ -2584,8 +2583,10 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         h->grids_dirty = true;  // cleared at the start of the next call (the work list stays resident)
       } else {
         clear_wave(h, d_matches, st);
+        kt.mark("k_tile_clear");
       }
     }
+    kt.dump();
     CK(cudaGetLastError());
   }
   if (timing) {

@@ -1133,6 +1133,7 @@ k_tile_stamp_lists(GridC g, const MatchDev* __restrict__ matches, const int2* __
 // work items at a time: the (match, tile) pairs and their slots are fetched lane-parallel (no
 // dependent-load chain per tile), then each tile is zeroed with four 8-byte stores per lane
 // (row stride is a multiple of 8 bytes).
+#define YSM_CLEAR_BATCH 8  // work items a warp takes per round (r02z: with 32, half the launched warps had no work)
 __global__ void __launch_bounds__(256)
 k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restrict__ work,
              const int* __restrict__ work_count, uint8_t* __restrict__ grids, uint32_t* __restrict__ rowmask,
@@ -1142,8 +1143,8 @@ k_tile_clear(GridC g, const MatchDev* __restrict__ matches, const int2* __restri
   const int nwork = *work_count;
   const int nwarps_total = gridDim.x * (blockDim.x >> 5);
   const int stride8 = g.stride4 >> 1;
-  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < nwork; base += nwarps_total * 32) {
-    const int cnt = min(32, nwork - base);
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * YSM_CLEAR_BATCH; base < nwork; base += nwarps_total * YSM_CLEAR_BATCH) {
+    const int cnt = min(YSM_CLEAR_BATCH, nwork - base);
     int my_tile = 0, my_slot = 0;
     uint32_t my_rows = 0u;  // rows of the tile that hold a non-zero cell: the only ones the stamp kernel wrote
     if (lane < cnt) {
