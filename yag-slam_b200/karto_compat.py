@@ -166,73 +166,89 @@ class Wrapper(object):
 
     def match_scan(self, query, base_scans, penalty=True, do_fine=False):
         """Wrapper.match_scan(query, base_scans, penalty, do_fine) (reference scan_matching.py:41).
-        Single-query fast path: the descriptor arrays are cached per base-set size; every scan's point readings
-        sit in a region of a persistent staging pool under their content tag, so the running scans of sequential
-        mapping (graph_slam.py:326) are packed -- and, through ysm_batch::scan_tag, uploaded -- once, not once
-        per match."""
-        import ctypes as C
+        Single-query fast path: the descriptor (a few ctypes arrays) is cached per base-set size and only the
+        entries that changed since the previous call are rewritten; every scan's point readings sit in a region
+        of a persistent staging pool under their content tag, so the running scans of sequential mapping
+        (graph_slam.py:326) are packed -- and, through ysm_batch::scan_tag, uploaded -- once, not once per
+        match. (The glue is on the critical path of a 30 us call: 7.6 -> 3 us, measured against a stub library.)"""
         nb = len(base_scans)
         c = self._one.get(nb)
         if c is None:
-            b = _capi.YsmBatch()
-            arr = dict(counts=np.zeros(nb + 1, np.int32), starts=np.zeros(nb + 1, np.int32),
-                       qidx=np.zeros(1, np.int32), pose=np.zeros((1, 3), np.float64),
-                       bptr=np.array([0, nb], np.int32), bidx=np.arange(1, nb + 1, dtype=np.int32),
-                       res=np.zeros(1, dtype=_capi.RESULT_DTYPE), tags=np.zeros(nb + 1, np.uint64),
-                       raw=np.zeros(nb + 1, np.int32))
-            arr["resf"] = arr["res"].view(np.float64).reshape(-1)  # the 128-B record as 16 doubles
-            b.n_matches, b.n_scans = 1, nb + 1
-            b.scan_start, b.scan_count = arr["starts"].ctypes.data, arr["counts"].ctypes.data
-            b.query_scan, b.query_pose = arr["qidx"].ctypes.data, arr["pose"].ctypes.data
-            b.base_ptr, b.base_idx = arr["bptr"].ctypes.data, (arr["bidx"].ctypes.data if nb else None)
-            b.pool_on_device = 0
-            b.scan_tag = arr["tags"].ctypes.data
-            b.scan_raw_count = arr["raw"].ctypes.data
-            c = self._one[nb] = (b, arr, C.byref(b), arr["res"].ctypes.data)
-        b, arr, bref, resp = c
-        pool = self._pool
-        if pool is None:
-            pool = self._pool = np.zeros((self.POOL_REGIONS * self.REGION_POINTS, 2), np.float64)
+            c = self._one[nb] = self._make_descriptor(nb)
+        b, bref, resp, starts, counts, tags, posec, rawc, resf, covv, last, lastr, flags = c
+        if self._pool is None:
+            self._pool = np.zeros((self.POOL_REGIONS * self.REGION_POINTS, 2), np.float64)
+            self._pool_ptr, self._pool_len = self._pool.ctypes.data, len(self._pool)
             self._region_of, self._region_tag, self._region_clock = {}, [0] * self.POOL_REGIONS, 0
-        counts, starts, tags = arr["counts"], arr["starts"], arr["tags"]
-        region_of, rp = self._region_of, self.REGION_POINTS
-        self._region_clock += 1
-        clock = self._region_clock
-        scans = [query]
-        scans.extend(base_scans)
-        if len(scans) > self.POOL_REGIONS:
+        if nb + 1 > self.POOL_REGIONS:
             return self._match_scan_unpooled(query, base_scans, penalty, do_fine)
-        used = self._region_used
-        for i, sc in enumerate(scans):
-            pts = sc.point_readings()
-            n = len(pts)
-            if n > rp:
-                return self._match_scan_unpooled(query, base_scans, penalty, do_fine)
+        clock = self._region_clock = self._region_clock + 1
+        used, region_of, rp = self._region_used, self._region_of, self.REGION_POINTS
+        i = 0
+        sc = query
+        while True:
+            pts = sc._points
+            if pts is None:
+                pts = sc.point_readings()
             tag = sc._tag
             r = region_of.get(tag)
             if r is None:
+                n = len(pts)
+                if n > rp:
+                    return self._match_scan_unpooled(query, base_scans, penalty, do_fine)
                 # a region no scan of this call sits in, least recently used first
                 r = min((k for k in range(self.POOL_REGIONS) if used[k] != clock), key=used.__getitem__)
                 region_of.pop(self._region_tag[r], None)
                 region_of[tag] = r
                 self._region_tag[r] = tag
                 if n:
-                    pool[r * rp:r * rp + n] = pts
+                    self._pool[r * rp:r * rp + n] = pts
             used[r] = clock
-            starts[i] = r * rp
-            counts[i] = n
-            tags[i] = tag
-        arr["pose"][0] = query.sensor_pose()
-        arr["raw"][0] = len(query.ranges)  # (Karto tests the RAW reading count for its early return)
-        b.pool_xy = pool.ctypes.data
-        b.n_points = len(pool)
-        b.do_penalize, b.do_refine = (1 if penalty else 0), (1 if do_fine else 0)
+            if last[i] != tag or lastr[i] != r:  # (same readings, same region, same position as last call: nothing to rewrite)
+                last[i] = tag
+                lastr[i] = r
+                starts[i] = r * rp
+                counts[i] = len(pts)
+                tags[i] = tag
+            if i == nb:
+                break
+            sc = base_scans[i]
+            i += 1
+        p = query._corrected_pose
+        posec[0], posec[1], posec[2] = p.x, p.y, p.yaw
+        rawc[0] = len(query.ranges)  # (Karto tests the RAW reading count for its early return)
+        f = (1 if penalty else 0, 1 if do_fine else 0, self._pool_ptr)
+        if f != flags[0]:
+            flags[0] = f
+            b.do_penalize, b.do_refine, b.pool_xy, b.n_points = f[0], f[1], self._pool_ptr, self._pool_len
         m = self._m
         rc = m._lib.ysm_match_batch(m._h, bref, resp, None)
         if rc != _capi.YSM_OK:
             raise _ERRORS.get(rc, RuntimeError)(_capi.last_error(m._h))
-        f = arr["resf"]
-        return MatchResult(float(f[0]), f[4:13].reshape(3, 3).copy(), Pose2(f[1], f[2], f[3]))
+        l = resf.tolist()
+        return MatchResult(l[0], covv.copy(), Pose2(l[1], l[2], l[3]))
+
+    def _make_descriptor(self, nb):
+        """ysm_batch of one match against nb base scans: the query is scan 0, the base scans 1..nb."""
+        import ctypes as C
+        ns = nb + 1
+        b = _capi.YsmBatch()
+        starts, counts, raw = (C.c_int32 * ns)(), (C.c_int32 * ns)(), (C.c_int32 * ns)()
+        tags, pose = (C.c_uint64 * ns)(), (C.c_double * 3)()
+        qidx, bptr = (C.c_int32 * 1)(0), (C.c_int32 * 2)(0, nb)
+        bidx = (C.c_int32 * max(nb, 1))(*range(1, nb + 1))
+        res = np.zeros(1, dtype=_capi.RESULT_DTYPE)
+        resf = res.view(np.float64).reshape(-1)  # the 128-B record as 16 doubles
+        b.n_matches, b.n_scans = 1, ns
+        b.scan_start, b.scan_count = C.addressof(starts), C.addressof(counts)
+        b.query_scan, b.query_pose = C.addressof(qidx), C.addressof(pose)
+        b.base_ptr, b.base_idx = C.addressof(bptr), (C.addressof(bidx) if nb else None)
+        b.pool_on_device = 0
+        b.scan_tag = C.addressof(tags)
+        b.scan_raw_count = C.addressof(raw)
+        keep = (qidx, bptr, bidx, res)  # (the descriptor points into these)
+        return (b, C.byref(b), res.ctypes.data, starts, counts, tags, pose, raw, resf, resf[4:13].reshape(3, 3),
+                [None] * ns, [None] * ns, [None, keep])
 
     def _match_scan_unpooled(self, query, base_scans, penalty, do_fine):
         """Scans too many / too long for the staging pool: pack per call (no content tags)."""
