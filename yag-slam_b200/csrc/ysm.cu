@@ -920,6 +920,13 @@ static void finalize_angular(const PassHost& ph, const PassOut& po, double headi
   cov[8] = acc;
 }
 
+// Matches per wave: the batch split into the fewest waves the slots allow, of equal size -- a runt last wave
+// (12 waves of 344 and one of 39) costs nearly a whole wave's pipeline latency (r02ze: ~2 ms per step at N = 8).
+static inline int balanced_wave(int n_matches, int slots) {
+  if (slots <= 0 || n_matches <= slots) return std::max(1, slots);
+  const int waves = (n_matches + slots - 1) / slots;
+  return (n_matches + waves - 1) / waves;
+}
 static inline int n_steps(double off, double res) { return (int)(uint32_t)(h_round(off * 2.0 / res) + 1); }
 
 static void fill_inverse_rotation(TableDev& t, const double* pose) {
@@ -1722,7 +1729,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
     CK(cudaMemcpy(h->d_dpc, dp.data(), dp.size() * 8, cudaMemcpyHostToDevice));
     h->dpc_nx = nX;
   }
-  const int S = h->static_grid ? 4096 : h->slots;  // matches per wave
+  const int S = h->static_grid ? 4096 : balanced_wave(b->n_matches, h->slots);  // matches per wave
   const int nAf = n_steps(0.5 * h->prm.coarse_angle_resolution, h->prm.fine_search_angle_resolution);
 
   std::vector<MatchState> states;
@@ -2664,12 +2671,12 @@ static int match_batch_lanes(ysm_handle* h, const ysm_batch* b, ysm_result* out,
       int max_waves = 0;
       for (int l = 0; l < nl; l++) {
         const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
-        max_waves = std::max(max_waves, (hi - lo + hs[l]->slots - 1) / hs[l]->slots);
+        max_waves = std::max(max_waves, (hi - lo + hs[l]->slots - 1) / hs[l]->slots);  // (balancing keeps the count)
       }
       for (int w = 0; w < max_waves; w++) {
         for (int l = 0; l < nl; l++) {
           const int lo = (int)((long long)b->n_matches * l / nl), hi = (int)((long long)b->n_matches * (l + 1) / nl);
-          const int S = hs[l]->slots, r0 = w * S, r1 = std::min(hi - lo, (w + 1) * S);
+          const int S = balanced_wave(hi - lo, hs[l]->slots), r0 = w * S, r1 = std::min(hi - lo, (w + 1) * S);
           if (r0 >= r1) continue;
           const size_t k = plan.size();
           if (k >= h->slice_events.size()) {
