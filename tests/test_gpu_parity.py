@@ -636,7 +636,9 @@ def test_exact_candidate_lists_equal_the_searched_build(world):
     cell list per tile (YSM_DEBUG_NO_CANDLISTS), on the sequential and the loop configuration."""
     import scenarios
     from yag_slam_b200 import _capi
-    for cfg, nb, P in ((None, 10, 720), (LOOP, 10, 360), (dict(resolution=0.02, smear_deviation=0.05), 4, 360)):
+    # (the last configuration has a 33 x 33 smear kernel: the widest class k_tile_stamp_lists takes)
+    for cfg, nb, P in ((None, 10, 720), (LOOP, 10, 360), (dict(resolution=0.02, smear_deviation=0.05), 4, 360),
+                       (dict(smear_deviation=0.08), 3, 360)):
         b = scenarios.make_batch(world, 40, P, nb, 91, perturb=(0.1, 0.05), degenerate_frac=0.1)
         grids, recs = [], []
         for flags in (0, _capi.DEBUG_NO_HALF_LISTS, _capi.DEBUG_NO_CANDLISTS):

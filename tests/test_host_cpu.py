@@ -297,3 +297,106 @@ def test_relocalisation_batch_generator_is_consistent_with_the_oracle(world):
                                       b["base_ptr"], b["base_idx"], True, True, 0)).reshape(-1, 13)
     err = np.hypot(r[:, 1] - b["truth"][:, 0], r[:, 2] - b["truth"][:, 1])
     assert np.median(err) < 0.03 and (r[:, 0] > 0.5).all()
+
+
+_FAKE_LIB_C = r"""
+#include <stdint.h>
+#include <string.h>
+#include "ysm.h"
+static double g_log[1 << 20];
+static int g_n = 0, g_calls = 0;
+/* stub of the C ABI entry point: serialises what the descriptor says and answers with a fixed record */
+int ysm_match_batch(ysm_handle* h, const ysm_batch* b, ysm_result* out, void* stream) {
+  int n = 0;
+  g_log[n++] = b->n_matches; g_log[n++] = b->n_scans; g_log[n++] = b->do_penalize; g_log[n++] = b->do_refine;
+  g_log[n++] = b->pool_on_device; g_log[n++] = b->query_scan[0];
+  g_log[n++] = b->query_pose[0]; g_log[n++] = b->query_pose[1]; g_log[n++] = b->query_pose[2];
+  g_log[n++] = b->scan_raw_count[0]; g_log[n++] = b->base_ptr[0]; g_log[n++] = b->base_ptr[1];
+  for (int i = 0; i < b->base_ptr[1]; i++) g_log[n++] = b->base_idx[i];
+  for (int s = 0; s < b->n_scans; s++) {
+    g_log[n++] = b->scan_count[s]; g_log[n++] = (double)b->scan_tag[s];
+    if ((int64_t)b->scan_start[s] + b->scan_count[s] > b->n_points) return 1;
+    memcpy(g_log + n, b->pool_xy + 2 * (size_t)b->scan_start[s], 16 * (size_t)b->scan_count[s]);
+    n += 2 * b->scan_count[s];
+  }
+  g_n = n; g_calls++;
+  double* r = (double*)out;
+  r[0] = 0.75; r[1] = 1.5; r[2] = -2.5; r[3] = 0.25 + g_calls;
+  for (int i = 0; i < 9; i++) r[4 + i] = i;
+  return h ? 0 : 0;
+}
+int fake_log(double* dst, int cap) { int n = g_n < cap ? g_n : cap; memcpy(dst, g_log, 8 * (size_t)n); return g_n; }
+"""
+
+
+def test_native_binding_of_the_single_query_call_equals_the_interpreted_glue(tmp_path):
+    """csrc/ysm_pyfast.c (the native binding of Wrapper.match_scan) against a stub of the C ABI (no GPU): over a
+    sequence of calls with growing, shrinking and re-posed scan sets -- enough distinct scans to recycle the
+    staging pool's regions -- the descriptor the library sees (counts, content tags, the point readings
+    themselves, pose, raw beam count, flags) and the result objects are those of the interpreted glue."""
+    import ctypes as C
+    import subprocess
+    from yag_slam_b200 import build as ybuild
+    ybuild.build_pyfast()
+    src = tmp_path / "fake.c"
+    src.write_text(_FAKE_LIB_C)
+    so = tmp_path / "libfake.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-I", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include"), "-o", str(so), str(src)])
+    lib = C.CDLL(str(so))
+    lib.ysm_match_batch.restype = C.c_int
+    lib.ysm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fake_log.restype = C.c_int
+    lib.fake_log.argtypes = [C.c_void_p, C.c_int]
+    buf = np.zeros(1 << 20, np.float64)
+
+    def seen():
+        n = lib.fake_log(buf.ctypes.data, len(buf))
+        return buf[:n].copy()
+
+    class FakeMatcher(object):
+        _lib, _h = lib, C.c_void_p(0)
+
+        def match_pool(self, pool, starts, counts, qs, qp, bp, bi, penalty, do_fine, scan_raw_count=None):
+            from yag_slam_b200 import _capi
+            return np.zeros(1, dtype=_capi.RESULT_DTYPE)  # (the unpooled path of calls too big for the staging pool)
+
+    def wrapper(native):
+        w = karto_compat.Wrapper.__new__(karto_compat.Wrapper)
+        w._one, w._m, w._pool, w._region_used = {}, FakeMatcher(), None, [0] * karto_compat.Wrapper.POOL_REGIONS
+        w._fast = w._bind_native(lib, FakeMatcher._h) if native else None
+        assert (w._fast is not None) == native
+        return w
+
+    world, rng = synth.make_world(), np.random.default_rng(5)
+    lp = synth.laser_params(60)
+    cfg = karto_compat.LaserScanConfig(lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], "")
+    path = synth.loop_path(80)
+    scans = [karto_compat.LocalizedRangeScan(cfg, synth.cast_scan(world, p, 60, rng), karto_compat.Pose2(*p),
+                                             karto_compat.Pose2(*p), i, 0.0) for i, p in enumerate(path)]
+    wn, wp = wrapper(True), wrapper(False)
+    calls = 0
+    for step in range(70):  # a sliding window of running scans, like graph_slam.py:326; 80 scans > 48 regions
+        q = scans[step + 10]
+        base = scans[max(0, step + 10 - (step % 11)):step + 10]
+        if step % 7 == 3:  # a corrected pose makes new readings under a new content tag
+            q.corrected_pose = karto_compat.Pose2(q.corrected_pose.x + 0.01, q.corrected_pose.y, q.corrected_pose.yaw)
+        pen, fine = bool(step & 1), bool(step & 2)
+        rn = wn.match_scan(q, base, pen, fine)
+        sn = seen()
+        rp = wp.match_scan(q, base, pen, fine)
+        sp = seen()
+        calls += 2
+        assert sn.shape == sp.shape and (sn == sp).all(), step
+        assert sn[1] == len(base) + 1 and sn[9] == 60 and tuple(sn[6:9]) == q.sensor_pose()
+        assert type(rn) is karto_compat.MatchResult and type(rn.best_pose) is karto_compat.Pose2
+        assert type(rn.response) is float and rn.response == rp.response == 0.75
+        assert (rn.best_pose.x, rn.best_pose.y) == (rp.best_pose.x, rp.best_pose.y) == (1.5, -2.5)
+        assert rn.best_pose.yaw == 0.25 + calls - 1 and rp.best_pose.yaw == 0.25 + calls
+        assert rn.covariance.shape == (3, 3) and (rn.covariance == rp.covariance).all() and rn.covariance[1][2] == 5.0
+        assert rn.covariance is not wn._fast_rec  # a copy: the next call must not change an earlier result
+    first = wn.match_scan(scans[0], scans[1:3], True, True)
+    wn.match_scan(scans[3], scans[1:3], True, True)
+    assert first.best_pose.yaw == 0.25 + calls + 1
+    # declined calls (more scans than regions) take the interpreted path and still answer
+    big = wn.match_scan(scans[79], scans[:60], True, False)
+    assert type(big) is karto_compat.MatchResult

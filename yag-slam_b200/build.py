@@ -36,5 +36,22 @@ def build(force=False, verbose=False):
     return SO_PATH
 
 
+PYFAST_SO = os.path.join(_HERE, "_ysm_pyfast.so")  # native binding of Wrapper.match_scan (csrc/ysm_pyfast.c)
+
+
+def build_pyfast(force=False):
+    """CPython extension over the C ABI (host glue only: it calls ysm_match_batch, it computes nothing)."""
+    import sysconfig
+    src = os.path.join(CSRC, "ysm_pyfast.c")
+    hdr = os.path.join(_HERE, "..", "include", "ysm.h")
+    if not force and os.path.exists(PYFAST_SO) and os.path.getmtime(PYFAST_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return PYFAST_SO
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"],
+           "-o", PYFAST_SO, src]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return PYFAST_SO
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_pyfast(force=True))
