@@ -353,6 +353,9 @@ def run_ours(args, rank, world, local_rank):
             extras.update(section(lambda: bench_cfg3(local_rank, cores, not args.no_cpu), "cfg3"))
             extras.update(section(lambda: bench_cfg4(local_rank, not args.no_cpu), "cfg4"))
             extras.update(section(lambda: bench_sequential(local_rank), "cfg2_sequential"))
+            extras.update(section(lambda: bench_final_map(local_rank, not args.no_cpu), "cfg5_final_map"))
+            extras.update(section(lambda: bench_chain_finder(local_rank, not args.no_cpu), "f2_chain_finder"))
+            extras.update(section(lambda: bench_map_match(local_rank, not args.no_cpu), "f3_map_match"))
         if not args.no_latency:
             extras.update(section(lambda: latency_probe(local_rank, with_cpu=not args.no_cpu), "latency"))
 
@@ -579,6 +582,137 @@ def bench_cfg4(device, with_cpu):
         res["bit_exact"] = bool(out["response"][0] == ref[0, 0] and out["x"][0] == ref[0, 1] and out["y"][0] == ref[0, 2]
                                 and out["heading"][0] == ref[0, 3])
     return {"cfg4": res}
+
+
+def bench_final_map(device, with_cpu):
+    """The second half of BASELINE cfg 5: occupancy grid of the final map (karto create_occupancy_grid over the
+    2,000-scan 720-beam log, reference graph_slam.py:341-342) and its ray-walk (reference raytracing.py:63-92,
+    one 1,439-angle sweep from each of 1,024 free cells, the splicing caller's shape). Wall clock through the
+    public API: host scan arrays in, host rays out (29 MB D2H inside the timed call)."""
+    from yag_slam_b200 import occupancy, raytracing, synth
+    world = synth.make_world()
+    log = synth.make_scan_log(world, 2000, 720, seed=2)
+    args = (log["poses"], log["lasers"], log["ranges"], log["beam_ptr"], 0.05, 12.0)
+    occupancy.occupancy_grid_from_arrays(*args, device=device).close()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g = occupancy.occupancy_grid_from_arrays(*args, device=device)
+        ts.append(time.perf_counter() - t0)
+        if len(ts) < 3:
+            g.close()
+    img = np.array(g.image)
+    ang = np.arange(1439) * (360.0 / 1439) - 180.0
+    free = np.argwhere(img == 255)
+    starts = free[np.random.default_rng(0).choice(len(free), 1024, replace=False)][:, ::-1].astype(np.float64)
+    raytracing.raytrace_many(g, ang, starts)
+    rts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        rays = raytracing.raytrace_many(g, ang, starts)
+        rts.append(time.perf_counter() - t0)
+    dt = float(np.median(rts))
+    nrays = rays.shape[0] * rays.shape[1]
+    cells = float(rays[..., 4].astype(np.float64).sum())  # one map byte per visited cell (unit steps)
+    res = {"workload": "final map of the 2000-scan 720-beam log at 0.05 m; 1024 starts x 1439 angles ray-walk",
+           "map_wh": [int(g.width), int(g.height)], "occupancy_grid_ms": float(np.median(ts) * 1e3),
+           "beams_per_s": float(len(log["ranges"]) / np.median(ts)), "raywalk_ms": dt * 1e3, "rays_per_s": nrays / dt,
+           "mean_ray_cells": cells / nrays,
+           "roofline": {"kernel": "k_raywalk (trace_ray)", "bound": "hbm",
+                        "achieved": (cells + 20.0 * nrays) / dt / 1e9, "unit": "GB/s",
+                        "algorithmic_bytes": "1 B per visited cell + 20 B per ray written; the call is bound by the "
+                                             "dependent-load chain of each ray and the D2H of the rays, not by HBM",
+                        "timed": "wall clock of the API call, D2H of the rays included"}}
+    peak, _src = measured_peak()
+    res["roofline"]["peak"] = peak
+    res["roofline"]["frac"] = res["roofline"]["achieved"] / peak
+    g.close()
+    if with_cpu:
+        from oracle import oracle
+        ns = 16  # bounded sample: 16 sweeps of 1,439 rays, single thread (the reference's numba walk is not parallel)
+        t0 = time.perf_counter()
+        ref = oracle.raywalk_sweep_many(img, ang, starts[:ns])
+        cdt = time.perf_counter() - t0
+        res["cpu_rays_per_s"] = ns * len(ang) / cdt
+        res["cpu_cores"] = 1
+        res["raywalk_speedup"] = res["rays_per_s"] / res["cpu_rays_per_s"]
+        res["rays_bit_exact_on_sample"] = bool((rays[:ns].view(np.uint32) == ref.view(np.uint32)).all())
+        t0 = time.perf_counter()
+        og = oracle.occupancy_grid(*args)
+        res["cpu_occupancy_grid_ms"] = (time.perf_counter() - t0) * 1e3
+        res["occupancy_image_equal"] = bool(og is not None and og["image"].shape == img.shape and (og["image"] == img).all())
+    return {"cfg5_final_map": res}
+
+
+def bench_chain_finder(device, with_cpu):
+    """find_possible_loop_closure_chains (reference graph_slam.py:274-304) for 4,096 query
+    vertices of a 2,000-vertex pose graph in one call of k_chain_find; CPU = the restatement of the reference's
+    Python on a bounded sample, one core."""
+    from yag_slam_b200 import chains, synth
+    n, nq = 2000, 4096
+    rng = np.random.default_rng(3)
+    path = synth.loop_path(n, step=0.25)[:, :2] + rng.normal(0, 0.05, (n, 2))
+    seq = np.stack([np.arange(n - 1), np.arange(1, n)], axis=1)
+    loops = np.array([[i - 283, i] for i in range(300, n, 40)])
+    ptr, idx = chains.adjacency_csr(n, np.concatenate([seq, loops]))
+    queries = rng.integers(0, n, nq).astype(np.int32)
+    for _ in range(3):
+        cs = chains.find_chains_batch(path, ptr, idx, queries, 3, 10)
+    ts, kms = [], []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        cs = chains.find_chains_batch(path, ptr, idx, queries, 3, 10)
+        ts.append(time.perf_counter() - t0)
+        kms.append(cs.kernel_ms)
+    res = {"workload": "2000-vertex pose graph, 4096 query vertices, one call", "chains": int(cs.n_chains),
+           "members": int(len(cs.members)), "call_ms_p50": float(np.median(ts) * 1e3),
+           "kernel_ms_p50": float(np.median(kms)), "queries_per_s_e2e": nq / float(np.median(ts))}
+    if with_cpu:
+        from oracle import chains_oracle as co
+        ns = 64
+        t0 = time.perf_counter()
+        ref = co.find_chains_batch(path, path, ptr, idx, queries[:ns], 3, 10)
+        res["cpu_queries_per_s"] = ns / (time.perf_counter() - t0)
+        res["cpu_sample"] = "%d queries, restatement of the reference's Python, 1 core" % ns
+        res["equal_on_sample"] = bool((cs.query_chain_ptr[:ns + 1] == ref[0]).all() and
+                                      (cs.members[:len(ref[2])] == ref[2]).all())
+    return {"f2_chain_finder": res}
+
+
+def bench_map_match(device, with_cpu):
+    """4,096 720-beam queries against ONE resident correlation grid made from a map image
+    (loop-matcher configuration, coarse only); CPU = the oracle on a bounded sample, one core."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_map_cpu import map_queries  # workload generator shared with the parity tests
+    from yag_slam_b200 import synth
+    from yag_slam_b200.matcher import DEFAULTS_LOOP, MapMatcherB200
+    world = synth.make_world()
+    n = 4096
+    img, off, pool, starts, counts, qs, guess, truth = map_queries(world, n, 720, 9, 0.05, perturb=(1.0, 0.1))
+    m = MapMatcherB200(DEFAULTS_LOOP, img, off, 0, device)
+    for _ in range(3):
+        out = m.match_map(pool, starts, counts, qs, guess, False, False)
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        out = m.match_map(pool, starts, counts, qs, guess, False, False)
+        ts.append(time.perf_counter() - t0)
+    err = np.hypot(out["x"] - truth[:, 0], out["y"] - truth[:, 1])
+    res = {"workload": "4096 queries x 720 beams vs a resident map grid, loop-matcher config, coarse only",
+           "map_shape": list(img.shape), "call_ms_p50": float(np.median(ts) * 1e3),
+           "matches_per_s_e2e": n / float(np.median(ts)), "median_position_error_m": float(np.median(err))}
+    m.close()
+    if with_cpu:
+        from oracle import oracle
+        ns = 48
+        o = oracle.KartoMapOracle(DEFAULTS_LOOP, img, off, 0)
+        t0 = time.perf_counter()
+        ref = o.match_many(pool, starts, counts, qs[:ns], guess[:ns], False, False)
+        res["cpu_matches_per_s"] = ns / (time.perf_counter() - t0)
+        res["cpu_sample"] = "%d queries, 1 core" % ns
+        res["bit_exact_on_sample"] = bool(all((out[k][:ns] == ref[:, c]).all()
+                                              for k, c in (("response", 0), ("x", 1), ("y", 2), ("heading", 3))))
+    return {"f3_map_match": res}
 
 
 def bench_sequential(device):
