@@ -2747,13 +2747,17 @@ static int match_batch_lanes(ysm_handle* h, const ysm_batch* b, ysm_result* out,
       }
       if (valid && !all_sent) {
         std::sort(news.begin(), news.end(), [&](int a, int c) { return b->scan_start[a] < b->scan_start[c]; });
-        for (int sc : news) {  // merge scans that are adjacent (or overlapping) in the pool
+        // merge scans that are adjacent, overlapping or less than a quarter piece (1 MB) apart in the pool: a copy
+        // costs a stream synchronise, and a few scans sent twice cost less than a wave that waits for the whole
+        // pool (r02zm: 321-match waves of the relocalisation batch made 65+ exact ranges and fell back to that)
+        const int64_t gap = piece / 4;
+        for (int sc : news) {
           const int64_t a = b->scan_start[sc], z = a + b->scan_count[sc];
-          if (!ranges.empty() && a <= ranges.back().second) ranges.back().second = std::max(ranges.back().second, z);
+          if (!ranges.empty() && a <= ranges.back().second + gap) ranges.back().second = std::max(ranges.back().second, z);
           else ranges.push_back({a, z});
         }
       }
-      if ((!valid || ranges.size() > 64) && !all_sent) {
+      if ((!valid || ranges.size() > 256) && !all_sent) {
         ranges.assign(1, {0, b->n_points});
         all_sent = true;
       }
