@@ -405,6 +405,10 @@ def run_ours(args, rank, world, local_rank):
             # exact zero-row pruning: the algorithmic lookups above are Karto's; this many were really issued
             "lookups_issued_frac": (snap["issued"] / snap["lookups"]) if snap["pruned_launches"] and snap["lookups"] else 1.0,
             "timed_in": "separate pass of %d steps on one lane with per-kernel CUDA events" % min(args.steps, 2),
+            # share_of_step is against the single-lane wall time of the timed pass, host gaps included (the GPU idles
+            # ~ a quarter of it there; three lanes fill those gaps in the headline run). The figure to hold against the
+            # ncu launch list (profiles/*_launches.csv: sweep / (sweep + find_valid + stamp + reduce)) is this one:
+            "share_of_timed_kernels": snap["sweep_ms"] / max(snap["sweep_ms"] + snap["build_ms"] + snap["reduce_ms"], 1e-9),
             "share_of_step": snap["sweep_ms"] / max(snap["total_ms"], 1e-9),
             "build_share": snap["build_ms"] / max(snap["total_ms"], 1e-9),
             "reduce_share": snap["reduce_ms"] / max(snap["total_ms"], 1e-9),
