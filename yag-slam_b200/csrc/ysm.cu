@@ -1489,6 +1489,17 @@ static int res_match(ysm_handle* h, const ysm_batch* b, ysm_result* out, PhaseTr
               (double)(int64_t)(f1[9] - f1[8]) * 1e-3, (double)(int64_t)(f1[10] - f1[9]) * 1e-3, (double)(int64_t)(f1[11] - f1[10]) * 1e-3,
               (double)(int64_t)(f1[12] - f1[11]) * 1e-3, (double)(int64_t)(f1[8] - pf[8]) * 1e-3);
     }
+    {
+      // the CTA every other one waits for at barrier 2
+      int slow = 1;
+      for (int c = 1; c < R.G; c++)
+        if ((int64_t)(pf[(size_t)c * YSM_RES_PROF + 3] - pf[(size_t)c * YSM_RES_PROF + 2]) >
+            (int64_t)(pf[(size_t)slow * YSM_RES_PROF + 3] - pf[(size_t)slow * YSM_RES_PROF + 2])) slow = c;
+      const uint64_t* q = pf + (size_t)slow * YSM_RES_PROF;
+      fprintf(stderr, "[ysm-resident]   slowest stamp: CTA %d, %d tiles: collect %.2f, slot list %.2f, scatter %.2f, barrier %.2f, write %.2f us\n",
+              slow, (int)q[7], (double)(int64_t)(q[2] - q[1]) * 1e-3, (double)(int64_t)(q[16] - q[2]) * 1e-3,
+              (double)(int64_t)(q[17] - q[16]) * 1e-3, (double)(int64_t)(q[18] - q[17]) * 1e-3, (double)(int64_t)(q[3] - q[18]) * 1e-3);
+    }
     int tmax = 0, tsum = 0;
     for (int c = 0; c < R.G; c++) { const int t = (int)pf[(size_t)c * YSM_RES_PROF + 7]; tmax = std::max(tmax, t); tsum += t; }
     uint64_t b1min = ~0ull, b1max = 0;
@@ -2747,14 +2758,18 @@ static int match_batch_lanes(ysm_handle* h, const ysm_batch* b, ysm_result* out,
       }
       if (valid && !all_sent) {
         std::sort(news.begin(), news.end(), [&](int a, int c) { return b->scan_start[a] < b->scan_start[c]; });
-        // merge scans that are adjacent, overlapping or less than a quarter piece (1 MB) apart in the pool: a copy
-        // costs a stream synchronise, and a few scans sent twice cost less than a wave that waits for the whole
-        // pool (r02zm: 321-match waves of the relocalisation batch made 65+ exact ranges and fell back to that)
-        const int64_t gap = piece / 4;
-        for (int sc : news) {
-          const int64_t a = b->scan_start[sc], z = a + b->scan_count[sc];
-          if (!ranges.empty() && a <= ranges.back().second + gap) ranges.back().second = std::max(ranges.back().second, z);
-          else ranges.push_back({a, z});
+        // merge scans that are adjacent (or overlapping) in the pool; when that leaves many ranges -- a copy costs a
+        // stream synchronise -- also those less than a quarter piece (1 MB) apart: a few scans sent twice cost less
+        // than a wave that waits for the whole pool (r02zm: 321-match waves of the relocalisation batch made 65+
+        // exact ranges and fell back to that)
+        for (int64_t gap = 0;; gap = piece / 4) {
+          ranges.clear();
+          for (int sc : news) {
+            const int64_t a = b->scan_start[sc], z = a + b->scan_count[sc];
+            if (!ranges.empty() && a <= ranges.back().second + gap) ranges.back().second = std::max(ranges.back().second, z);
+            else ranges.push_back({a, z});
+          }
+          if (ranges.size() <= 48 || gap > 0) break;
         }
       }
       if ((!valid || ranges.size() > 256) && !all_sent) {

@@ -346,18 +346,67 @@ res_filter_scan(const GridC& g, const ResArgs& A, int s, int pstride, int n_in, 
 }
 
 // ---- phase B: the tiles this CTA owns ------------------------------------------------------------------
+// Every CTA walks all cells and keeps the (tile, cell) pairs of the tiles it owns in a small shared-memory hash
+// table. Cells arrive in scan order, so the lanes of a warp mostly name the SAME tile: one lane per (warp, tile)
+// finds the slot and bumps its counter for the whole group (MATCH.ANY), the others only store their step.
+// (r02zp, cfg-2 shape: with one atomicCAS + atomicAdd per pair the CTA owning the densest tiles -- a wall corner
+// all ten running scans see -- spent 18 us here, serialised on four shared-memory words, and 147 CTAs waited for
+// it at barrier 2.)
 __device__ __forceinline__ void
 res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int maxt, int cand, int* s_tile, int* s_cnt,
             uint32_t* s_steps, int* s_fail, const uint32_t (&c_first)[4]) {
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+  const unsigned ltmask = (1u << lane) - 1u;
   const int tnx = (g.width + YSM_TILE - 1) / YSM_TILE;
   const int h = g.half_kernel;
+  const bool two = 2 * h <= YSM_TILE;  // a stamp spans at most 2 x 2 tiles
   for (int i0 = 0; i0 < total; i0 += 4 * T) {
     uint32_t c[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int i = i0 + k * T + tid;
       c[k] = i >= total ? YSM_INVALID_CELL : (i0 == 0 ? c_first[k] : __ldcg(A.cells + i));  // (first round: preloaded)
+    }
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool cv = c[k] != YSM_INVALID_CELL;
+        const int ax = (int)(c[k] & 0xFFFFu), ay = (int)(c[k] >> 16);
+        const int tx0 = (ax - h) / YSM_TILE, tx1 = (ax + h) / YSM_TILE;
+        const int ty0 = (ay - h) / YSM_TILE, ty1 = (ay + h) / YSM_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int ty = ty0 + (q >> 1), tx = tx0 + (q & 1);
+          const int t = ty * tnx + tx;
+          const unsigned hsh = res_tile_hash(t);
+          // owner = hash scaled to [0, G) (a multiply, not a division); the slot probe starts from other bits
+          const bool mine = cv && ty <= ty1 && tx <= tx1 && (int)__umulhi(hsh, (unsigned)G) == bid;
+          if (!__any_sync(0xffffffffu, mine)) continue;  // warp-uniform (a CTA owns ~ 1 tile in 148)
+          const unsigned grp = __match_any_sync(0xffffffffu, mine ? t : -1);
+          const int leader = __ffs(grp) - 1;
+          int sl = -1, base = 0;
+          if (mine && lane == leader) {
+            for (int probe = 0; probe < maxt; probe++) {
+              const int s2 = (int)((hsh >> 9) + (unsigned)probe) & (maxt - 1);
+              const int old = atomicCAS(&s_tile[s2], -1, t);
+              if (old == -1 || old == t) {
+                sl = s2;
+                base = atomicAdd(&s_cnt[s2], __popc(grp));
+                break;
+              }
+            }
+            if (sl < 0) *s_fail = 1;
+          }
+          sl = __shfl_sync(0xffffffffu, sl, leader);
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (mine && sl >= 0) {
+            const int k2 = base + __popc(grp & ltmask);
+            if (k2 < cand) s_steps[sl * cand + k2] = stamp_step(c[k], h, g.K, g.Wt, tx * YSM_TILE, ty * YSM_TILE);
+            else *s_fail = 1;
+          }
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
