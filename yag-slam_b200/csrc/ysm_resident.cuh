@@ -371,6 +371,7 @@ res_collect(const GridC& g, const ResArgs& A, int total, int G, int bid, int max
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const bool cv = c[k] != YSM_INVALID_CELL;
+        if (!__any_sync(0xffffffffu, cv)) continue;  // (warps past the end of the cell list: nothing to look at)
         const int ax = (int)(c[k] & 0xFFFFu), ay = (int)(c[k] >> 16);
         const int tx0 = (ax - h) / YSM_TILE, tx1 = (ax + h) / YSM_TILE;
         const int ty0 = (ay - h) / YSM_TILE, ty1 = (ay + h) / YSM_TILE;
