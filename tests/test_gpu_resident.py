@@ -203,3 +203,35 @@ def test_wrapper_match_scan_uses_it(world):
     assert w.matcher.last_work()["scan_store_hits"] == 1
     rtt = w.matcher.ping(50)
     assert rtt.shape == (50,) and (rtt > 0).all()
+
+
+def test_dense_tiles_and_stamp_list_overflow(world):
+    """The tile collect of the resident kernel bumps a tile's counter once per (warp, tile): base scans whose
+    points repeat (every running scan sees the same wall from almost the same pose) put hundreds of stamps into a
+    few tiles. Up to 256 stamps per tile the kernel serves the request; past that the CTA reports the overflow at
+    barrier 2 and the general path reruns the match. Either way the result is the oracle's."""
+    import scenarios
+    from oracle.oracle import KartoOracle
+    from test_gpu_parity import _assert_parity
+    from yag_slam_b200 import synth
+    from yag_slam_b200.matcher import ScanMatcherB200, pack_pool
+    rng = np.random.default_rng(141)
+    pose = np.array(synth.loop_path(40)[7], dtype=np.float64)
+    qpose = pose + np.array([0.05, -0.03, 0.02])  # the query: taken at `pose`, localised 6 cm off
+    q = synth.scan_points(world, qpose, 720, rng, sense_pose=pose)
+    m = ScanMatcherB200(None, max_slots=2, lanes=1)
+    o = KartoOracle(None)
+    served = []
+    for nbase, jitter in ((3, 0.003), (6, 0.002), (12, 0.0)):
+        # nbase scans taken within millimetres of each other: their cells coincide or neighbour
+        base = [synth.scan_points(world, pose + np.array([jitter * k, -jitter * k, 0.0]), 720, rng) for k in range(nbase)]
+        pool, starts, counts = pack_pool([q] + base)
+        out = m.match_pool(pool, starts, counts, np.array([0], np.int32), qpose[None, :],
+                           np.array([0, nbase], np.int32), np.arange(1, nbase + 1, dtype=np.int32), True, True)
+        served.append(m.last_work()["resident_requests"])
+        r, p, cov = o.match(q, tuple(qpose), base, True, True)
+        _assert_parity(out, np.concatenate([[r], p, cov.reshape(-1)]), "dense tiles, %d coincident base scans" % nbase)
+    assert served[0] == 1, "three coincident scans fit the per-tile lists: the resident kernel must serve them"
+    # and the handle keeps serving ordinary requests after an overflow
+    _check(m, None, scenarios.make_batch(world, 3, 360, 1, 142, perturb=(0.07, 0.03)), True, True, "after dense tiles")
+    m.close()
