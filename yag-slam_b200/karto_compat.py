@@ -189,7 +189,7 @@ class Wrapper(object):
         (graph_slam.py:326) are packed -- and, through ysm_batch::scan_tag, uploaded -- once, not once per
         match. (The glue is on the critical path of a 30 us call: 7.6 -> 3 us, measured against a stub library.)"""
         fast = self._fast
-        if fast is not None:
+        if fast is not None and self._m._h is not None:  # (a closed matcher: the interpreted path reports it)
             r = fast[1](fast[0], query, base_scans, penalty, do_fine)
             if r.__class__ is MatchResult:
                 return r
