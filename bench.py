@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--max-slots", type=int, default=0,
                     help="correlation grids resident per rank (all lanes together; 0 = the library's HBM budget): "
                          "the wave size of the throughput path")
+    ap.add_argument("--grid-gb", type=float, default=0.0,
+                    help="HBM budget of the correlation-grid slots per rank in GiB (0 = the library default, 16)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no cfg 2/3/4 sections)")
@@ -241,7 +243,8 @@ def run_ours(args, rank, world, local_rank):
     lo, hi = shard_range(n, rank, world)  # strong scaling: this rank's contiguous share of the same batch
     qs, qp, bp, bi = slice_batch(b["query_scan"], b["query_pose"], b["base_ptr"], b["base_idx"], lo, hi)
     nloc = hi - lo
-    m = ScanMatcherB200(None, device=local_rank, lanes=args.lanes, max_slots=args.max_slots)
+    m = ScanMatcherB200(None, device=local_rank, lanes=args.lanes, max_slots=args.max_slots,
+                        max_grid_bytes=int(args.grid_gb * (1 << 30)))
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     dpool = torch.from_numpy(b["pool"]).to(dev)
