@@ -32,3 +32,6 @@ print("match_pool p50/p99 us", p50(lambda: m.match_pool(*args, True, True)))
 print("match_pool coarse-only p50/p99 us", p50(lambda: m.match_pool(*args, True, False)))
 if os.environ.get("YSM_TRACE"):
     m.match_pool(*args, True, True)
+    print("==== through Wrapper.match_scan (content tags: scans come from the device-resident store)", file=sys.stderr, flush=True)
+    for _ in range(3):
+        w.match_scan(q, scans, True, True)
