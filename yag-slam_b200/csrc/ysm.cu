@@ -317,7 +317,7 @@ struct ysm_handle {
   DevBuf d_pool, d_scan_start, d_scan_count, d_base_idx, d_matches, d_cells, d_ptcell, d_cellcount;
   DevBuf d_gbox, d_work, d_workcount;
   DevBuf d_tables, d_passes, d_palist, d_fineids, d_trig, d_offsets, d_sums, d_outs, d_angsums, d_blob;
-  DevBuf d_wblob, d_cellmax, d_scan_emit, d_tileflag, d_cand, d_wcand;
+  DevBuf d_wblob, d_cellmax, d_scan_emit, d_tileflag, d_cand, d_wcand, d_isums;
   PinBuf h_blob, h_wblob, h_outs, h_angsums, h_flags;
   int epoch = 0;           // completion-flag value of the current latency-kernel launch
   size_t mega_occ_smem = ~(size_t)0;  // dynamic shared memory size mega_ctas_per_sm was computed for
@@ -718,7 +718,7 @@ extern "C" void ysm_destroy(ysm_handle* h) {
                     &h->d_tables, &h->d_passes,
                     &h->d_palist, &h->d_fineids, &h->d_trig, &h->d_offsets, &h->d_sums, &h->d_outs,
                     &h->d_angsums, &h->d_blob, &h->d_wblob, &h->d_cellmax, &h->d_scan_emit,
-                    &h->d_tileflag, &h->d_cand, &h->d_wcand};
+                    &h->d_tileflag, &h->d_cand, &h->d_wcand, &h->d_isums};
   for (DevBuf* b : bufs) b->release();
   h->h_blob.release();
   h->h_wblob.release();
@@ -2459,12 +2459,18 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
         kt.mark("k_sweep_lattice");
       }
       if (timing) CK(cudaEventRecord(h->ev[3], st));
+      bool fine9_ran = false;
       if (nhostfine > 0) {
         dim3 grid((pl.max_fine_poses + 7) / 8, (unsigned)nhostfine);
-        if (!pl.fine_not9 && nhostfine >= 64 && !(h->debug & YSM_DEBUG_NO_FINE9))  // waves of 3 x 3 fine passes: a warp per (pass, angle), nine cells per offset
+        if (!pl.fine_not9 && nhostfine >= 64 && !(h->debug & YSM_DEBUG_NO_FINE9)) {
+          // waves of 3 x 3 fine passes: a warp per (pass, angle), nine cells per offset; the integer sums are kept
+          // for the reduce's angular-covariance sums
+          CK(h->d_isums.ensure(std::max<size_t>(16, pl.sums_elems * 4)));
           k_sweep_fine9<<<(unsigned)nhostfine, 32 * std::min(12, std::max(1, nAf)), 0, st>>>(
-              g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids, (double*)h->d_sums.p, d_pmax);
-        else
+              g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids, (double*)h->d_sums.p, d_pmax,
+              (unsigned*)h->d_isums.p);
+          fine9_ran = true;
+        } else
         k_sweep_points<<<grid, 256, 0, st>>>(g, h->pen, d_pass, d_fine, d_tab, (const int*)h->d_offsets.p, h->d_grids,
                                              (double*)h->d_sums.p, d_pmax);
         h->launches++;
@@ -2474,7 +2480,8 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
       if (timing) CK(cudaEventRecord(h->ev[4], st));
       k_reduce<<<ncoarse_total, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
                                              d_pmax, (const unsigned long long*)h->d_cellmax.p, d_trig, h->d_grids,
-                                             (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, 0);
+                                             (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, 0,
+                                             fine9_ran ? (const unsigned*)h->d_isums.p : nullptr);
       h->launches++;
       kt.mark("k_reduce");
       if (nspec > 0) {
@@ -2489,7 +2496,7 @@ static int match_batch_impl(ysm_handle* h, const ysm_batch* b, ysm_result* out, 
                                            h->d_grids, (double*)h->d_sums.p, d_pmax);
         k_reduce<<<nspec, 512, 0, st>>>(g, d_pass, d_tab, (const int*)h->d_offsets.p, (const double*)h->d_sums.p,
                                        d_pmax, (const unsigned long long*)h->d_cellmax.p, d_trig, h->d_grids,
-                                       (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, ncoarse_total);
+                                       (PassOut*)h->d_outs.p, (int*)h->d_angsums.p, ncoarse_total, nullptr);
         h->launches += 3;
         kt.mark("speculative fine");
       }

@@ -1801,7 +1801,8 @@ k_sweep_points(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const 
 __global__ void __launch_bounds__(384)
 k_sweep_fine9(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const int* __restrict__ pass_ids,
               const TableDev* __restrict__ tables, const int* __restrict__ offsets,
-              const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax) {
+              const uint8_t* __restrict__ grids, double* __restrict__ resp, double* __restrict__ passmax,
+              unsigned* __restrict__ isums) {
   __shared__ PassDev s_ps;
   __shared__ int s_out_off, s_ppad;
   const int pid = pass_ids[blockIdx.x];
@@ -1858,6 +1859,7 @@ k_sweep_fine9(GridC g, PenaltyC pen, const PassDev* __restrict__ passes, const i
       const int iy = lane / 3, ix = lane - iy * 3;
       const double rr = response_of(ps, pen, mine, ix, iy, a);
       resp[ps.sums_off + (iy * 3 + ix) * nA + a] = rr;
+      isums[ps.sums_off + (iy * 3 + ix) * nA + a] = mine;  // (the reduce's angular-covariance sums come from here)
       bits = (unsigned long long)__double_as_longlong(rr);
     }
     const unsigned hi = (unsigned)(bits >> 32);
@@ -1902,7 +1904,8 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* s_tmp) {
 // (one CTA of <= 512 threads reduces pass `ps`; *po may live in shared memory)
 __device__ __forceinline__ void
 reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* offsets, const double* resp, double best,
-            const unsigned long long* cellmax, const double* trig, const uint8_t* grids, PassOut* po, int* angsums) {
+            const unsigned long long* cellmax, const double* trig, const uint8_t* grids, PassOut* po, int* angsums,
+            const unsigned* isums = nullptr) {
   __shared__ int s_list[YSM_TIE_CAP];
   __shared__ int s_sorted[YSM_TIE_CAP];
   __shared__ int s_count;
@@ -2153,11 +2156,33 @@ reduce_body(const GridC& g, const PassDev& ps, const TableDev& tb, const int* of
     if (n > 0) {
       const int gx = world_to_grid1(avg_x, ps.gox, g.scale) + g.border;
       const int gy = world_to_grid1(avg_y, ps.goy, g.scale) + g.border;
+      // The best cell is one of the fine lattice's 3 x 3 cells whenever the (tie-averaged) best pose rounds onto
+      // one -- nearly always -- and then the sums asked for are exactly the integer sums k_sweep_fine9 made for
+      // that cell (same offsets, same bounds check). r02z: re-gathering them cost 78 % of the fine reduce's warp
+      // time, 7,920 scattered bytes per match fetched from DRAM again.
+      int cell = -1;
+      if (isums != nullptr && ps.nX == 3 && ps.nY == 3) {  // block-uniform
+        __shared__ int s_cell;
+        if (tid == 0) s_cell = -1;
+        __syncthreads();
+        if (tid < 9) {
+          const int iy = tid / 3, ix = tid - iy * 3;
+          const double x = -ps.offx + (double)ix * ps.resx;
+          const double y = -ps.offy + (double)iy * ps.resy;
+          const int cx = world_to_grid1(ps.cx + x, ps.gox, g.scale) + g.border;
+          const int cy = world_to_grid1(ps.cy + y, ps.goy, g.scale) + g.border;
+          if (cx == gx && cy == gy) atomicMax(&s_cell, tid);
+        }
+        __syncthreads();
+        cell = s_cell;
+        if (cell >= 0)
+          for (int a = tid; a < ps.nA; a += blockDim.x) angsums[ps.ang_off + a] = (int)isums[ps.sums_off + cell * ps.nA + a];
+      }
       const int base = gx + gy * g.stride;
       const uint8_t* grid = grids + (size_t)ps.slot * g.grid_bytes;
       const unsigned dsz = (unsigned)g.data_size;
       const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-      for (int a = warp; a < ps.nA; a += nwarps) {
+      for (int a = warp; a < (cell >= 0 ? 0 : ps.nA); a += nwarps) {
         const int* goff = offsets + tb.out_off + (size_t)a * tb.Ppad;
         unsigned sum = 0;
         for (int p0 = lane; p0 < ps.P; p0 += 384) {
@@ -2198,11 +2223,12 @@ k_reduce(GridC g, PassDev* passes, TableDev* tables,
          const int* __restrict__ offsets, const double* __restrict__ resp,
          const double* __restrict__ passmax, const unsigned long long* __restrict__ cellmax,
          const double* __restrict__ trig, const uint8_t* __restrict__ grids, PassOut* __restrict__ outs,
-         int* __restrict__ angsums, int pass_base) {
+         int* __restrict__ angsums, int pass_base, const unsigned* __restrict__ isums) {
+  // isums: integer sums of the fine passes' poses when k_sweep_fine9 made them ([sums_off + pose]); else null
   const int pid = pass_base + blockIdx.x;
   const PassDev ps = passes[pid];
   const TableDev tb = tables[ps.table];
-  reduce_body(g, ps, tb, offsets, resp, passmax[pid], cellmax, trig, grids, outs + pid, angsums);
+  reduce_body(g, ps, tb, offsets, resp, passmax[pid], cellmax, trig, grids, outs + pid, angsums, isums);
   if (ps.spec >= 0 && threadIdx.x == 0) {
     PassDev* f = passes + ps.spec;
     spec_resolve(ps, outs[pid], trig, f, tables + f->table);  // thread 0 wrote outs[pid] itself
