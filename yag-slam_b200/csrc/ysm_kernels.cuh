@@ -210,15 +210,28 @@ find_valid_body(const GridC& g, const MatchDev* matches, const int* base_idx, co
         s_next[i] = (unsigned short)j;
       }
       __syncwarp();
+      // the trigger chain 0 -> next[0] -> ... , 32 points at a time: inside a block of 32 the points the chain
+      // visits are found by pointer doubling on the lanes (five rounds of SHFL + REDUX.OR), the chain leaves the
+      // block through the next[] of its last point (r02zj: one lane chasing the pointers through shared memory
+      // was 14 % of the kernel's warp time)
       int ntrig = 0;
-      if (lane == 0) {
-        int t = 0;
-        while (t < n) {
-          s_trig[ntrig++] = (unsigned short)t;
-          t = s_next[t];
+      for (int e = 0; e < n;) {  // e: the chain's entry into the block that holds it (warp-uniform)
+        const int b0 = e & ~31;
+        const int i = b0 + lane;
+        const int nx = i < n ? (int)s_next[i] : n;  // > i
+        int J = nx < n ? nx - b0 : 64;              // in-block target lane, or >= 32: the chain leaves the block / ends
+        unsigned reach = 1u << (e - b0);
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const bool on = (reach >> lane) & 1u;
+          reach |= __reduce_or_sync(0xffffffffu, (on && J < 32) ? (1u << J) : 0u);
+          const int JJ = __shfl_sync(0xffffffffu, J, J & 31);
+          if (J < 32) J = JJ;
         }
+        if ((reach >> lane) & 1u) s_trig[ntrig + __popc(reach & ((1u << lane) - 1u))] = (unsigned short)i;
+        ntrig += __popc(reach);
+        e = __shfl_sync(0xffffffffu, nx, 31 - __clz(reach));  // where the chain's last point in this block points
       }
-      ntrig = __shfl_sync(0xffffffffu, ntrig, 0);
       __syncwarp();
       for (int k = lane; k < ntrig - 1; k += 32) {
         const int f = s_trig[k], c = s_trig[k + 1];
