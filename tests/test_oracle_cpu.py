@@ -179,3 +179,43 @@ def test_raywalk_survey_sample_values():
     assert tuple(out[0, 2:4]) == (251.0, 100.0) and out[0, 4] == 151.0
     assert tuple(out[1, 2:4]) == (100.0, 1151.0)
     assert tuple(out[2, 2:4]) == (0.0, 100.0)
+
+
+def test_blockwise_trigger_chain_equals_the_serial_walk():
+    """FindValidPoints' trigger chain (0 -> next[0] -> next[next[0]] ...) as k_find_valid finds it: 32 points at
+    a time, the visited points of a block by pointer doubling on the lanes (five rounds: reach |= OR of 1 << J over
+    the reached lanes, J = J[J]), leaving the block through next[] of its last visited point. A Python model of
+    that schedule (the kernel's shuffles / REDUX written as loops) against the serial walk on random chains."""
+    rng = np.random.default_rng(0)
+
+    def serial(nxt, n):
+        t, out = 0, []
+        while t < n:
+            out.append(t)
+            t = int(nxt[t])
+        return out
+
+    def blockwise(nxt, n):
+        out, e = [], 0
+        while e < n:
+            b0 = e & ~31
+            nx = [int(nxt[b0 + lane]) if b0 + lane < n else n for lane in range(32)]
+            J = [nx[lane] - b0 if nx[lane] < n else 64 for lane in range(32)]
+            reach = 1 << (e - b0)
+            for _ in range(5):
+                add = 0
+                for lane in range(32):
+                    if (reach >> lane) & 1 and J[lane] < 32:
+                        add |= 1 << J[lane]
+                JJ = [J[J[lane] & 31] for lane in range(32)]
+                reach |= add
+                J = [JJ[lane] if J[lane] < 32 else J[lane] for lane in range(32)]
+            out.extend(b0 + lane for lane in range(32) if (reach >> lane) & 1)
+            e = nx[reach.bit_length() - 1]
+        return out
+
+    for _ in range(400):
+        n = int(rng.integers(1, 800))
+        span = int(rng.integers(1, 40))
+        nxt = np.array([min(n, i + 1 + int(rng.integers(0, span))) for i in range(n)])
+        assert serial(nxt, n) == blockwise(nxt, n)
